@@ -1,0 +1,141 @@
+/*
+ * pcb200.h -- C ABI of libpcb200.so: the B200 (sm_100a) replacement for the native half of the
+ * MinkowskiEngine v0.4.3 operator library on PointContrast's Res16UNet34C hot path.
+ *
+ * What each entry point replaces (reference call sites are relative to /root/reference; the ME
+ * native sources are an external, un-vendored dependency pinned at README.md:24,34):
+ *
+ *   pcb_coords_* / pcb_hash_* / pcb_kernel_map*   ME CoordsManager (CPU hash map): initialize, stride, getKernelMap.
+ *        Reached implicitly from every `ME.SparseTensor(F, coords=C)` (pretrain/pointcontrast/lib/ddp_trainer.py:290-297,392-398)
+ *        and every strided / 3x3x3 convolution (pretrain/pointcontrast/model/res16unet.py:47-190).
+ *   pcb_conv_forward / pcb_conv_wgrad / pcb_weight_prep
+ *        ME ConvolutionForwardGPU / ConvolutionBackwardGPU (and the Transpose variants), bound in ME's python as
+ *        MinkowskiConvolutionFunction.apply(input_features, kernel, tensor_stride, stride, kernel_size, dilation,
+ *        region_type, region_offset, in_coords_key, out_coords_key, coords_manager) -- signature evidenced by
+ *        downstream/votenet_det_new/models/backbone/sparseconv/models/conditional_random_fields.py:135-137;
+ *        constructed at pretrain/pointcontrast/model/modules/common.py:130-138,159-167.
+ *   pcb_bn_*      MinkowskiBatchNorm == torch.nn.BatchNorm1d on .F (model/modules/common.py:21, model/resnet.py:95-97).
+ *   pcb_nce_*     PointInfoNCE (lib/ddp_trainer.py:420-426 + lib/criterion.py:15-19).
+ *   pcb_pdist_rowmin   pdist + min(1) of the hardest-contrastive loss (lib/ddp_trainer.py:182-184,215-219).
+ *   pcb_sgd_step  optim.SGD(momentum, weight_decay) step (lib/ddp_trainer.py:107-111,319,435).
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; pcb_last_error() returns the message
+ *     of the last failure on the calling thread.  Nothing throws across this boundary.
+ *   - all data pointers are CALLER-OWNED DEVICE memory (16-byte aligned); the library never allocates
+ *     device memory.  Workspaces are sized by the *_ws_bytes queries.
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous on it unless stated.
+ *   - feature matrices are fp32 row-major [rows, channels]; coordinates int32 [rows, 4] = (batch, x, y, z).
+ *   - a kernel map is a dense neighbour table  tbl[K][n_out]  (int32): tbl[k][j] = input row feeding output
+ *     row j through kernel offset k, or -1.  The ME per-offset (in,out) pair lists are exactly the
+ *     non-negative entries of row k, in ascending j.
+ */
+#ifndef PCB200_H_
+#define PCB200_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCB_OK 0
+#define PCB_ERR_CUDA 1
+#define PCB_ERR_ARG 2
+#define PCB_ERR_RANGE 3      /* coordinate outside the packable range */
+#define PCB_ERR_DUPLICATE 4  /* duplicate coordinates in a SparseTensor */
+#define PCB_MAX_KERNEL_VOLUME 27
+
+const char* pcb_last_error(void);
+/* "pcb200 <version> sm_100a" */
+const char* pcb_version(void);
+/* Number of kernels this library has launched on this process since load (bench.py's gpu_launches). */
+uint64_t pcb_launch_count(void);
+/* The library links its own (static) CUDA runtime: select the device the caller's pointers/streams live on. */
+int pcb_set_device(int device);
+
+/* ----------------------------------------------------------------------------------------------- coordinates */
+/* (b,x,y,z) -> 64-bit keys whose unsigned order is lexicographic (b,x,y,z).  b in [0,65535), |x|,|y|,|z| < 32768.
+ * `status` (device int32, caller-zeroed) receives PCB_ERR_RANGE bits on violation. */
+int pcb_coords_pack(const int32_t* coords, int64_t n, uint64_t* keys, int32_t* status, void* stream);
+int pcb_coords_unpack(const uint64_t* keys, int64_t n, int32_t* coords, void* stream);
+
+/* Open-addressing hash table key -> row.  capacity must be a power of two >= 2n.  `status` gets
+ * PCB_ERR_DUPLICATE if a key occurs twice. */
+int pcb_hash_build(const uint64_t* keys, int64_t n, uint64_t* table_keys, int32_t* table_vals,
+                   int64_t capacity, int32_t* status, void* stream);
+
+/* Stride a level: coarse = floor(c / new_ts) * new_ts, unique, rows ordered by key (canonical order).
+ * Writes out_keys[0..*n_out) and parent[i] = coarse row of fine row i.
+ * SYNCHRONISES the stream once to return *n_out on the host. */
+size_t pcb_coords_stride_ws_bytes(int64_t n);
+int pcb_coords_stride(const uint64_t* keys, int64_t n, int32_t new_ts, uint64_t* out_keys, int32_t* parent,
+                      int64_t* n_out, void* ws, size_t ws_bytes, void* stream);
+
+/* tbl[k][j] = row of (out_coord[j] + offsets[k]) in the hashed level, or -1.  offsets: HOST int32 [K][3]. */
+int pcb_kernel_map(const uint64_t* out_keys, int64_t n_out, const uint64_t* table_keys,
+                   const int32_t* table_vals, int64_t capacity, const int32_t* offsets, int K, int32_t* tbl,
+                   void* stream);
+/* counts[k] = number of non-negative entries of row k (device int64 [K]). */
+int pcb_kernel_map_count(const int32_t* tbl, int K, int64_t n_out, int64_t* counts, void* stream);
+
+/* ----------------------------------------------------------------------------------------------- convolution */
+/* fp32 W[K][Cin][Cout] -> bf16 hi/lo split planes in the same layout (w_hi, w_lo) and per-offset transposed
+ * [K][Cout][Cin] (wt_hi, wt_lo).  x ~= hi + lo with |x - hi - lo| <= 2^-17 |x|. */
+int pcb_weight_prep(const float* W, int K, int Cin, int Cout, uint16_t* w_hi, uint16_t* w_lo,
+                    uint16_t* wt_hi, uint16_t* wt_lo, void* stream);
+
+/* Y[j, :] = bias + sum_k X[tbl[kmap[k]][j], :] . W[k]      (j < n_out)
+ *   X  : [*, Cin] row stride ldx (floats);  Y: [n_out, Cout] row stride ldy.
+ *   w_hi/w_lo : bf16 split weights [K][Cin][Cout] for THIS call's (Cin, Cout) roles (use the wt_* planes and
+ *               swapped channel counts for the data gradient).   w_f32: the fp32 weights in the same layout
+ *               (used by the exact SIMT path; may be NULL when the tensor-core path applies).
+ *   kmap      : HOST int32 [K] table row used by weight k (NULL = identity).
+ *   flags     : PCB_CONV_FORCE_SIMT forces the exact fp32 SIMT kernel.
+ * Tensor-core path (bf16x3 split, fp32 accumulate) requires Cin % 32 == 0, Cout % 32 == 0, K <= 27. */
+#define PCB_CONV_FORCE_SIMT 1
+int pcb_conv_forward(const float* X, int ldx, const int32_t* tbl, int64_t tbl_stride, const int32_t* kmap, int K,
+                     int64_t n_out, int Cin, int Cout, const uint16_t* w_hi, const uint16_t* w_lo,
+                     const float* w_f32, const float* bias, float* Y, int ldy, int flags, void* stream);
+
+/* dW[k] = sum_j A[tbl[k][j], :]^T . B[j, :]       A: gathered [*, Ca] (lda), B: contiguous rows [n_out, Cb] (ldb).
+ *   transpose_out = 0: dW is [K][Ca][Cb];  1: dW is [K][Cb][Ca]. */
+size_t pcb_conv_wgrad_ws_bytes(int K, int64_t n_out, int Ca, int Cb);
+int pcb_conv_wgrad(const float* A, int lda, const float* B, int ldb, const int32_t* tbl, int64_t tbl_stride, int K,
+                   int64_t n_out, int Ca, int Cb, float* dW, int transpose_out, void* ws, size_t ws_bytes,
+                   int flags, void* stream);
+
+/* ----------------------------------------------------------------------------------------------- batch norm */
+/* Training-mode statistics over n rows: mean[C], invstd[C] = 1/sqrt(var_biased + eps); if running_* non-NULL:
+ * running = (1-momentum)*running + momentum*{mean, var_unbiased}.  ws: pcb_bn_ws_bytes(n, C). */
+size_t pcb_bn_ws_bytes(int64_t n, int C);
+int pcb_bn_stats(const float* X, int64_t n, int C, float eps, float momentum, float* mean, float* invstd,
+                 float* running_mean, float* running_var, void* ws, size_t ws_bytes, void* stream);
+/* Y = (X - mean) * invstd * gamma + beta  [+ residual] [relu].   Y may alias X. */
+int pcb_bn_apply(const float* X, int64_t n, int C, const float* mean, const float* invstd, const float* gamma,
+                 const float* beta, const float* residual, int relu, float* Y, void* stream);
+/* Backward of the affine-normalise (no relu): given dY and X, writes dX, dgamma[C], dbeta[C]. */
+int pcb_bn_backward(const float* dY, const float* X, int64_t n, int C, const float* mean, const float* invstd,
+                    const float* gamma, float* dX, float* dgamma, float* dbeta, void* ws, size_t ws_bytes,
+                    void* stream);
+
+/* ----------------------------------------------------------------------------------------------- losses */
+/* PointInfoNCE on gathered rows q,k [n, D] (D % 4 == 0, D <= 128): loss = mean_i(logsumexp_j(q_i.k_j/T) - q_i.k_i/T).
+ * Writes loss (device float), dq, dk (= d loss / d q, d k).  ws: pcb_nce_ws_bytes(n). */
+size_t pcb_nce_ws_bytes(int64_t n);
+int pcb_nce_forward_backward(const float* q, const float* k, int64_t n, int D, float inv_T, float* loss, float* dq,
+                             float* dk, void* ws, size_t ws_bytes, void* stream);
+/* minval[i] = min_j sqrt(sum_d (A[i,d]-B[j,d])^2 + 1e-7), argmin[i] = smallest such j.   packed: u64 scratch [P]. */
+int pcb_pdist_rowmin(const float* A, int64_t P, const float* B, int64_t S, int D, float* minval, int32_t* argmin,
+                     uint64_t* packed, void* stream);
+
+/* ----------------------------------------------------------------------------------------------- optimiser */
+/* torch.optim.SGD semantics on a flat buffer:  d = g*grad_scale + wd*p;  buf = first ? d : momentum*buf + d;  p -= lr*buf */
+int pcb_sgd_step(float* p, const float* g, float* buf, int64_t n, float lr, float momentum, float weight_decay,
+                 float grad_scale, int first, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCB200_H_ */

@@ -1,0 +1,48 @@
+// Shared helpers for libpcb200 (sm_100a).  Not part of the public ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <atomic>
+#include "../../include/pcb200.h"
+
+namespace pcb {
+
+void set_error(const char* fmt, ...);
+extern std::atomic<uint64_t> g_launches;
+
+inline int check_launch(const char* what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("%s: %s", what, cudaGetErrorString(e)); return PCB_ERR_CUDA; }
+  return PCB_OK;
+}
+#define PCB_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { pcb::set_error("%s: %s", #call, cudaGetErrorString(e_)); return PCB_ERR_CUDA; } } while (0)
+#define PCB_ARG(cond) do { if (!(cond)) { pcb::set_error("bad argument: %s (%s:%d)", #cond, __FILE__, __LINE__); return PCB_ERR_ARG; } } while (0)
+
+constexpr uint64_t KEY_EMPTY = 0xFFFFFFFFFFFFFFFFull;
+constexpr int COORD_BIAS = 32768;
+
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t k) {
+  k ^= k >> 33; k *= 0xff51afd7ed558ccdULL; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL; k ^= k >> 33; return k;
+}
+
+__device__ __forceinline__ int hash_lookup(const uint64_t* __restrict__ tk, const int32_t* __restrict__ tv,
+                                           uint64_t mask, uint64_t key) {
+  uint64_t slot = mix64(key) & mask;
+  while (true) {
+    uint64_t k = tk[slot];
+    if (k == key) return tv[slot];
+    if (k == KEY_EMPTY) return -1;
+    slot = (slot + 1) & mask;
+  }
+}
+
+inline int num_sms() {
+  static int n = 0;
+  if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
+  return n;
+}
+
+}  // namespace pcb

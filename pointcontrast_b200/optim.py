@@ -1,0 +1,79 @@
+"""Flat-buffer SGD: all parameters (and their gradients) are views into one contiguous fp32 buffer, so the
+optimiser step is ONE kernel launch and the DDP gradient all-reduce is one (chunkable) buffer.
+
+Semantics and state_dict layout are those of `torch.optim.SGD(momentum, weight_decay)` as used at
+`pretrain/pointcontrast/lib/ddp_trainer.py:107-111` (no dampening, no nesterov), so `ExponentialLR`
+(`:113`) and the checkpoint's `optimizer` entry (`:155-161`) work unchanged.
+"""
+import torch
+
+from ._lib import check, lib, ptr, stream
+
+
+class FlatSGD(torch.optim.Optimizer):
+    def __init__(self, params, lr, momentum=0.0, weight_decay=0.0):
+        params = list(params)
+        if any(isinstance(p, dict) for p in params):
+            raise NotImplementedError("FlatSGD supports a single parameter group")
+        super().__init__(params, dict(lr=lr, momentum=momentum, weight_decay=weight_decay, dampening=0, nesterov=False))
+        ps = self.param_groups[0]["params"]
+        dev = ps[0].device
+        if dev.type != "cuda" or any(p.device != dev or p.dtype != torch.float32 for p in ps):
+            raise RuntimeError("FlatSGD needs float32 CUDA parameters on one device")
+        self._offsets, total = [], 0
+        for p in ps:
+            self._offsets.append(total)
+            total += (p.numel() + 3) // 4 * 4           # keep every view 16-byte aligned
+        self.flat_param = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_grad = torch.zeros_like(self.flat_param)
+        self.flat_buf = torch.zeros_like(self.flat_param)
+        with torch.no_grad():
+            for p, off in zip(ps, self._offsets):
+                view = self.flat_param[off:off + p.numel()].view(p.shape)
+                view.copy_(p.data)
+                p.data = view
+                g = self.flat_grad[off:off + p.numel()].view(p.shape)
+                if p.grad is not None:
+                    g.copy_(p.grad)
+                p.grad = g
+        self._first = True
+        self.grad_scale = 1.0                            # e.g. 1/world_size after a sum all-reduce
+
+    def _views(self, flat):
+        return [flat[off:off + p.numel()].view(p.shape) for p, off in zip(self.param_groups[0]["params"], self._offsets)]
+
+    def zero_grad(self, set_to_none=False):
+        self.flat_grad.zero_()
+        for p, g in zip(self.param_groups[0]["params"], self._views(self.flat_grad)):
+            if p.grad is None or p.grad.data_ptr() != g.data_ptr():
+                p.grad = g
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        grp = self.param_groups[0]
+        ps = grp["params"]
+        for p, g in zip(ps, self._views(self.flat_grad)):     # a grad replaced behind our back is folded in
+            if p.grad is not None and p.grad.data_ptr() != g.data_ptr():
+                g.copy_(p.grad)
+                p.grad = g
+        with torch.cuda.device(self.flat_param.device):
+            check(lib.pcb_sgd_step(ptr(self.flat_param), ptr(self.flat_grad), ptr(self.flat_buf), self.flat_param.numel(),
+                                   float(grp["lr"]), float(grp["momentum"]), float(grp["weight_decay"]), float(self.grad_scale),
+                                   1 if self._first else 0, stream()))
+        if self._first:
+            for p, b in zip(ps, self._views(self.flat_buf)):
+                self.state[p]["momentum_buffer"] = b
+            self._first = False
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        ps = self.param_groups[0]["params"]
+        loaded = False
+        with torch.no_grad():
+            for p, b in zip(ps, self._views(self.flat_buf)):
+                mb = self.state.get(p, {}).get("momentum_buffer")
+                if mb is not None:
+                    b.copy_(mb)
+                    self.state[p]["momentum_buffer"] = b
+                    loaded = True
+        self._first = not loaded

@@ -1,0 +1,106 @@
+"""Whole-network parity on the GPU (BASELINE config C0): Res16UNet34C + PointInfoNCE, forward and backward.
+  * against the committed golden vectors, produced by the REFERENCE's model file running on the fp64 oracle
+    (tests/golden/make_golden.py);
+  * against the oracle run live with this repo's own model wiring (needs no reference tree).
+Tolerance: 1e-3 relative (north star): per-point features, loss, and every parameter gradient."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import loss_cpu
+from oracle import me_cpu as OR
+from tests import refload
+from tests.helpers import det_init, max_rel_err, model_backend, rel_err
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "c0_res16unet34c.npz")
+
+
+def _gpu_net(seed=0, normalize=True):
+    from pointcontrast_b200.model import load_model
+    cfg = refload.default_config()
+    cfg["net"]["normalize_feature"] = normalize
+    net = load_model("Res16UNet34C")(3, 32, cfg, D=3)
+    det_init(net, seed)
+    return net.cuda().train()
+
+
+def test_c0_against_reference_graph_golden():
+    from pointcontrast_b200 import losses, me
+    g = np.load(GOLD)
+    net = _gpu_net(0)
+    F = []
+    for v in ("0", "1"):
+        st = me.SparseTensor(torch.from_numpy(g["X" + v]), coords=torch.from_numpy(g["C" + v])).to("cuda")
+        F.append(net(st).F)
+    assert max_rel_err(F[0], torch.from_numpy(g["F0"])) < 1e-3 and max_rel_err(F[1], torch.from_numpy(g["F1"])) < 1e-3
+    loss = losses.point_nce_loss(F[0], F[1], torch.from_numpy(g["q_rows"]).cuda(), torch.from_numpy(g["k_rows"]).cuda(), 0.4)
+    assert abs(float(loss) - float(g["loss"])) / float(g["loss"]) < 1e-3
+    loss.backward()
+    names = [n for n, _ in net.named_parameters()]
+    assert names == list(g["param_names"])
+    gn = np.array([float(p.grad.norm()) for _, p in net.named_parameters()])
+    rel = np.abs(gn - g["grad_norms"]) / (g["grad_norms"] + 1e-30)
+    assert rel.max() < 1e-3, (names[int(rel.argmax())], rel.max())
+    sd = dict(net.named_parameters())
+    assert rel_err(sd["conv0p1s1.kernel"].grad, torch.from_numpy(g["g_conv0"])) < 1e-3
+    assert rel_err(sd["final.kernel"].grad, torch.from_numpy(g["g_final"])) < 1e-3
+    assert rel_err(sd["block8.1.conv2.kernel"].grad[13], torch.from_numpy(g["g_b8"])) < 1e-3
+    rm = np.array([float(m.running_mean.abs().sum()) for m in net.modules() if isinstance(m, torch.nn.BatchNorm1d)])
+    assert (np.abs(rm - g["bn_running_mean_l1"]) / (g["bn_running_mean_l1"] + 1e-30)).max() < 1e-3
+
+
+def test_small_scene_against_live_oracle_all_gradients():
+    """Own wiring on both sides; every one of the 187 parameter gradients is compared tensor by tensor."""
+    from pointcontrast_b200 import losses, me, synth
+    batch = synth.collate_pairs([synth.synth_pair(3, scale=0.12), synth.synth_pair(4, scale=0.1)])
+    net = _gpu_net(1)
+    with model_backend(OR) as mod:
+        onet = mod.Res16UNet34C(3, 32, refload.default_config(), D=3).double()
+        onet.load_state_dict({k: v.double().cpu() for k, v in net.state_dict().items()})
+        onet.train()
+        Fo = [onet(OR.SparseTensor(torch.from_numpy(batch[f"sinput{v}_F"]).double(),
+                                   coords=torch.from_numpy(batch[f"sinput{v}_C"]))).F for v in "01"]
+    F = [net(me.SparseTensor(torch.from_numpy(batch[f"sinput{v}_F"]), coords=torch.from_numpy(batch[f"sinput{v}_C"])).to("cuda")).F
+         for v in "01"]
+    assert max_rel_err(F[0], Fo[0]) < 1e-3 and max_rel_err(F[1], Fo[1]) < 1e-3
+    rng = np.random.default_rng(0)
+    pairs = batch["correspondences"]
+    nq = len(np.unique(pairs[:, 0]))
+    q, k = loss_cpu.select_positives(pairs, rng.random(nq).astype(np.float32), 4096,
+                                     rng.choice(nq, 4096, replace=False) if nq > 4096 else None)
+    lo = loss_cpu.point_nce_loss(Fo[0], Fo[1], q, k, 0.4)
+    lo.backward()
+    l = losses.point_nce_loss(F[0], F[1], q.cuda(), k.cuda(), 0.4)
+    l.backward()
+    assert abs(float(l) - float(lo)) / abs(float(lo)) < 1e-3
+    worst = max(((rel_err(p.grad, po.grad), n) for (n, p), (_, po) in zip(net.named_parameters(), onet.named_parameters())))
+    assert worst[0] < 1e-3, worst
+    for (n, b), (_, bo) in zip(net.named_buffers(), onet.named_buffers()):
+        if b.dtype.is_floating_point:
+            assert rel_err(b, bo) < 1e-3, n
+
+
+def test_eval_mode_forward_matches_oracle_semseg_shape():
+    """BASELINE config 5 shape: eval-mode BatchNorm, no L2 normalisation, 13 output classes, forward only."""
+    from pointcontrast_b200 import me, synth
+    from pointcontrast_b200.model import load_model
+    sc = synth.synth_scene(0, scale=0.3, voxel=0.05, n_raw=60_000)
+    cfg = refload.default_config(); cfg["net"]["normalize_feature"] = False
+    net = load_model("Res16UNet34C")(3, 13, cfg, D=3)
+    det_init(net, 2)
+    for m in net.modules():
+        if isinstance(m, torch.nn.BatchNorm1d):
+            m.running_mean.uniform_(-0.1, 0.1); m.running_var.uniform_(0.5, 1.5)
+    net = net.cuda().eval()
+    with model_backend(OR) as mod:
+        onet = mod.Res16UNet34C(3, 13, cfg, D=3).double()
+        onet.load_state_dict({k: v.double().cpu() for k, v in net.state_dict().items()})
+        onet.eval()
+        with torch.no_grad():
+            yo = onet(OR.SparseTensor(torch.from_numpy(sc["feats"]).double(), coords=torch.from_numpy(sc["coords"]))).F
+    with torch.no_grad():
+        y = net(me.SparseTensor(torch.from_numpy(sc["feats"]), coords=torch.from_numpy(sc["coords"])).to("cuda")).F
+    assert y.shape == (len(sc["coords"]), 13) and max_rel_err(y, yo) < 1e-3

@@ -1,0 +1,203 @@
+"""Per-operator parity on the GPU against the fp64 oracle (tolerance: 1e-3 relative, the north-star bar; the bf16x3
+tensor-core path is expected near 1e-5, the exact SIMT path near 1e-6)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import loss_cpu
+from oracle import me_cpu as OR
+from tests.helpers import max_rel_err, rand_coords, rel_err, surface_coords
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+
+
+def _pair(kind, cin, cout, bias=False):
+    from pointcontrast_b200 import me
+    def gen(M):
+        if kind == "k3hyb":
+            return M.KernelGenerator(3, 1, 1, region_type=M.RegionType.HYBRID, axis_types=[M.RegionType.HYPERCUBE] * 3, dimension=3)
+        if kind == "k3cube":
+            return M.KernelGenerator([3, 3, 3], 1, 1, region_type=M.RegionType.HYPERCUBE, dimension=3)
+        if kind == "k1":
+            return M.KernelGenerator(1, 1, 1, dimension=3)
+        return M.KernelGenerator([2, 2, 2], 2, 1, dimension=3)
+    stride = 2 if kind in ("down", "up") else 1
+    ks = {"k3hyb": 3, "k3cube": [3, 3, 3], "k1": 1}.get(kind, [2, 2, 2])
+    def make(M):
+        cls = M.MinkowskiConvolutionTranspose if kind == "up" else M.MinkowskiConvolution
+        return cls(in_channels=cin, out_channels=cout, kernel_size=ks, stride=stride, dilation=1, has_bias=bias,
+                   kernel_generator=gen(M), dimension=3)
+    return make(me), make(OR)
+
+
+CASES = [("k3cube", 3, 32, False), ("k3hyb", 32, 32, False), ("k3hyb", 32, 64, False), ("k3hyb", 128, 96, False),
+         ("k3hyb", 96, 96, False), ("k3hyb", 256, 256, False), ("k3hyb", 384, 256, False), ("k3hyb", 192, 128, False),
+         ("k1", 96, 32, True), ("k1", 128, 96, False), ("down", 32, 32, False), ("down", 128, 128, False),
+         ("up", 256, 128, False), ("up", 96, 96, False)]
+
+
+@pytest.mark.parametrize("simt", [False, True])
+@pytest.mark.parametrize("kind,cin,cout,bias", CASES)
+def test_conv_forward_backward(kind, cin, cout, bias, simt):
+    from pointcontrast_b200 import me
+    if simt and cin * cout > 128 * 96:
+        pytest.skip("exact SIMT kernel is only exercised on the smaller shapes")
+    rng = np.random.default_rng(cin * 1000 + cout)
+    n = 3000 if cin * cout <= 128 * 128 else 1200
+    coords = surface_coords(rng, n)
+    g = torch.Generator().manual_seed(cin + cout)
+    conv, oconv = _pair(kind, cin, cout, bias)
+    oconv = oconv.double()
+    with torch.no_grad():
+        oconv.kernel.copy_(conv.kernel.double())
+        if bias:
+            oconv.bias.copy_(conv.bias.double())
+    conv = conv.cuda()
+    # input level: the fine level for k3/k1/down, the strided level for up
+    st0 = me.SparseTensor(torch.zeros(len(coords), 1, device="cuda"), coords=torch.from_numpy(coords))
+    ost0 = OR.SparseTensor(torch.zeros(len(coords), 1, dtype=torch.float64), coords=torch.from_numpy(coords))
+    if kind == "up":
+        key = st0.coords_man.stride(st0.coords_key, [2, 2, 2]); okey = ost0.coords_man.stride(ost0.coords_key, [2, 2, 2])
+    else:
+        key, okey = st0.coords_key, ost0.coords_key
+    n_in = st0.coords_man.num_rows(key)
+    x = torch.randn(n_in, cin, generator=g, dtype=torch.float64)
+    xg = x.float().cuda().requires_grad_(True)
+    xo = x.clone().requires_grad_(True)
+    me.FORCE_SIMT = simt
+    try:
+        y = conv(me.SparseTensor(xg, coords_key=key, coords_manager=st0.coords_man))
+        yo = oconv(OR.SparseTensor(xo, coords_key=okey, coords_manager=ost0.coords_man))
+        assert y.F.shape == yo.F.shape and y.coords_key.ts == yo.coords_key.ts
+        dy = torch.randn(yo.F.shape, generator=g, dtype=torch.float64)
+        y.F.backward(dy.float().cuda())
+        yo.F.backward(dy)
+    finally:
+        me.FORCE_SIMT = False
+    assert max_rel_err(y.F, yo.F) < TOL and rel_err(y.F, yo.F) < TOL / 10
+    assert max_rel_err(xg.grad, xo.grad) < TOL and rel_err(xg.grad, xo.grad) < TOL / 10
+    assert max_rel_err(conv.kernel.grad, oconv.kernel.grad) < TOL and rel_err(conv.kernel.grad, oconv.kernel.grad) < TOL / 10
+    if bias:
+        assert rel_err(conv.bias.grad, oconv.bias.grad) < TOL / 10
+
+
+def test_tensor_core_and_simt_paths_agree_tightly():
+    from pointcontrast_b200 import me
+    rng = np.random.default_rng(11)
+    coords = surface_coords(rng, 6000)
+    conv, _ = _pair("k3hyb", 96, 96)
+    conv = conv.cuda()
+    st = me.SparseTensor(torch.randn(len(coords), 96, device="cuda"), coords=torch.from_numpy(coords))
+    y_tc = conv(st).F
+    me.FORCE_SIMT = True
+    try:
+        y_simt = conv(st).F
+    finally:
+        me.FORCE_SIMT = False
+    assert max_rel_err(y_tc, y_simt) < 1e-4
+
+
+@pytest.mark.parametrize("n,C", [(5000, 32), (777, 96), (1, 64), (20000, 256), (3001, 384)])
+def test_batchnorm_matches_torch(n, C):
+    from pointcontrast_b200 import me
+    g = torch.Generator().manual_seed(n + C)
+    x = torch.randn(n, C, generator=g, dtype=torch.float64) * 2 + 0.5
+    bn = me.MinkowskiBatchNorm(C, momentum=0.05).cuda()
+    ref = torch.nn.BatchNorm1d(C, momentum=0.05).double()
+    with torch.no_grad():
+        w = torch.rand(C, generator=g, dtype=torch.float64) + 0.5; b = torch.randn(C, generator=g, dtype=torch.float64)
+        bn.bn.weight.copy_(w.float()); bn.bn.bias.copy_(b.float()); ref.weight.copy_(w); ref.bias.copy_(b)
+    coords = torch.cat([torch.zeros(n, 1, dtype=torch.int32), torch.arange(n, dtype=torch.int32)[:, None].repeat(1, 3)], 1)
+    xg = x.float().cuda().requires_grad_(True)
+    xo = x.clone().requires_grad_(True)
+    if n == 1:
+        y = bn(me.SparseTensor(xg, coords=coords)).F          # torch refuses n == 1 in training; ours gives beta
+        assert torch.allclose(y.cpu().double(), b[None], atol=1e-5)
+        return
+    y = bn(me.SparseTensor(xg, coords=coords)).F
+    yo = ref(xo)
+    dy = torch.randn(n, C, generator=g, dtype=torch.float64)
+    y.backward(dy.float().cuda()); yo.backward(dy)
+    assert max_rel_err(y, yo) < 1e-4 and max_rel_err(xg.grad, xo.grad) < 1e-4
+    assert rel_err(bn.bn.weight.grad, ref.weight.grad) < 1e-4 and rel_err(bn.bn.bias.grad, ref.bias.grad) < 1e-4
+    assert rel_err(bn.bn.running_mean, ref.running_mean) < 1e-5 and rel_err(bn.bn.running_var, ref.running_var) < 1e-5
+    assert int(bn.bn.num_batches_tracked) == 1
+    bn.eval(); ref.eval()
+    assert max_rel_err(bn(me.SparseTensor(xg.detach(), coords=coords)).F, ref(x)) < 1e-4
+
+
+@pytest.mark.parametrize("n,T", [(4096, 0.4), (1000, 0.07), (37, 0.4)])
+def test_point_nce_loss_and_grads(n, T):
+    from pointcontrast_b200 import losses
+    g = torch.Generator().manual_seed(n)
+    N0, N1 = 3 * n, 3 * n + 11
+    F0 = torch.nn.functional.normalize(torch.randn(N0, 32, generator=g, dtype=torch.float64), dim=1)
+    F1 = torch.nn.functional.normalize(torch.randn(N1, 32, generator=g, dtype=torch.float64), dim=1)
+    q_rows = torch.randperm(N0, generator=g)[:n]
+    k_rows = torch.randint(0, N1, (n,), generator=g)          # keys may repeat
+    F1[k_rows] = F1[k_rows] * 0.5 + F0[q_rows] * 0.5
+    f0o, f1o = F0.clone().requires_grad_(True), F1.clone().requires_grad_(True)
+    lo = loss_cpu.point_nce_loss(f0o, f1o, q_rows, k_rows, T)
+    lo.backward()
+    f0, f1 = F0.float().cuda().requires_grad_(True), F1.float().cuda().requires_grad_(True)
+    l = losses.point_nce_loss(f0, f1, q_rows.cuda(), k_rows.cuda(), T)
+    l.backward()
+    assert abs(float(l) - float(lo)) / abs(float(lo)) < 1e-4
+    assert rel_err(f0.grad, f0o.grad) < 1e-4 and rel_err(f1.grad, f1o.grad) < 1e-4
+
+
+def test_hardest_contrastive_loss_and_grads():
+    from pointcontrast_b200 import losses
+    g = torch.Generator().manual_seed(5)
+    N0, N1, P = 6000, 5500, 20000
+    F0 = torch.nn.functional.normalize(torch.randn(N0, 32, generator=g, dtype=torch.float64), dim=1)
+    F1 = torch.nn.functional.normalize(torch.randn(N1, 32, generator=g, dtype=torch.float64), dim=1)
+    F1[:3000] = torch.nn.functional.normalize(F0[:3000] + 0.3 * torch.randn(3000, 32, generator=g, dtype=torch.float64), dim=1)
+    rng = np.random.default_rng(0)
+    i0 = np.sort(rng.integers(0, 3000, P))
+    pairs = np.unique(np.stack([i0, np.clip(i0 + rng.integers(-2, 3, P), 0, N1 - 1)], 1), axis=0)
+    sel0 = rng.choice(N0, 1024, replace=False); sel1 = rng.choice(N1, 1024, replace=False)
+    pos_sel = rng.choice(len(pairs), 4096, replace=False)
+    f0o, f1o = F0.clone().requires_grad_(True), F1.clone().requires_grad_(True)
+    po, no = loss_cpu.hardest_contrastive_loss(f0o, f1o, pairs, sel0, sel1, pos_sel)
+    (po + no).backward()
+    f0, f1 = F0.float().cuda().requires_grad_(True), F1.float().cuda().requires_grad_(True)
+    p, n_ = losses.hardest_contrastive_loss(f0, f1, torch.from_numpy(pairs).cuda(), torch.from_numpy(sel0).cuda(),
+                                            torch.from_numpy(sel1).cuda(), torch.from_numpy(pos_sel).cuda())
+    (p + n_).backward()
+    assert abs(float(p) - float(po)) < 1e-5 and abs(float(n_) - float(no)) < 1e-4
+    assert rel_err(f0.grad, f0o.grad) < 1e-3 and rel_err(f1.grad, f1o.grad) < 1e-3
+
+
+def test_pdist_rowmin_against_torch():
+    from pointcontrast_b200 import losses
+    g = torch.Generator().manual_seed(9)
+    for P, S, D in ((4096, 1024, 32), (100, 3000, 32), (1, 1, 32), (513, 65, 16)):
+        A = torch.randn(P, D, generator=g); B = torch.randn(S, D, generator=g)
+        mv, am = losses.pdist_rowmin(A.cuda(), B.cuda())
+        D2 = torch.sqrt(((A.double()[:, None] - B.double()[None]) ** 2).sum(2) + 1e-7)
+        rv, ra = D2.min(1)
+        assert torch.allclose(mv.cpu().double(), rv, rtol=1e-5, atol=1e-6)
+        picked = D2[torch.arange(P), am.cpu().long()]
+        assert torch.allclose(picked, rv, rtol=1e-5, atol=1e-6)      # argmin may differ only between numerical ties
+
+
+def test_sgd_matches_torch():
+    from pointcontrast_b200 import optim as pco
+    g = torch.Generator().manual_seed(1)
+    shapes = [(27, 32, 64), (64,), (1, 32), (7,)]
+    ps = [torch.randn(s, generator=g) for s in shapes]
+    ref = [p.clone().requires_grad_(True) for p in ps]
+    mine = [torch.nn.Parameter(p.clone().cuda()) for p in ps]
+    o_ref = torch.optim.SGD(ref, lr=0.1, momentum=0.8, weight_decay=1e-4)
+    o = pco.FlatSGD(mine, lr=0.1, momentum=0.8, weight_decay=1e-4)
+    for step in range(3):
+        for r, m in zip(ref, mine):
+            gr = torch.randn(r.shape, generator=g)
+            r.grad = gr.clone(); m.grad.copy_(gr.cuda()) if m.grad is not None else setattr(m, "grad", gr.cuda())
+        o_ref.step(); o.step()
+        for r, m in zip(ref, mine):
+            assert torch.allclose(m.detach().cpu(), r.detach(), rtol=1e-6, atol=1e-7)
+    sd = o.state_dict()
+    assert sd["param_groups"][0]["momentum"] == 0.8 and len(sd["state"]) == len(shapes)
