@@ -379,6 +379,23 @@ class SparseTensor:
 
 # ------------------------------------------------------------------------------------------------ convolution
 FORCE_SIMT = False      # tests flip this to run the exact fp32 kernels
+PROFILE = None          # bench.py sets this to a list: every conv launch is then bracketed by CUDA events
+
+
+def _prof_begin():
+    if PROFILE is None:
+        return None
+    ev = torch.cuda.Event(enable_timing=True)
+    ev.record()
+    return ev
+
+
+def _prof_end(ev0, kind, plan, K, Cin, Cout, tc):
+    if ev0 is None:
+        return
+    ev1 = torch.cuda.Event(enable_timing=True)
+    ev1.record()
+    PROFILE.append(dict(kind=kind, K=K, Cin=Cin, Cout=Cout, n_in=plan.n_in, n_out=plan.n_out, plan=plan, tc=tc, ev0=ev0, ev1=ev1))
 
 
 class _PreparedWeights:
@@ -425,8 +442,10 @@ class _SparseConvFunction(torch.autograd.Function):
             if _use_tc(Cin, Cout):
                 pl = prepared.get(kernel)
                 hi, lo = pl[0], pl[1]
+            ev = _prof_begin()
             y = _conv_forward_raw(x, plan.fwd_tbl, plan.fwd_kmap, K, plan.n_out, Cin, Cout, hi, lo,
                                   kernel.detach().contiguous(), bias.detach().reshape(-1) if bias is not None else None)
+            _prof_end(ev, "fwd", plan, K, Cin, Cout, hi is not None)
         ctx.save_for_backward(x, kernel)
         ctx.plan, ctx.prepared, ctx.has_bias = plan, prepared, bias is not None
         return y
@@ -446,7 +465,9 @@ class _SparseConvFunction(torch.autograd.Function):
                     hi, lo = pl[2], pl[3]
                 else:
                     wt = kernel.detach().transpose(1, 2).contiguous()
+                ev = _prof_begin()
                 dx = _conv_forward_raw(dy, plan.dg_tbl, plan.dg_kmap, K, plan.n_in, Cout, Cin, hi, lo, wt, None)
+                _prof_end(ev, "dgrad", plan, K, Cin, Cout, hi is not None)
             if ctx.needs_input_grad[1]:
                 dw = torch.empty_like(kernel)
                 flags = 1 if FORCE_SIMT else 0
@@ -456,8 +477,10 @@ class _SparseConvFunction(torch.autograd.Function):
                     A, B, Ca, Cb, tr, rows = dy, x, Cout, Cin, 1, plan.n_in
                 wsb = lib.pcb_conv_wgrad_ws_bytes(K, rows, Ca, Cb)
                 ws = workspace(wsb, dy.device)
+                ev = _prof_begin()
                 check(lib.pcb_conv_wgrad(ptr(A), A.stride(0), ptr(B), B.stride(0), ptr(plan.wg_tbl), plan.wg_tbl.shape[1], K,
                                          rows, Ca, Cb, ptr(dw), tr, ptr(ws), wsb, flags, stream()))
+                _prof_end(ev, "wgrad", plan, K, Cin, Cout, Ca % 32 == 0 and Cb % 32 == 0 and not FORCE_SIMT)
             if ctx.has_bias and ctx.needs_input_grad[2]:
                 db = dy.sum(0, keepdim=True)
         return dx, dw, db, None, None
