@@ -95,9 +95,12 @@ int pcb_weight_prep(const float* W, int K, int Cin, int Cout, uint16_t* w_hi, ui
  *   flags     : PCB_CONV_FORCE_SIMT forces the exact fp32 SIMT kernel.
  * Tensor-core path (bf16x3 split, fp32 accumulate) requires Cin % 32 == 0, Cout % 32 == 0, K <= 27. */
 #define PCB_CONV_FORCE_SIMT 1
+/* Small levels split the (offset, channel-chunk) loop over extra CTAs and reduce through `ws` (deterministic). */
+size_t pcb_conv_forward_ws_bytes(int K, int64_t n_out, int Cin, int Cout);
 int pcb_conv_forward(const float* X, int ldx, const int32_t* tbl, int64_t tbl_stride, const int32_t* kmap, int K,
                      int64_t n_out, int Cin, int Cout, const uint16_t* w_hi, const uint16_t* w_lo,
-                     const float* w_f32, const float* bias, float* Y, int ldy, int flags, void* stream);
+                     const float* w_f32, const float* bias, float* Y, int ldy, void* ws, size_t ws_bytes, int flags,
+                     void* stream);
 
 /* dW[k] = sum_j A[tbl[k][j], :]^T . B[j, :]       A: gathered [*, Ca] (lda), B: contiguous rows [n_out, Cb] (ldb).
  *   transpose_out = 0: dW is [K][Ca][Cb];  1: dW is [K][Cb][Ca]. */

@@ -71,6 +71,7 @@ struct ConvArgs {
   const __nv_bfloat16* w_hi; const __nv_bfloat16* w_lo;
   const float* bias;
   float* Y; int ldy;
+  float* partial;     // non-NULL: gridDim.z CTAs split the (offset, channel-chunk) loop; tile sums go to partial[z][row][Cout]
 };
 
 template <int BN>
@@ -206,16 +207,18 @@ __global__ void __launch_bounds__(NTHR, 2) conv_mma_kernel(const ConvArgs p) {
     }
   };
 
-  if (T > 0) {
+  const int it0 = (int)((int64_t)T * blockIdx.z / gridDim.z);
+  const int it1 = (int)((int64_t)T * (blockIdx.z + 1) / gridDim.z);
+  if (it1 > it0) {
     float4 v[4];
-    load_B(0, 0);
-    load_A(0, v);
+    load_B(0, it0);
+    load_A(it0, v);
     store_A(0, v);
     cp_async_wait_all();
     __syncthreads();
-    for (int it = 0; it < T; ++it) {
-      const int s = it & 1;
-      const bool more = (it + 1 < T);
+    for (int it = it0; it < it1; ++it) {
+      const int s = (it - it0) & 1;
+      const bool more = (it + 1 < it1);
       if (more) { load_B(s ^ 1, it + 1); load_A(it + 1, v); }
       compute(s, it);
       if (more) store_A(s ^ 1, v);
@@ -226,22 +229,42 @@ __global__ void __launch_bounds__(NTHR, 2) conv_mma_kernel(const ConvArgs p) {
 
   // ---- epilogue: fp32 accumulators -> Y (each quad writes 32 contiguous bytes per row)
   const int g = lane >> 2, t = lane & 3;
+  float* outp = p.partial ? p.partial + (int64_t)blockIdx.z * p.n_out * p.Cout : p.Y;
+  const int ldo = p.partial ? p.Cout : p.ldy;
+  const float* bias = p.partial ? nullptr : p.bias;
 #pragma unroll
   for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
       int col = n0 + wn * WN + nt * 8 + 2 * t;
       float b0 = 0.f, b1 = 0.f;
-      if (p.bias) { b0 = p.bias[col]; b1 = p.bias[col + 1]; }
+      if (bias) { b0 = bias[col]; b1 = bias[col + 1]; }
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         int64_t row = row0 + wm * 32 + mi * 16 + g + h * 8;
         if (row < p.n_out) {
           float2 o = make_float2(acc[mi][nt][2 * h] + b0, acc[mi][nt][2 * h + 1] + b1);
-          *reinterpret_cast<float2*>(p.Y + row * p.ldy + col) = o;
+          *reinterpret_cast<float2*>(outp + row * ldo + col) = o;
         }
       }
     }
+}
+
+// Y[row, c] = bias[c] + sum_z partial[z][row][c]   (fixed order: deterministic)
+__global__ void conv_split_reduce_kernel(const float* __restrict__ partial, int nsplit, int64_t n_out, int Cout,
+                                         const float* __restrict__ bias, float* __restrict__ Y, int ldy) {
+  const int cv = Cout / 4;
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n_out * cv) return;
+  int64_t row = i / cv;
+  int c4 = (int)(i - row * cv);
+  float4 s = bias ? reinterpret_cast<const float4*>(bias)[c4] : make_float4(0.f, 0.f, 0.f, 0.f);
+  const int64_t plane = n_out * cv;
+  for (int z = 0; z < nsplit; ++z) {
+    float4 v = __ldg(reinterpret_cast<const float4*>(partial) + z * plane + i);
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+  }
+  *reinterpret_cast<float4*>(Y + row * ldy + c4 * 4) = s;
 }
 
 // --------------------------------------------------------------------------------------------- forward (exact fp32 SIMT)
@@ -489,17 +512,46 @@ __global__ void weight_prep_kernel(const float* __restrict__ W, int K, int Cin, 
   thi[te] = h; tlo[te] = l;
 }
 
+int pick_tile(int C) {      // largest of {128, 96, 64, 32} dividing C
+  if (C % 128 == 0) return 128;
+  if (C % 96 == 0) return 96;
+  if (C % 64 == 0) return 64;
+  if (C % 32 == 0) return 32;
+  return 0;
+}
+
+// Small levels (a few hundred rows at 256 channels) would otherwise be a handful of CTAs each walking 27 x Cin/32
+// pipeline steps serially: split that loop over gridDim.z and reduce.
+int conv_splits(int K, int64_t n_out, int Cin, int Cout) {
+  int bn = pick_tile(Cout);
+  int64_t base = ((n_out + BM - 1) / BM) * (Cout / bn);
+  const int64_t one_wave = 2ll * num_sms();
+  if (base >= one_wave) return 1;
+  int64_t s = (2 * one_wave + base - 1) / base;
+  int64_t T = (int64_t)K * (Cin / BK);
+  if (s > T) s = T;
+  if (s > 64) s = 64;
+  return s < 2 ? 1 : (int)s;
+}
+
 template <int BN>
-int launch_conv(const ConvArgs& a, cudaStream_t st) {
+int launch_conv(ConvArgs a, int nsplit, float* ws, cudaStream_t st) {
   using S = ConvSmem<BN>;
   static bool attr_set = false;
   if (!attr_set) {
     PCB_CUDA(cudaFuncSetAttribute(conv_mma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     attr_set = true;
   }
-  dim3 grid((unsigned)((a.n_out + BM - 1) / BM), a.Cout / BN);
+  a.partial = nsplit > 1 ? ws : nullptr;
+  dim3 grid((unsigned)((a.n_out + BM - 1) / BM), a.Cout / BN, nsplit);
   conv_mma_kernel<BN><<<grid, NTHR, S::TOTAL, st>>>(a);
-  return check_launch("conv_mma_kernel");
+  if (int e = check_launch("conv_mma_kernel")) return e;
+  if (nsplit > 1) {
+    int64_t n4 = a.n_out * (a.Cout / 4);
+    conv_split_reduce_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(ws, nsplit, a.n_out, a.Cout, a.bias, a.Y, a.ldy);
+    return check_launch("conv_split_reduce_kernel");
+  }
+  return PCB_OK;
 }
 
 template <int TM, int TN>
@@ -513,14 +565,6 @@ int launch_wgrad(const WgradArgs& a, int splits, cudaStream_t st) {
   dim3 grid((unsigned)(a.K * (a.Ca / TM) * (a.Cb / TN)), splits);
   wgrad_mma_kernel<TM, TN><<<grid, NTHR, S::TOTAL, st>>>(a);
   return check_launch("wgrad_mma_kernel");
-}
-
-int pick_tile(int C) {      // largest of {128, 96, 64, 32} dividing C
-  if (C % 128 == 0) return 128;
-  if (C % 96 == 0) return 96;
-  if (C % 64 == 0) return 64;
-  if (C % 32 == 0) return 32;
-  return 0;
 }
 
 int wgrad_splits(int K, int64_t n_out, int Ca, int Cb, int tm, int tn) {
@@ -545,9 +589,16 @@ extern "C" int pcb_weight_prep(const float* W, int K, int Cin, int Cout, uint16_
   return check_launch("weight_prep_kernel");
 }
 
+extern "C" size_t pcb_conv_forward_ws_bytes(int K, int64_t n_out, int Cin, int Cout) {
+  if (Cin % 32 || Cout % 32 || n_out <= 0) return 256;
+  int s = conv_splits(K, n_out, Cin, Cout);
+  return s > 1 ? (size_t)s * n_out * Cout * sizeof(float) + 256 : 256;
+}
+
 extern "C" int pcb_conv_forward(const float* X, int ldx, const int32_t* tbl, int64_t tbl_stride, const int32_t* kmap, int K,
                                 int64_t n_out, int Cin, int Cout, const uint16_t* w_hi, const uint16_t* w_lo,
-                                const float* w_f32, const float* bias, float* Y, int ldy, int flags, void* stream) {
+                                const float* w_f32, const float* bias, float* Y, int ldy, void* ws, size_t ws_bytes,
+                                int flags, void* stream) {
   PCB_ARG(K >= 1 && K <= PCB_MAX_KERNEL_VOLUME && n_out >= 0 && Cin >= 1 && Cout >= 1 && ldx >= Cin && ldy >= Cout);
   if (n_out == 0) return PCB_OK;
   PCB_ARG(X && tbl && Y && tbl_stride >= n_out);
@@ -566,11 +617,17 @@ extern "C" int pcb_conv_forward(const float* X, int ldx, const int32_t* tbl, int
   ConvArgs a;
   a.X = X; a.ldx = ldx; a.tbl = tbl; a.tbl_stride = tbl_stride; a.kmap = km; a.K = K; a.n_out = n_out; a.Cin = Cin;
   a.Cout = Cout; a.w_hi = (const __nv_bfloat16*)w_hi; a.w_lo = (const __nv_bfloat16*)w_lo; a.bias = bias; a.Y = Y; a.ldy = ldy;
+  a.partial = nullptr;
+  int nsplit = conv_splits(K, n_out, Cin, Cout);
+  if (nsplit > 1) {
+    PCB_ARG(ws && ws_bytes >= (size_t)nsplit * n_out * Cout * sizeof(float));
+    PCB_ARG(ldy % 4 == 0);
+  }
   switch (pick_tile(Cout)) {
-    case 128: return launch_conv<128>(a, st);
-    case 96: return launch_conv<96>(a, st);
-    case 64: return launch_conv<64>(a, st);
-    default: return launch_conv<32>(a, st);
+    case 128: return launch_conv<128>(a, nsplit, (float*)ws, st);
+    case 96: return launch_conv<96>(a, nsplit, (float*)ws, st);
+    case 64: return launch_conv<64>(a, nsplit, (float*)ws, st);
+    default: return launch_conv<32>(a, nsplit, (float*)ws, st);
   }
 }
 

@@ -424,8 +424,10 @@ def _conv_forward_raw(x, tbl, kmap, K, n_out, Cin, Cout, planes_hi, planes_lo, w
     y = torch.empty(n_out, Cout, dtype=torch.float32, device=x.device)
     km = _c_int_array(kmap) if kmap is not None else None
     flags = 1 if FORCE_SIMT else 0
+    wsb = lib.pcb_conv_forward_ws_bytes(K, n_out, Cin, Cout)
+    ws = workspace(wsb, x.device, slot=2)
     check(lib.pcb_conv_forward(ptr(x), x.stride(0), ptr(tbl), tbl.shape[1], km, K, n_out, Cin, Cout, ptr(planes_hi),
-                               ptr(planes_lo), ptr(w_f32), ptr(bias), ptr(y), Cout, flags, stream()))
+                               ptr(planes_lo), ptr(w_f32), ptr(bias), ptr(y), Cout, ptr(ws), wsb, flags, stream()))
     return y
 
 

@@ -108,9 +108,9 @@ def test_golden_fixture_is_consistent_with_the_oracle():
     from tests.helpers import det_init, max_rel_err, model_backend
     g = np.load(os.path.join(ROOT, "tests", "golden", "c0_res16unet34c.npz"))
     with model_backend(OR) as mod:
-        net = mod.Res16UNet34C(3, 32, refload.default_config(), D=3).double()
-        det_init(net, 0)
-        net.train()
+        net = mod.Res16UNet34C(3, 32, refload.default_config(), D=3)
+        det_init(net, 0)                   # fp32 parameter values (what the GPU model holds), evaluated in fp64
+        net = net.double().train()
         torch.set_num_threads(os.cpu_count())
         with torch.no_grad():
             F0 = net(OR.SparseTensor(torch.from_numpy(g["X0"]).double(), coords=torch.from_numpy(g["C0"]))).F
