@@ -91,16 +91,19 @@ int pcb_weight_prep(const float* W, int K, int Cin, int Cout, uint16_t* w_hi, ui
  *   w_hi/w_lo : bf16 split weights [K][Cin][Cout] for THIS call's (Cin, Cout) roles (use the wt_* planes and
  *               swapped channel counts for the data gradient).   w_f32: the fp32 weights in the same layout
  *               (used by the exact SIMT path; may be NULL when the tensor-core path applies).
+ *   wk_hi/wk_lo : the same weights K-major, [K][Cout][Cin] (the transposed planes of pcb_weight_prep), used by the
+ *               tcgen05 kernel (PCB_CONV_TCGEN05); may be NULL otherwise.
  *   kmap      : HOST int32 [K] table row used by weight k (NULL = identity).
  *   flags     : PCB_CONV_FORCE_SIMT forces the exact fp32 SIMT kernel.
  * Tensor-core path (bf16x3 split, fp32 accumulate) requires Cin % 32 == 0, Cout % 32 == 0, K <= 27. */
 #define PCB_CONV_FORCE_SIMT 1
+#define PCB_CONV_TCGEN05 2     /* use the tcgen05/TMEM kernel (needs wk_hi/wk_lo = the K-major planes [K][Cout][Cin]) */
 /* Small levels split the (offset, channel-chunk) loop over extra CTAs and reduce through `ws` (deterministic). */
 size_t pcb_conv_forward_ws_bytes(int K, int64_t n_out, int Cin, int Cout);
 int pcb_conv_forward(const float* X, int ldx, const int32_t* tbl, int64_t tbl_stride, const int32_t* kmap, int K,
                      int64_t n_out, int Cin, int Cout, const uint16_t* w_hi, const uint16_t* w_lo,
-                     const float* w_f32, const float* bias, float* Y, int ldy, void* ws, size_t ws_bytes, int flags,
-                     void* stream);
+                     const uint16_t* wk_hi, const uint16_t* wk_lo, const float* w_f32, const float* bias, float* Y,
+                     int ldy, void* ws, size_t ws_bytes, int flags, void* stream);
 
 /* dW[k] = sum_j A[tbl[k][j], :]^T . B[j, :]       A: gathered [*, Ca] (lda), B: contiguous rows [n_out, Cb] (ldb).
  *   transpose_out = 0: dW is [K][Ca][Cb];  1: dW is [K][Cb][Ca]. */

@@ -589,6 +589,12 @@ extern "C" int pcb_weight_prep(const float* W, int K, int Cin, int Cout, uint16_
   return check_launch("weight_prep_kernel");
 }
 
+namespace pcb {
+int launch_conv_tcgen05(const float* X, int ldx, const int32_t* tbl, int64_t tbl_stride, const int* kmap, int K, int64_t n_out,
+                        int Cin, int Cout, const uint16_t* wk_hi, const uint16_t* wk_lo, const float* bias, float* Y, int ldy,
+                        float* partial, int nsplit, int bn, cudaStream_t st);
+}
+
 extern "C" size_t pcb_conv_forward_ws_bytes(int K, int64_t n_out, int Cin, int Cout) {
   if (Cin % 32 || Cout % 32 || n_out <= 0) return 256;
   int s = conv_splits(K, n_out, Cin, Cout);
@@ -597,8 +603,8 @@ extern "C" size_t pcb_conv_forward_ws_bytes(int K, int64_t n_out, int Cin, int C
 
 extern "C" int pcb_conv_forward(const float* X, int ldx, const int32_t* tbl, int64_t tbl_stride, const int32_t* kmap, int K,
                                 int64_t n_out, int Cin, int Cout, const uint16_t* w_hi, const uint16_t* w_lo,
-                                const float* w_f32, const float* bias, float* Y, int ldy, void* ws, size_t ws_bytes,
-                                int flags, void* stream) {
+                                const uint16_t* wk_hi, const uint16_t* wk_lo, const float* w_f32, const float* bias, float* Y,
+                                int ldy, void* ws, size_t ws_bytes, int flags, void* stream) {
   PCB_ARG(K >= 1 && K <= PCB_MAX_KERNEL_VOLUME && n_out >= 0 && Cin >= 1 && Cout >= 1 && ldx >= Cin && ldy >= Cout);
   if (n_out == 0) return PCB_OK;
   PCB_ARG(X && tbl && Y && tbl_stride >= n_out);
@@ -622,6 +628,16 @@ extern "C" int pcb_conv_forward(const float* X, int ldx, const int32_t* tbl, int
   if (nsplit > 1) {
     PCB_ARG(ws && ws_bytes >= (size_t)nsplit * n_out * Cout * sizeof(float));
     PCB_ARG(ldy % 4 == 0);
+  }
+  if ((flags & PCB_CONV_TCGEN05) && wk_hi && wk_lo && ldy % 4 == 0) {
+    if (int e = launch_conv_tcgen05(X, ldx, tbl, tbl_stride, km.v, K, n_out, Cin, Cout, wk_hi, wk_lo, bias, Y, ldy,
+                                    nsplit > 1 ? (float*)ws : nullptr, nsplit, pick_tile(Cout), st)) return e;
+    if (nsplit > 1) {
+      int64_t n4 = n_out * (Cout / 4);
+      conv_split_reduce_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>((const float*)ws, nsplit, n_out, Cout, bias, Y, ldy);
+      return check_launch("conv_split_reduce_kernel");
+    }
+    return PCB_OK;
   }
   switch (pick_tile(Cout)) {
     case 128: return launch_conv<128>(a, nsplit, (float*)ws, st);

@@ -1,0 +1,306 @@
+// Blackwell-native sparse convolution: the same output-stationary gather-GEMM as conv.cu, with the per-offset
+// Cin x Cout contraction issued as tcgen05.mma (5th-gen tensor cores), accumulators in Tensor Memory.
+//
+//   CTA = 128 output rows x BN output channels, 256 threads.
+//   producers (all 8 warps): gather the neighbour rows of the current kernel offset with 128-bit loads, split fp32 ->
+//       bf16 hi/lo, store into shared memory in the canonical UMMA K-major / no-swizzle core-matrix layout
+//       (8 rows x 16 B per core matrix); weights (pre-split bf16, K-major = [K][Cout][Cin]) arrive by cp.async;
+//   one elected thread: 2 k16-steps x 3 products (lo.hi + hi.lo + hi.hi) tcgen05.mma.cta_group::1.kind::f16,
+//       M = 128, N = BN, fp32 accumulate in TMEM; tcgen05.commit -> mbarrier releases the smem stage (3-stage ring);
+//   epilogue: tcgen05.ld 32x32b -> registers -> 64-byte contiguous stores per thread.
+//
+// Same arguments, kernel-offset skipping and split-reduce mode as conv_mma_kernel; results agree with it to fp32
+// rounding (same 3-term bf16 split, fp32 accumulation).
+#include "common.cuh"
+
+using namespace pcb;
+
+namespace pcb {
+
+namespace tc5 {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                 "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+
+// UMMA shared-memory descriptor, K-major, SWIZZLE_NONE: 8x16B core matrices; LBO = byte stride between the two
+// core matrices of one k16 step (K direction), SBO = byte stride between 8-row groups (M/N direction); version 1.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  uint32_t lo = ((saddr >> 4) & 0x3FFFu) | (((lbo >> 4) & 0x3FFFu) << 16);
+  uint32_t hi = ((sbo >> 4) & 0x3FFFu) | (1u << 14);
+  return ((uint64_t)hi << 32) | lo;
+}
+
+__device__ __forceinline__ void split4(const float4& v, uint2& hi, uint2& lo) {
+  __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y);
+  __nv_bfloat162 h1 = __floats2bfloat162_rn(v.z, v.w);
+  float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+  __nv_bfloat162 l0 = __floats2bfloat162_rn(v.x - f0.x, v.y - f0.y);
+  __nv_bfloat162 l1 = __floats2bfloat162_rn(v.z - f1.x, v.w - f1.y);
+  hi.x = *reinterpret_cast<uint32_t*>(&h0); hi.y = *reinterpret_cast<uint32_t*>(&h1);
+  lo.x = *reinterpret_cast<uint32_t*>(&l0); lo.y = *reinterpret_cast<uint32_t*>(&l1);
+}
+
+constexpr int BM = 128, BK = 32, NTHR = 256, NS = 3;
+constexpr int A_SBO = 128;
+constexpr int A_LBO = (BM / 8) * 128 + 64;          // +64: the 4 k-chunks of a row land in different bank groups
+constexpr int A_PLANE = (BK / 8) * A_LBO;
+
+struct Args {
+  const float* X; int ldx;
+  const int32_t* tbl; int64_t tbl_stride;
+  int kmap[PCB_MAX_KERNEL_VOLUME]; int K;
+  int64_t n_out; int Cin; int Cout;
+  const __nv_bfloat16* wk_hi; const __nv_bfloat16* wk_lo;      // K-major weights: [K][Cout][Cin]
+  const float* bias;
+  float* Y; int ldy;
+  float* partial;
+};
+
+template <int BN>
+struct Smem {
+  static constexpr int B_SBO = 128;
+  static constexpr int B_LBO = (BN / 8) * 128 + 16;
+  static constexpr int B_PLANE = (BK / 8) * B_LBO;
+  static constexpr int STAGE = 2 * A_PLANE + 2 * B_PLANE;
+  static constexpr int IDX_OFF = NS * STAGE;
+  static constexpr int META_OFF = IDX_OFF + PCB_MAX_KERNEL_VOLUME * BM * 4;     // flags[32] klist[32] nk, tmem ptr
+  static constexpr int BAR_OFF = META_OFF + 72 * 4;
+  static constexpr int TOTAL = BAR_OFF + (NS + 1) * 8 + 16;
+  static constexpr int TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
+};
+
+template <int BN>
+__global__ void __launch_bounds__(NTHR, 2) conv_tcgen05_kernel(const Args p) {
+  using S = Smem<BN>;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t row0 = (int64_t)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  int* s_idx = reinterpret_cast<int*>(smem + S::IDX_OFF);
+  int* s_flag = reinterpret_cast<int*>(smem + S::META_OFF);
+  int* s_klist = s_flag + 32;
+  int* s_nk = s_klist + 32;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_nk + 1);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bar_base = smem_base + S::BAR_OFF;          // NS "stage free" barriers + 1 "accumulator done"
+
+  if (tid == 0) {
+    for (int i = 0; i <= NS; ++i) mbar_init(bar_base + 8 * i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 0) {      // one warp allocates the accumulator columns
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(s_tmem)), "r"(S::TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
+  }
+  for (int e = tid; e < p.K * BM; e += NTHR) {
+    int k = e / BM, r = e - k * BM;
+    int64_t row = row0 + r;
+    int v = -1;
+    if (row < p.n_out) v = p.tbl[(int64_t)p.kmap[k] * p.tbl_stride + row];
+    s_idx[e] = v;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = *s_tmem;
+  for (int k = warp; k < p.K; k += NTHR / 32) {
+    unsigned any = 0;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) any |= __ballot_sync(0xffffffffu, s_idx[k * BM + s * 32 + lane] >= 0);
+    if (lane == 0) s_flag[k] = any ? 1 : 0;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int nk = 0;
+    for (int k = 0; k < p.K; ++k) if (s_flag[k]) s_klist[nk++] = k;
+    *s_nk = nk;
+  }
+  __syncthreads();
+  const int nk = *s_nk;
+  const int nkc = p.Cin / BK;
+  const int T = nk * nkc;
+  const int it0 = (int)((int64_t)T * blockIdx.z / gridDim.z);
+  const int it1 = (int)((int64_t)T * (blockIdx.z + 1) / gridDim.z);
+
+  const int a_chunk = tid & 7, a_row = tid >> 3;
+  constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+  auto load_B = [&](int stage, int it) {
+    const int k = s_klist[it / nkc], kc = it % nkc;
+    constexpr int PER_PLANE = BN * (BK / 8);             // 16-byte chunks: BN rows x 4 k-chunks
+    for (int c = tid; c < 2 * PER_PLANE; c += NTHR) {
+      int plane = c / PER_PLANE, rem = c - plane * PER_PLANE;
+      int n = rem >> 2, k8 = rem & 3;
+      const __nv_bfloat16* src = (plane ? p.wk_lo : p.wk_hi) + ((int64_t)k * p.Cout + n0 + n) * p.Cin + kc * BK + k8 * 8;
+      uint32_t dst = smem_base + stage * S::STAGE + 2 * A_PLANE + plane * S::B_PLANE + k8 * S::B_LBO + (n >> 3) * S::B_SBO +
+                     (n & 7) * 16;
+      cp_async16(dst, src);
+    }
+    cp_async_commit();
+  };
+  auto load_A = [&](int it, float4 (&v)[4]) {
+    const int k = s_klist[it / nkc], kc = it % nkc;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int idx = s_idx[k * BM + a_row + 32 * i];
+      if (idx >= 0) v[i] = __ldg(reinterpret_cast<const float4*>(p.X + (int64_t)idx * p.ldx + kc * BK) + a_chunk);
+      else v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  auto store_A = [&](int stage, const float4 (&v)[4]) {
+    unsigned char* base = smem + stage * S::STAGE + (a_chunk >> 1) * A_LBO + (a_chunk & 1) * 8;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = a_row + 32 * i;
+      uint2 hi, lo;
+      split4(v[i], hi, lo);
+      const int off = (r >> 3) * A_SBO + (r & 7) * 16;
+      *reinterpret_cast<uint2*>(base + off) = hi;
+      *reinterpret_cast<uint2*>(base + A_PLANE + off) = lo;
+    }
+  };
+
+  if (it1 > it0) {
+    float4 v[4];
+    load_B(0, it0);
+    load_A(it0, v);
+    for (int it = it0; it < it1; ++it) {
+      const int i = it - it0;
+      const int s = i % NS;
+      const bool more = it + 1 < it1;
+      store_A(s, v);
+      if (more) {
+        const int s1 = (i + 1) % NS, u1 = (i + 1) / NS;
+        if (u1 >= 1) mbar_wait(bar_base + 8 * s1, (u1 - 1) & 1);     // the MMAs that read stage s1 have retired
+        load_B(s1, it + 1);
+        load_A(it + 1, v);
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
+      fence_proxy_async();              // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        const uint32_t a_hi = smem_base + s * S::STAGE, a_lo = a_hi + A_PLANE;
+        const uint32_t b_hi = a_hi + 2 * A_PLANE, b_lo = b_hi + S::B_PLANE;
+#pragma unroll
+        for (int j = 0; j < BK / 16; ++j) {
+          const uint64_t dah = make_desc(a_hi + j * 2 * A_LBO, A_LBO, A_SBO), dal = make_desc(a_lo + j * 2 * A_LBO, A_LBO, A_SBO);
+          const uint64_t dbh = make_desc(b_hi + j * 2 * S::B_LBO, S::B_LBO, S::B_SBO);
+          const uint64_t dbl = make_desc(b_lo + j * 2 * S::B_LBO, S::B_LBO, S::B_SBO);
+          tc_mma(tmem_acc, dal, dbh, IDESC, (i > 0 || j > 0) ? 1u : 0u);
+          tc_mma(tmem_acc, dah, dbl, IDESC, 1u);
+          tc_mma(tmem_acc, dah, dbh, IDESC, 1u);
+        }
+        tc_commit(bar_base + 8 * s);
+        if (!more) tc_commit(bar_base + 8 * NS);
+      }
+    }
+    mbar_wait(bar_base + 8 * NS, 0);
+    tc_fence_after();
+  }
+
+  // ---- epilogue: warp w owns TMEM lanes 32*(w%4)..+31 (= tile rows) and column half w/4
+  float* outp = p.partial ? p.partial + (int64_t)blockIdx.z * p.n_out * p.Cout : p.Y;
+  const int ldo = p.partial ? p.Cout : p.ldy;
+  const float* bias = p.partial ? nullptr : p.bias;
+  const int q = warp & 3, half = warp >> 2;
+  const int64_t row = row0 + q * 32 + lane;
+  constexpr int HALF = BN / 2;
+#pragma unroll
+  for (int c0 = 0; c0 < HALF; c0 += 16) {
+    const int col = half * HALF + c0;
+    uint32_t r[16];
+    if (it1 > it0) {
+      tc_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)col, r);
+      tc_ld_wait();
+    } else {
+#pragma unroll
+      for (int e = 0; e < 16; ++e) r[e] = 0u;
+    }
+    if (row < p.n_out) {
+      float* dst = outp + row * ldo + n0 + col;
+#pragma unroll
+      for (int e = 0; e < 16; e += 4) {
+        float4 o = make_float4(__uint_as_float(r[e]), __uint_as_float(r[e + 1]), __uint_as_float(r[e + 2]), __uint_as_float(r[e + 3]));
+        if (bias) { o.x += bias[n0 + col + e]; o.y += bias[n0 + col + e + 1]; o.z += bias[n0 + col + e + 2]; o.w += bias[n0 + col + e + 3]; }
+        *reinterpret_cast<float4*>(dst + e) = o;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_acc), "r"(S::TMEM_COLS));
+  }
+}
+
+template <int BN>
+int launch(const Args& a, int nsplit, cudaStream_t st) {
+  using S = Smem<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PCB_CUDA(cudaFuncSetAttribute(conv_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)((a.n_out + BM - 1) / BM), a.Cout / BN, nsplit);
+  conv_tcgen05_kernel<BN><<<grid, NTHR, S::TOTAL, st>>>(a);
+  return check_launch("conv_tcgen05_kernel");
+}
+
+}  // namespace tc5
+
+// Called by pcb_conv_forward (conv.cu).  wk_*: K-major split weights [K][Cout][Cin] for this call's roles.
+int launch_conv_tcgen05(const float* X, int ldx, const int32_t* tbl, int64_t tbl_stride, const int* kmap, int K, int64_t n_out,
+                        int Cin, int Cout, const uint16_t* wk_hi, const uint16_t* wk_lo, const float* bias, float* Y, int ldy,
+                        float* partial, int nsplit, int bn, cudaStream_t st) {
+  tc5::Args a;
+  a.X = X; a.ldx = ldx; a.tbl = tbl; a.tbl_stride = tbl_stride; a.K = K; a.n_out = n_out; a.Cin = Cin; a.Cout = Cout;
+  for (int k = 0; k < K; ++k) a.kmap[k] = kmap[k];
+  a.wk_hi = (const __nv_bfloat16*)wk_hi; a.wk_lo = (const __nv_bfloat16*)wk_lo; a.bias = bias; a.Y = Y; a.ldy = ldy;
+  a.partial = partial;
+  switch (bn) {
+    case 128: return tc5::launch<128>(a, nsplit, st);
+    case 96: return tc5::launch<96>(a, nsplit, st);
+    case 64: return tc5::launch<64>(a, nsplit, st);
+    default: return tc5::launch<32>(a, nsplit, st);
+  }
+}
+
+}  // namespace pcb

@@ -378,7 +378,10 @@ class SparseTensor:
 
 
 # ------------------------------------------------------------------------------------------------ convolution
+import os as _os
+
 FORCE_SIMT = False      # tests flip this to run the exact fp32 kernels
+CONV_IMPL = _os.environ.get("PCB_CONV_IMPL", "tcgen05")     # "mma" (mma.sync) | "tcgen05" (TMEM accumulators)
 PROFILE = None          # bench.py sets this to a list: every conv launch is then bracketed by CUDA events
 
 
@@ -420,14 +423,15 @@ def _use_tc(Cin, Cout):
     return (not FORCE_SIMT) and Cin % 32 == 0 and Cout % 32 == 0
 
 
-def _conv_forward_raw(x, tbl, kmap, K, n_out, Cin, Cout, planes_hi, planes_lo, w_f32, bias):
+def _conv_forward_raw(x, tbl, kmap, K, n_out, Cin, Cout, planes_hi, planes_lo, w_f32, bias, kmajor_hi=None, kmajor_lo=None):
     y = torch.empty(n_out, Cout, dtype=torch.float32, device=x.device)
     km = _c_int_array(kmap) if kmap is not None else None
-    flags = 1 if FORCE_SIMT else 0
+    flags = (1 if FORCE_SIMT else 0) | (2 if CONV_IMPL == "tcgen05" else 0)
     wsb = lib.pcb_conv_forward_ws_bytes(K, n_out, Cin, Cout)
     ws = workspace(wsb, x.device, slot=2)
     check(lib.pcb_conv_forward(ptr(x), x.stride(0), ptr(tbl), tbl.shape[1], km, K, n_out, Cin, Cout, ptr(planes_hi),
-                               ptr(planes_lo), ptr(w_f32), ptr(bias), ptr(y), Cout, ptr(ws), wsb, flags, stream()))
+                               ptr(planes_lo), ptr(kmajor_hi), ptr(kmajor_lo), ptr(w_f32), ptr(bias), ptr(y), Cout, ptr(ws), wsb,
+                               flags, stream()))
     return y
 
 
@@ -440,13 +444,13 @@ class _SparseConvFunction(torch.autograd.Function):
             raise _lib.PcbError("features must be float32")
         K, Cin, Cout = kernel.shape
         with torch.cuda.device(x.device):
-            hi = lo = None
+            hi = lo = khi = klo = None
             if _use_tc(Cin, Cout):
                 pl = prepared.get(kernel)
-                hi, lo = pl[0], pl[1]
+                hi, lo, khi, klo = pl[0], pl[1], pl[2], pl[3]
             ev = _prof_begin()
             y = _conv_forward_raw(x, plan.fwd_tbl, plan.fwd_kmap, K, plan.n_out, Cin, Cout, hi, lo,
-                                  kernel.detach().contiguous(), bias.detach().reshape(-1) if bias is not None else None)
+                                  kernel.detach().contiguous(), bias.detach().reshape(-1) if bias is not None else None, khi, klo)
             _prof_end(ev, "fwd", plan, K, Cin, Cout, hi is not None)
         ctx.save_for_backward(x, kernel)
         ctx.plan, ctx.prepared, ctx.has_bias = plan, prepared, bias is not None
@@ -461,14 +465,14 @@ class _SparseConvFunction(torch.autograd.Function):
         dx = dw = db = None
         with torch.cuda.device(dy.device):
             if ctx.needs_input_grad[0]:
-                hi = lo = wt = None
+                hi = lo = khi = klo = wt = None
                 if _use_tc(Cout, Cin):
                     pl = ctx.prepared.get(kernel)
-                    hi, lo = pl[2], pl[3]
+                    hi, lo, khi, klo = pl[2], pl[3], pl[0], pl[1]
                 else:
                     wt = kernel.detach().transpose(1, 2).contiguous()
                 ev = _prof_begin()
-                dx = _conv_forward_raw(dy, plan.dg_tbl, plan.dg_kmap, K, plan.n_in, Cout, Cin, hi, lo, wt, None)
+                dx = _conv_forward_raw(dy, plan.dg_tbl, plan.dg_kmap, K, plan.n_in, Cout, Cin, hi, lo, wt, None, khi, klo)
                 _prof_end(ev, "dgrad", plan, K, Cin, Cout, hi is not None)
             if ctx.needs_input_grad[1]:
                 dw = torch.empty_like(kernel)

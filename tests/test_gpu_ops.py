@@ -82,6 +82,48 @@ def test_conv_forward_backward(kind, cin, cout, bias, simt):
         assert rel_err(conv.bias.grad, oconv.bias.grad) < TOL / 10
 
 
+@pytest.mark.parametrize("kind,cin,cout,bias", [c for c in CASES if c[1] % 32 == 0])
+def test_tcgen05_conv_forward_backward(kind, cin, cout, bias):
+    """The Blackwell-native (tcgen05 / TMEM) kernel: same parity bar, and near-exact agreement with the mma.sync kernel."""
+    from pointcontrast_b200 import me
+    rng = np.random.default_rng(cin * 7 + cout)
+    n = 3000 if cin * cout <= 128 * 128 else 1200
+    coords = surface_coords(rng, n)
+    g = torch.Generator().manual_seed(cin + cout + 1)
+    conv, oconv = _pair(kind, cin, cout, bias)
+    oconv = oconv.double()
+    with torch.no_grad():
+        oconv.kernel.copy_(conv.kernel.double())
+        if bias:
+            oconv.bias.copy_(conv.bias.double())
+    conv = conv.cuda()
+    st0 = me.SparseTensor(torch.zeros(len(coords), 1, device="cuda"), coords=torch.from_numpy(coords))
+    ost0 = OR.SparseTensor(torch.zeros(len(coords), 1, dtype=torch.float64), coords=torch.from_numpy(coords))
+    if kind == "up":
+        key = st0.coords_man.stride(st0.coords_key, [2, 2, 2]); okey = ost0.coords_man.stride(ost0.coords_key, [2, 2, 2])
+    else:
+        key, okey = st0.coords_key, ost0.coords_key
+    x = torch.randn(st0.coords_man.num_rows(key), cin, generator=g, dtype=torch.float64)
+    xo = x.clone().requires_grad_(True)
+    yo = oconv(OR.SparseTensor(xo, coords_key=okey, coords_manager=ost0.coords_man))
+    dy = torch.randn(yo.F.shape, generator=g, dtype=torch.float64)
+    yo.F.backward(dy)
+    res = {}
+    default_impl = me.CONV_IMPL
+    for impl in ("mma", "tcgen05"):
+        me.CONV_IMPL = impl
+        try:
+            xg = x.float().cuda().requires_grad_(True)
+            y = conv(me.SparseTensor(xg, coords_key=key, coords_manager=st0.coords_man))
+            y.F.backward(dy.float().cuda())
+            res[impl] = (y.F.detach().clone(), xg.grad.clone())
+        finally:
+            me.CONV_IMPL = default_impl
+    y5, dx5 = res["tcgen05"]
+    assert max_rel_err(y5, yo.F) < TOL and max_rel_err(dx5, xo.grad) < TOL
+    assert max_rel_err(y5, res["mma"][0]) < 2e-5 and max_rel_err(dx5, res["mma"][1]) < 2e-5
+
+
 def test_tensor_core_and_simt_paths_agree_tightly():
     from pointcontrast_b200 import me
     rng = np.random.default_rng(11)
