@@ -98,6 +98,7 @@ int pcb_weight_prep(const float* W, int K, int Cin, int Cout, uint16_t* w_hi, ui
  * Tensor-core path (bf16x3 split, fp32 accumulate) requires Cin % 32 == 0, Cout % 32 == 0, K <= 27. */
 #define PCB_CONV_FORCE_SIMT 1
 #define PCB_CONV_TCGEN05 2     /* use the tcgen05/TMEM kernel (needs wk_hi/wk_lo = the K-major planes [K][Cout][Cin]) */
+#define PCB_CONV_ACCUMULATE 4  /* Y += result (pcb_conv_forward, tcgen05 path) / dW += result (pcb_conv_wgrad) */
 /* Small levels split the (offset, channel-chunk) loop over extra CTAs and reduce through `ws` (deterministic). */
 size_t pcb_conv_forward_ws_bytes(int K, int64_t n_out, int Cin, int Cout);
 int pcb_conv_forward(const float* X, int ldx, const int32_t* tbl, int64_t tbl_stride, const int32_t* kmap, int K,
@@ -125,6 +126,21 @@ int pcb_bn_apply(const float* X, int64_t n, int C, const float* mean, const floa
 int pcb_bn_backward(const float* dY, const float* X, int64_t n, int C, const float* mean, const float* invstd,
                     const float* gamma, float* dX, float* dgamma, float* dbeta, void* ws, size_t ws_bytes,
                     void* stream);
+
+/* Strided / fused variants used by the fused network executor (pointcontrast_b200/fused.py).  All ld* are row strides
+ * in floats (>= C, multiples of 4), so inputs/outputs may be column slices of wider (concatenated) buffers.
+ *   pcb_bn_apply2   : Y = [relu]( (X-mean)*invstd*gamma+beta [+ residual] )
+ *   pcb_bn_backward2: g = dY * (relu_out > 0) if relu_out else dY;   dgamma/dbeta (+)= sum(g*xhat) / sum(g);
+ *                     dX = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat));   gout (=|+=) g  (gout_mode 0 none, 1 write, 2 add)
+ *                     -- gout is the gradient of the residual input of the forward unit; it may alias dY. */
+int pcb_bn_stats2(const float* X, int ldx, int64_t n, int C, float eps, float momentum, float* mean, float* invstd,
+                  float* running_mean, float* running_var, void* ws, size_t ws_bytes, void* stream);
+int pcb_bn_apply2(const float* X, int ldx, int64_t n, int C, const float* mean, const float* invstd, const float* gamma,
+                  const float* beta, const float* residual, int ldr, int relu, float* Y, int ldy, void* stream);
+int pcb_bn_backward2(const float* dY, int lddy, const float* X, int ldx, const float* relu_out, int ldm, int64_t n, int C,
+                     const float* mean, const float* invstd, const float* gamma, float* dX, int lddx, float* dgamma,
+                     float* dbeta, int accumulate_param_grads, float* gout, int ldg, int gout_mode, void* ws,
+                     size_t ws_bytes, void* stream);
 
 /* ----------------------------------------------------------------------------------------------- losses */
 /* PointInfoNCE on gathered rows q,k [n, D] (D % 4 == 0, D <= 128): loss = mean_i(logsumexp_j(q_i.k_j/T) - q_i.k_i/T).

@@ -12,8 +12,10 @@ constexpr int ROWS_PER_CHUNK = 512;
 
 // partial[chunk][0][C] = sum(a), partial[chunk][1][C] = sum(a*b)    (b == a for the forward statistics)
 // block: (C/4) channel-vectors x RP row lanes; grid: one CTA per chunk of rows.
+// Strides: lda / ldb / ldm (floats).  Mask (backward only): a is zeroed where mask <= 0 (ReLU folded into the BN backward).
 template <bool TWO_INPUTS>
-__global__ void colsum_kernel(const float* __restrict__ A, const float* __restrict__ Bm, int64_t n, int C,
+__global__ void colsum_kernel(const float* __restrict__ A, int lda, const float* __restrict__ Bm, int ldb,
+                              const float* __restrict__ Mask, int ldm, int64_t n, int C,
                               const float* __restrict__ mean, const float* __restrict__ invstd, float* __restrict__ partial) {
   extern __shared__ float sm[];      // [RP][2][C]
   const int cv = C / 4;
@@ -27,9 +29,13 @@ __global__ void colsum_kernel(const float* __restrict__ A, const float* __restri
   if (TWO_INPUTS && rl < rp) { mu = reinterpret_cast<const float4*>(mean)[c4]; is = reinterpret_cast<const float4*>(invstd)[c4]; }
   if (rl < rp) {
     for (int64_t r = r0 + rl; r < r1; r += rp) {
-      float4 a = __ldg(reinterpret_cast<const float4*>(A + r * C) + c4);
+      float4 a = __ldg(reinterpret_cast<const float4*>(A + r * lda) + c4);
       if (TWO_INPUTS) {
-        float4 x = __ldg(reinterpret_cast<const float4*>(Bm + r * C) + c4);
+        if (Mask) {
+          float4 m = __ldg(reinterpret_cast<const float4*>(Mask + r * ldm) + c4);
+          a.x = m.x > 0.f ? a.x : 0.f; a.y = m.y > 0.f ? a.y : 0.f; a.z = m.z > 0.f ? a.z : 0.f; a.w = m.w > 0.f ? a.w : 0.f;
+        }
+        float4 x = __ldg(reinterpret_cast<const float4*>(Bm + r * ldb) + c4);
         // a = dY, second sum = dY * xhat
         s1.x += a.x; s1.y += a.y; s1.z += a.z; s1.w += a.w;
         s2.x += a.x * ((x.x - mu.x) * is.x); s2.y += a.y * ((x.y - mu.y) * is.y);
@@ -69,46 +75,64 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, int chunks
   }
 }
 
-__global__ void bn_apply_kernel(const float* __restrict__ X, int64_t n4, int cv, const float* __restrict__ mean,
+__global__ void bn_apply_kernel(const float* __restrict__ X, int ldx, int64_t n4, int cv, const float* __restrict__ mean,
                                 const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                const float* __restrict__ residual, int relu, float* __restrict__ Y) {
+                                const float* __restrict__ residual, int ldr, int relu, float* __restrict__ Y, int ldy) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n4) return;
   int c4 = (int)(i % cv);
-  float4 x = __ldg(reinterpret_cast<const float4*>(X) + i);
+  const int64_t row = i / cv;
+  float4 x = __ldg(reinterpret_cast<const float4*>(X + row * ldx) + c4);
   float4 mu = reinterpret_cast<const float4*>(mean)[c4], is = reinterpret_cast<const float4*>(invstd)[c4];
   float4 g = reinterpret_cast<const float4*>(gamma)[c4], b = reinterpret_cast<const float4*>(beta)[c4];
   float4 y;
   y.x = (x.x - mu.x) * is.x * g.x + b.x; y.y = (x.y - mu.y) * is.y * g.y + b.y;
   y.z = (x.z - mu.z) * is.z * g.z + b.z; y.w = (x.w - mu.w) * is.w * g.w + b.w;
   if (residual) {
-    float4 r = __ldg(reinterpret_cast<const float4*>(residual) + i);
+    float4 r = __ldg(reinterpret_cast<const float4*>(residual + row * ldr) + c4);
     y.x += r.x; y.y += r.y; y.z += r.z; y.w += r.w;
   }
   if (relu) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
-  reinterpret_cast<float4*>(Y)[i] = y;
+  *reinterpret_cast<float4*>(Y + row * ldy + c4 * 4) = y;
 }
 
 // dgamma = sum(dY*xhat), dbeta = sum(dY); also leaves them in ws for the apply pass
+// sums[0][C] = dbeta, sums[1][C] = dgamma for the apply pass; the parameter gradients are written or accumulated
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int chunks, int C, float* __restrict__ dgamma,
-                                       float* __restrict__ dbeta) {
+                                       float* __restrict__ dbeta, int accumulate, float* __restrict__ sums) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   double s1 = 0.0, s2 = 0.0;
   for (int k = 0; k < chunks; ++k) { s1 += partial[(int64_t)k * 2 * C + c]; s2 += partial[(int64_t)k * 2 * C + C + c]; }
-  dbeta[c] = (float)s1;
-  dgamma[c] = (float)s2;
+  sums[c] = (float)s1;
+  sums[C + c] = (float)s2;
+  if (accumulate) { dbeta[c] += (float)s1; dgamma[c] += (float)s2; }
+  else { dbeta[c] = (float)s1; dgamma[c] = (float)s2; }
 }
 
-__global__ void bn_bwd_apply_kernel(const float* __restrict__ dY, const float* __restrict__ X, int64_t n4, int cv, float inv_n,
+// gout_mode: 0 none, 1 write, 2 accumulate -- the (ReLU-masked) incoming gradient, i.e. the gradient of the residual input
+__global__ void bn_bwd_apply_kernel(const float* dY, int lddy, const float* __restrict__ X, int ldx,
+                                    const float* __restrict__ Mask, int ldm, int64_t n4, int cv, float inv_n,
                                     const float* __restrict__ mean, const float* __restrict__ invstd,
                                     const float* __restrict__ gamma, const float* __restrict__ dgamma,
-                                    const float* __restrict__ dbeta, float* __restrict__ dX) {
+                                    const float* __restrict__ dbeta, float* __restrict__ dX, int lddx, float* gout, int ldg,
+                                    int gout_mode) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n4) return;
   int c4 = (int)(i % cv);
-  float4 dy = __ldg(reinterpret_cast<const float4*>(dY) + i);
-  float4 x = __ldg(reinterpret_cast<const float4*>(X) + i);
+  const int64_t row = i / cv;
+  float4 dy = *(reinterpret_cast<const float4*>(dY + row * lddy) + c4);
+  if (Mask) {
+    float4 m = __ldg(reinterpret_cast<const float4*>(Mask + row * ldm) + c4);
+    dy.x = m.x > 0.f ? dy.x : 0.f; dy.y = m.y > 0.f ? dy.y : 0.f; dy.z = m.z > 0.f ? dy.z : 0.f; dy.w = m.w > 0.f ? dy.w : 0.f;
+  }
+  if (gout_mode) {
+    float4* gp = reinterpret_cast<float4*>(gout + row * ldg) + c4;
+    float4 gv = dy;
+    if (gout_mode == 2) { float4 o = *gp; gv.x += o.x; gv.y += o.y; gv.z += o.z; gv.w += o.w; }
+    *gp = gv;
+  }
+  float4 x = __ldg(reinterpret_cast<const float4*>(X + row * ldx) + c4);
   float4 mu = reinterpret_cast<const float4*>(mean)[c4], is = reinterpret_cast<const float4*>(invstd)[c4];
   float4 g = reinterpret_cast<const float4*>(gamma)[c4];
   float4 dg = reinterpret_cast<const float4*>(dgamma)[c4], db = reinterpret_cast<const float4*>(dbeta)[c4];
@@ -117,7 +141,7 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ dY, const float* _
   o.y = g.y * is.y * (dy.y - db.y * inv_n - (x.y - mu.y) * is.y * dg.y * inv_n);
   o.z = g.z * is.z * (dy.z - db.z * inv_n - (x.z - mu.z) * is.z * dg.z * inv_n);
   o.w = g.w * is.w * (dy.w - db.w * inv_n - (x.w - mu.w) * is.w * dg.w * inv_n);
-  reinterpret_cast<float4*>(dX)[i] = o;
+  *reinterpret_cast<float4*>(dX + row * lddx + c4 * 4) = o;
 }
 
 inline int chunks_for(int64_t n) { return (int)((n + ROWS_PER_CHUNK - 1) / ROWS_PER_CHUNK); }
@@ -132,50 +156,74 @@ inline int colsum_threads(int C) {       // (C/4) * row lanes, <= 256, at least 
 
 extern "C" size_t pcb_bn_ws_bytes(int64_t n, int C) {
   if (n < 1) n = 1;
-  return (size_t)chunks_for(n) * 2 * C * sizeof(float) + 256;
+  return (size_t)(chunks_for(n) + 1) * 2 * C * sizeof(float) + 256;
 }
 
-extern "C" int pcb_bn_stats(const float* X, int64_t n, int C, float eps, float momentum, float* mean, float* invstd,
-                            float* running_mean, float* running_var, void* ws, size_t ws_bytes, void* stream) {
-  PCB_ARG(X && mean && invstd && ws && n >= 1 && C >= 4 && C % 4 == 0 && C <= 1024);
+extern "C" int pcb_bn_stats2(const float* X, int ldx, int64_t n, int C, float eps, float momentum, float* mean, float* invstd,
+                             float* running_mean, float* running_var, void* ws, size_t ws_bytes, void* stream) {
+  PCB_ARG(X && mean && invstd && ws && n >= 1 && C >= 4 && C % 4 == 0 && C <= 1024 && ldx >= C && ldx % 4 == 0);
   PCB_ARG(ws_bytes >= pcb_bn_ws_bytes(n, C) - 256);
   cudaStream_t st = (cudaStream_t)stream;
   const int chunks = chunks_for(n);
   const int thr = colsum_threads(C);
   const int rp = thr / (C / 4);
-  colsum_kernel<false><<<chunks, thr, (size_t)rp * 2 * C * sizeof(float), st>>>(X, nullptr, n, C, nullptr, nullptr, (float*)ws);
+  colsum_kernel<false><<<chunks, thr, (size_t)rp * 2 * C * sizeof(float), st>>>(X, ldx, nullptr, 0, nullptr, 0, n, C, nullptr, nullptr,
+                                                                                 (float*)ws);
   if (int e = check_launch("colsum_kernel")) return e;
   bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>((const float*)ws, chunks, n, C, eps, momentum, mean, invstd, running_mean,
                                                       running_var);
   return check_launch("bn_finalize_kernel");
 }
 
-extern "C" int pcb_bn_apply(const float* X, int64_t n, int C, const float* mean, const float* invstd, const float* gamma,
-                            const float* beta, const float* residual, int relu, float* Y, void* stream) {
-  PCB_ARG(n >= 0 && C >= 4 && C % 4 == 0);
+extern "C" int pcb_bn_stats(const float* X, int64_t n, int C, float eps, float momentum, float* mean, float* invstd,
+                            float* running_mean, float* running_var, void* ws, size_t ws_bytes, void* stream) {
+  return pcb_bn_stats2(X, C, n, C, eps, momentum, mean, invstd, running_mean, running_var, ws, ws_bytes, stream);
+}
+
+extern "C" int pcb_bn_apply2(const float* X, int ldx, int64_t n, int C, const float* mean, const float* invstd, const float* gamma,
+                             const float* beta, const float* residual, int ldr, int relu, float* Y, int ldy, void* stream) {
+  PCB_ARG(n >= 0 && C >= 4 && C % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && ldx >= C && ldy >= C);
   if (n == 0) return PCB_OK;
-  PCB_ARG(X && Y && mean && invstd && gamma && beta);
+  PCB_ARG(X && Y && mean && invstd && gamma && beta && (!residual || (ldr >= C && ldr % 4 == 0)));
   int64_t n4 = n * (C / 4);
-  bn_apply_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(X, n4, C / 4, mean, invstd, gamma, beta, residual,
-                                                                                 relu, Y);
+  bn_apply_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(X, ldx, n4, C / 4, mean, invstd, gamma, beta, residual,
+                                                                                 ldr, relu, Y, ldy);
   return check_launch("bn_apply_kernel");
 }
 
-extern "C" int pcb_bn_backward(const float* dY, const float* X, int64_t n, int C, const float* mean, const float* invstd,
-                               const float* gamma, float* dX, float* dgamma, float* dbeta, void* ws, size_t ws_bytes,
-                               void* stream) {
+extern "C" int pcb_bn_apply(const float* X, int64_t n, int C, const float* mean, const float* invstd, const float* gamma,
+                            const float* beta, const float* residual, int relu, float* Y, void* stream) {
+  return pcb_bn_apply2(X, C, n, C, mean, invstd, gamma, beta, residual, C, relu, Y, C, stream);
+}
+
+extern "C" int pcb_bn_backward2(const float* dY, int lddy, const float* X, int ldx, const float* relu_out, int ldm, int64_t n, int C,
+                                const float* mean, const float* invstd, const float* gamma, float* dX, int lddx, float* dgamma,
+                                float* dbeta, int accumulate_param_grads, float* gout, int ldg, int gout_mode, void* ws,
+                                size_t ws_bytes, void* stream) {
   PCB_ARG(dY && X && mean && invstd && gamma && dX && dgamma && dbeta && ws && n >= 1 && C >= 4 && C % 4 == 0 && C <= 1024);
+  PCB_ARG(lddy >= C && ldx >= C && lddx >= C && lddy % 4 == 0 && ldx % 4 == 0 && lddx % 4 == 0);
+  PCB_ARG(!relu_out || (ldm >= C && ldm % 4 == 0));
+  PCB_ARG(gout_mode == 0 || (gout && ldg >= C && ldg % 4 == 0));
   PCB_ARG(ws_bytes >= pcb_bn_ws_bytes(n, C) - 256);
   cudaStream_t st = (cudaStream_t)stream;
   const int chunks = chunks_for(n);
   const int thr = colsum_threads(C);
   const int rp = thr / (C / 4);
-  colsum_kernel<true><<<chunks, thr, (size_t)rp * 2 * C * sizeof(float), st>>>(dY, X, n, C, mean, invstd, (float*)ws);
+  float* partial = (float*)ws;
+  float* sums = partial + (size_t)chunks * 2 * C;        // [2][C]: dbeta, dgamma of THIS call (the apply pass needs them)
+  colsum_kernel<true><<<chunks, thr, (size_t)rp * 2 * C * sizeof(float), st>>>(dY, lddy, X, ldx, relu_out, ldm, n, C, mean, invstd, partial);
   if (int e = check_launch("colsum_kernel<bwd>")) return e;
-  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>((const float*)ws, chunks, C, dgamma, dbeta);
+  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(partial, chunks, C, dgamma, dbeta, accumulate_param_grads, sums);
   if (int e = check_launch("bn_bwd_finalize_kernel")) return e;
   int64_t n4 = n * (C / 4);
-  bn_bwd_apply_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(dY, X, n4, C / 4, 1.0f / (float)n, mean, invstd, gamma, dgamma,
-                                                                    dbeta, dX);
+  bn_bwd_apply_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(dY, lddy, X, ldx, relu_out, ldm, n4, C / 4, 1.0f / (float)n, mean,
+                                                                    invstd, gamma, sums + C, sums, dX, lddx, gout, ldg, gout_mode);
   return check_launch("bn_bwd_apply_kernel");
+}
+
+extern "C" int pcb_bn_backward(const float* dY, const float* X, int64_t n, int C, const float* mean, const float* invstd,
+                               const float* gamma, float* dX, float* dgamma, float* dbeta, void* ws, size_t ws_bytes,
+                               void* stream) {
+  return pcb_bn_backward2(dY, C, X, C, nullptr, 0, n, C, mean, invstd, gamma, dX, C, dgamma, dbeta, 0, nullptr, 0, 0, ws, ws_bytes,
+                          stream);
 }

@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(NTHR, 2) conv_mma_kernel(const ConvArgs p) {
 
 // Y[row, c] = bias[c] + sum_z partial[z][row][c]   (fixed order: deterministic)
 __global__ void conv_split_reduce_kernel(const float* __restrict__ partial, int nsplit, int64_t n_out, int Cout,
-                                         const float* __restrict__ bias, float* __restrict__ Y, int ldy) {
+                                         const float* __restrict__ bias, float* __restrict__ Y, int ldy, int accumulate) {
   const int cv = Cout / 4;
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n_out * cv) return;
@@ -264,7 +264,9 @@ __global__ void conv_split_reduce_kernel(const float* __restrict__ partial, int 
     float4 v = __ldg(reinterpret_cast<const float4*>(partial) + z * plane + i);
     s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
   }
-  *reinterpret_cast<float4*>(Y + row * ldy + c4 * 4) = s;
+  float4* dst = reinterpret_cast<float4*>(Y + row * ldy + c4 * 4);
+  if (accumulate) { float4 o = *dst; s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w; }
+  *dst = s;
 }
 
 // --------------------------------------------------------------------------------------------- forward (exact fp32 SIMT)
@@ -485,12 +487,12 @@ __global__ void wgrad_simt_kernel(const WgradArgs p) {
   }
 }
 
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int64_t n, float* __restrict__ dW) {
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int64_t n, float* __restrict__ dW, int accumulate) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
   float s = 0.f;
   for (int sp = 0; sp < splits; ++sp) s += partial[(int64_t)sp * n + i];
-  dW[i] = s;
+  dW[i] = accumulate ? dW[i] + s : s;
 }
 
 // --------------------------------------------------------------------------------------------- weight preparation
@@ -548,7 +550,7 @@ int launch_conv(ConvArgs a, int nsplit, float* ws, cudaStream_t st) {
   if (int e = check_launch("conv_mma_kernel")) return e;
   if (nsplit > 1) {
     int64_t n4 = a.n_out * (a.Cout / 4);
-    conv_split_reduce_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(ws, nsplit, a.n_out, a.Cout, a.bias, a.Y, a.ldy);
+    conv_split_reduce_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(ws, nsplit, a.n_out, a.Cout, a.bias, a.Y, a.ldy, 0);
     return check_launch("conv_split_reduce_kernel");
   }
   return PCB_OK;
@@ -592,7 +594,7 @@ extern "C" int pcb_weight_prep(const float* W, int K, int Cin, int Cout, uint16_
 namespace pcb {
 int launch_conv_tcgen05(const float* X, int ldx, const int32_t* tbl, int64_t tbl_stride, const int* kmap, int K, int64_t n_out,
                         int Cin, int Cout, const uint16_t* wk_hi, const uint16_t* wk_lo, const float* bias, float* Y, int ldy,
-                        float* partial, int nsplit, int bn, cudaStream_t st);
+                        float* partial, int nsplit, int bn, int accumulate, cudaStream_t st);
 }
 
 extern "C" size_t pcb_conv_forward_ws_bytes(int K, int64_t n_out, int Cin, int Cout) {
@@ -614,6 +616,7 @@ extern "C" int pcb_conv_forward(const float* X, int ldx, const int32_t* tbl, int
   const bool tc_ok = (Cin % 32 == 0) && (Cout % 32 == 0) && (ldx % 4 == 0) && (ldy % 2 == 0) && w_hi && w_lo &&
                      !(flags & PCB_CONV_FORCE_SIMT);
   if (!tc_ok) {
+    if (flags & PCB_CONV_ACCUMULATE) { set_error("PCB_CONV_ACCUMULATE needs the tcgen05 path"); return PCB_ERR_ARG; }
     if (!w_f32) { set_error("pcb_conv_forward: SIMT path needs w_f32 (Cin=%d Cout=%d)", Cin, Cout); return PCB_ERR_ARG; }
     int64_t total = n_out * Cout;
     conv_simt_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(X, ldx, tbl, tbl_stride, km, K, n_out, Cin, Cout,
@@ -629,16 +632,19 @@ extern "C" int pcb_conv_forward(const float* X, int ldx, const int32_t* tbl, int
     PCB_ARG(ws && ws_bytes >= (size_t)nsplit * n_out * Cout * sizeof(float));
     PCB_ARG(ldy % 4 == 0);
   }
+  const int accumulate = (flags & PCB_CONV_ACCUMULATE) ? 1 : 0;
   if ((flags & PCB_CONV_TCGEN05) && wk_hi && wk_lo && ldy % 4 == 0) {
     if (int e = launch_conv_tcgen05(X, ldx, tbl, tbl_stride, km.v, K, n_out, Cin, Cout, wk_hi, wk_lo, bias, Y, ldy,
-                                    nsplit > 1 ? (float*)ws : nullptr, nsplit, pick_tile(Cout), st)) return e;
+                                    nsplit > 1 ? (float*)ws : nullptr, nsplit, pick_tile(Cout), accumulate, st)) return e;
     if (nsplit > 1) {
       int64_t n4 = n_out * (Cout / 4);
-      conv_split_reduce_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>((const float*)ws, nsplit, n_out, Cout, bias, Y, ldy);
+      conv_split_reduce_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>((const float*)ws, nsplit, n_out, Cout, bias, Y, ldy,
+                                                                             accumulate);
       return check_launch("conv_split_reduce_kernel");
     }
     return PCB_OK;
   }
+  if (accumulate) { set_error("PCB_CONV_ACCUMULATE needs the tcgen05 path"); return PCB_ERR_ARG; }
   switch (pick_tile(Cout)) {
     case 128: return launch_conv<128>(a, nsplit, (float*)ws, st);
     case 96: return launch_conv<96>(a, nsplit, (float*)ws, st);
@@ -662,7 +668,10 @@ extern "C" int pcb_conv_wgrad(const float* A, int lda, const float* B, int ldb, 
   PCB_ARG(K >= 1 && K <= PCB_MAX_KERNEL_VOLUME && n_out >= 0 && Ca >= 1 && Cb >= 1 && dW && lda >= Ca && ldb >= Cb);
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t nW = (int64_t)K * Ca * Cb;
-  if (n_out == 0) { PCB_CUDA(cudaMemsetAsync(dW, 0, nW * sizeof(float), st)); return PCB_OK; }
+  if (n_out == 0) {
+    if (!(flags & PCB_CONV_ACCUMULATE)) PCB_CUDA(cudaMemsetAsync(dW, 0, nW * sizeof(float), st));
+    return PCB_OK;
+  }
   PCB_ARG(A && B && tbl && ws && tbl_stride >= n_out);
   int tm = pick_tile(Ca), tn = pick_tile(Cb);
   const bool tc_ok = tm && tn && (lda % 4 == 0) && (ldb % 4 == 0) && !(flags & PCB_CONV_FORCE_SIMT);
@@ -688,6 +697,7 @@ extern "C" int pcb_conv_wgrad(const float* A, int lda, const float* B, int ldb, 
     WG_CASE(32, 128);  WG_CASE(32, 96);  WG_CASE(32, 64);  WG_CASE(32, 32);
   }
   if (rc) return rc;
-  wgrad_reduce_kernel<<<(unsigned)((nW + 255) / 256), 256, 0, st>>>((const float*)ws, splits, nW, dW);
+  wgrad_reduce_kernel<<<(unsigned)((nW + 255) / 256), 256, 0, st>>>((const float*)ws, splits, nW, dW,
+                                                                    (flags & PCB_CONV_ACCUMULATE) ? 1 : 0);
   return check_launch("wgrad_reduce_kernel");
 }

@@ -88,6 +88,7 @@ struct Args {
   const float* bias;
   float* Y; int ldy;
   float* partial;
+  int accumulate;       // Y += result (direct mode only; the split mode accumulates in the reduce kernel)
 };
 
 template <int BN>
@@ -260,6 +261,10 @@ __global__ void __launch_bounds__(NTHR, 2) conv_tcgen05_kernel(const Args p) {
       for (int e = 0; e < 16; e += 4) {
         float4 o = make_float4(__uint_as_float(r[e]), __uint_as_float(r[e + 1]), __uint_as_float(r[e + 2]), __uint_as_float(r[e + 3]));
         if (bias) { o.x += bias[n0 + col + e]; o.y += bias[n0 + col + e + 1]; o.z += bias[n0 + col + e + 2]; o.w += bias[n0 + col + e + 3]; }
+        if (p.accumulate && !p.partial) {
+          float4 old = *reinterpret_cast<const float4*>(dst + e);
+          o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+        }
         *reinterpret_cast<float4*>(dst + e) = o;
       }
     }
@@ -289,8 +294,9 @@ int launch(const Args& a, int nsplit, cudaStream_t st) {
 // Called by pcb_conv_forward (conv.cu).  wk_*: K-major split weights [K][Cout][Cin] for this call's roles.
 int launch_conv_tcgen05(const float* X, int ldx, const int32_t* tbl, int64_t tbl_stride, const int* kmap, int K, int64_t n_out,
                         int Cin, int Cout, const uint16_t* wk_hi, const uint16_t* wk_lo, const float* bias, float* Y, int ldy,
-                        float* partial, int nsplit, int bn, cudaStream_t st) {
+                        float* partial, int nsplit, int bn, int accumulate, cudaStream_t st) {
   tc5::Args a;
+  a.accumulate = accumulate;
   a.X = X; a.ldx = ldx; a.tbl = tbl; a.tbl_stride = tbl_stride; a.K = K; a.n_out = n_out; a.Cin = Cin; a.Cout = Cout;
   for (int k = 0; k < K; ++k) a.kmap[k] = kmap[k];
   a.wk_hi = (const __nv_bfloat16*)wk_hi; a.wk_lo = (const __nv_bfloat16*)wk_lo; a.bias = bias; a.Y = Y; a.ldy = ldy;

@@ -1,0 +1,281 @@
+"""Fused training executor for Res16UNet on libpcb200.
+
+The modular surface in `me.py` (one autograd node per MinkowskiConvolution / BatchNorm / ReLU, as in MinkowskiEngine)
+is what makes the reference's model file run unchanged; it costs ~1.5k Python-dispatched autograd nodes per step.
+This module runs the SAME graph (`pretrain/pointcontrast/model/res16unet.py:206-268`) as one autograd node per forward:
+
+  * unit = conv -> BatchNorm statistics -> one elementwise pass doing normalise + residual add + ReLU
+    (`model/modules/resnet_block.py:44-60` collapses to two units per BasicBlock);
+  * `me.cat` is free: the two producers write straight into the column halves of one wider buffer (row strides);
+  * backward is a hand-written reverse sweep: ReLU mask + BatchNorm backward + residual-gradient fan-out in one pass,
+    data-gradient convs accumulate into their consumer's gradient buffer, weight gradients accumulate straight into
+    the (flat) parameter gradient buffer -- no autograd bookkeeping, no intermediate copies.
+
+Numerics are those of the modular path (same kernels, same order of operations per element).
+"""
+import ctypes
+
+import torch
+
+from . import _lib, me
+from ._lib import check, lib, ptr, stream
+
+ENABLED = True
+
+
+class Buf:
+    """fp32 matrix [n, C] with row stride ld (floats); `owner` keeps the storage alive."""
+    __slots__ = ("owner", "p", "n", "C", "ld", "slot", "_grad", "parent", "col")
+
+    def __init__(self, owner, p, n, C, ld, parent=None, col=0):
+        self.owner, self.p, self.n, self.C, self.ld = owner, p, n, C, ld
+        self.parent, self.col = parent, col
+        self._grad = None
+        self.slot = parent.slot if parent is not None else [False]     # [gradient buffer initialised?]
+
+    @staticmethod
+    def new(n, C, device):
+        t = torch.empty(n * C, dtype=torch.float32, device=device)
+        return Buf(t, t.data_ptr(), n, C, C)
+
+    def cols(self, c0, C):
+        return Buf(self.owner, self.p + 4 * c0, self.n, C, self.ld, parent=self, col=c0)
+
+    def grad(self):
+        if self._grad is None:
+            if self.parent is not None:
+                g = self.parent.grad()
+                self._grad = Buf(g.owner, g.p + 4 * self.col, self.n, self.C, g.ld)
+            else:
+                t = torch.empty(self.n * self.ld, dtype=torch.float32, device=self.owner.device)
+                self._grad = Buf(t, t.data_ptr(), self.n, self.C, self.ld)
+        return self._grad
+
+
+def _kmap(plan_kmap):
+    return me._c_int_array(plan_kmap) if plan_kmap is not None else None
+
+
+class Runner:
+    def __init__(self, model):
+        self.model = model
+        self.anchor = torch.zeros(1, requires_grad=True)
+
+    # ------------------------------------------------------------------------------------------ launches
+    def _conv(self, x, tbl, kmap, conv, transposed_roles, n_out, out, accumulate, bias=None, plan=None):
+        kern = conv.kernel
+        K, Cin, Cout = kern.shape
+        ev = me._prof_begin() if plan is not None else None
+        try:
+            self._conv_launch(x, tbl, kmap, conv, transposed_roles, n_out, out, accumulate, bias)
+        finally:
+            me._prof_end(ev, "dgrad" if transposed_roles else "fwd", plan, K, Cin, Cout, Cin % 32 == 0 and Cout % 32 == 0)
+
+    def _conv_launch(self, x, tbl, kmap, conv, transposed_roles, n_out, out, accumulate, bias):
+        kern = conv.kernel
+        K, Cin, Cout = kern.shape
+        if transposed_roles:
+            Cin, Cout = Cout, Cin
+        st = stream()
+        if Cin % 32 == 0 and Cout % 32 == 0:
+            pl = conv._prepared.get(kern)
+            hi, lo, khi, klo = (pl[2], pl[3], pl[0], pl[1]) if transposed_roles else (pl[0], pl[1], pl[2], pl[3])
+            flags = 2 | (4 if accumulate else 0)
+            wsb = lib.pcb_conv_forward_ws_bytes(K, n_out, Cin, Cout)
+            ws = me.workspace(wsb, self.device, slot=2)
+            check(lib.pcb_conv_forward(x.p, x.ld, ptr(tbl), tbl.shape[1], kmap, K, n_out, Cin, Cout, ptr(hi), ptr(lo), ptr(khi),
+                                       ptr(klo), None, ptr(bias), out.p, out.ld, ptr(ws), wsb, flags, st))
+        else:
+            assert not accumulate and not transposed_roles
+            check(lib.pcb_conv_forward(x.p, x.ld, ptr(tbl), tbl.shape[1], kmap, K, n_out, Cin, Cout, None, None, None, None,
+                                       ptr(kern.detach()), ptr(bias), out.p, out.ld, None, 0, 0, st))
+
+    def _wgrad(self, conv, plan, a_in, dz):
+        kern = conv.kernel
+        K, Cin, Cout = kern.shape
+        if kern.grad is None:
+            kern.grad = torch.zeros_like(kern)
+        if plan.wg_gather_x:
+            A, B, Ca, Cb, tr, rows = a_in, dz, Cin, Cout, 0, plan.n_out
+        else:
+            A, B, Ca, Cb, tr, rows = dz, a_in, Cout, Cin, 1, plan.n_in
+        wsb = lib.pcb_conv_wgrad_ws_bytes(K, rows, Ca, Cb)
+        ws = me.workspace(wsb, self.device)
+        ev = me._prof_begin()
+        check(lib.pcb_conv_wgrad(A.p, A.ld, B.p, B.ld, ptr(plan.wg_tbl), plan.wg_tbl.shape[1], K, rows, Ca, Cb, kern.grad.data_ptr(),
+                                 tr, ptr(ws), wsb, 4, stream()))
+        me._prof_end(ev, "wgrad", plan, K, Cin, Cout, Ca % 32 == 0 and Cb % 32 == 0)
+
+    # ------------------------------------------------------------------------------------------ forward
+    def _unit(self, conv, bnm, a_in, plan, relu, residual=None, out=None):
+        """out = [relu]( BN(conv(a_in)) [+ residual] )"""
+        bn = bnm.bn
+        K, Cin, Cout = conv.kernel.shape
+        n = plan.n_out
+        z = Buf.new(n, Cout, self.device)
+        self._conv(a_in, plan.fwd_tbl, _kmap(plan.fwd_kmap), conv, False, n, z, False, plan=plan)
+        if out is None:
+            out = Buf.new(n, Cout, self.device)
+        mean = self._stat(Cout)
+        invstd = self._stat(Cout)
+        wsb = lib.pcb_bn_ws_bytes(n, Cout)
+        ws = me.workspace(wsb, self.device)
+        st = stream()
+        check(lib.pcb_bn_stats2(z.p, z.ld, n, Cout, bn.eps, bn.momentum, mean, invstd, bn.running_mean.data_ptr(),
+                                bn.running_var.data_ptr(), ptr(ws), wsb, st))
+        check(lib.pcb_bn_apply2(z.p, z.ld, n, Cout, mean, invstd, bn.weight.data_ptr(), bn.bias.data_ptr(),
+                                residual.p if residual is not None else None, residual.ld if residual is not None else 0,
+                                1 if relu else 0, out.p, out.ld, st))
+        self.bns.append(bn)
+        self.tape.append((conv, bn, a_in, z, out, mean, invstd, plan, relu, residual))
+        return out
+
+    def _stat(self, C):
+        p = self.stats.data_ptr() + 4 * self.stat_off
+        self.stat_off += C
+        return p
+
+    def _block(self, blk, x, plan3, plan1, out=None):
+        h = self._unit(blk.conv1, blk.norm1, x, plan3, True)
+        res = x if blk.downsample is None else self._unit(blk.downsample[0], blk.downsample[1], x, plan1, False)
+        return self._unit(blk.conv2, blk.norm2, h, plan3, True, residual=res, out=out)
+
+    def _stage(self, seq, x, plan3, plan1, out=None):
+        blocks = list(seq)
+        for i, blk in enumerate(blocks):
+            x = self._block(blk, x, plan3, plan1, out if i == len(blocks) - 1 else None)
+        return x
+
+    def forward(self, sinput):
+        m = self.model
+        feats = sinput.F
+        _lib.require_cuda(feats)
+        self.device = feats.device
+        cm = sinput.coords_man
+        self.tape, self.bns = [], []
+        self.stats = torch.empty(2 * sum(mod.bn.num_features for mod in m.modules() if isinstance(mod, me.MinkowskiBatchNorm)),
+                                 dtype=torch.float32, device=self.device)
+        self.stat_off = 0
+        with torch.cuda.device(self.device):
+            keys = [sinput.coords_key]
+            for _ in range(4):
+                keys.append(cm.stride(keys[-1], [2, 2, 2]))
+            n = [cm.num_rows(k) for k in keys]
+            kg3 = m.block1[0].conv1.kernel_generator
+            kg1 = m.final.kernel_generator
+            kg2 = m.conv1p1s2.kernel_generator
+            p3 = [cm.conv_plan(k, k, kg3, False) for k in keys]
+            p1 = [cm.conv_plan(k, k, kg1, False) for k in keys]
+            down = [cm.conv_plan(keys[i], keys[i + 1], kg2, False) for i in range(4)]
+            up = [cm.conv_plan(keys[i + 1], keys[i], kg2, True) for i in range(4)]
+            p0 = cm.conv_plan(keys[0], keys[0], m.conv0p1s1.kernel_generator, False)
+            P = m.PLANES
+            x_in = feats.detach().contiguous().float()
+            a0 = Buf(x_in, x_in.data_ptr(), n[0], x_in.shape[1], x_in.shape[1])
+            a0.slot[0] = None                    # network input: no gradient wanted
+            dev = self.device
+            # concatenation buffers (left = decoder branch, right = encoder skip)
+            cat8 = Buf.new(n[0], P[7] + m.INIT_DIM, dev)
+            cat7 = Buf.new(n[1], P[6] + P[0], dev)
+            cat6 = Buf.new(n[2], P[5] + P[1], dev)
+            cat5 = Buf.new(n[3], P[4] + P[2], dev)
+            out_p1 = self._unit(m.conv0p1s1, m.bn0, a0, p0, True, out=cat8.cols(P[7], m.INIT_DIM))
+            x = self._unit(m.conv1p1s2, m.bn1, out_p1, down[0], True)
+            b1 = self._stage(m.block1, x, p3[1], p1[1], out=cat7.cols(P[6], P[0]))
+            x = self._unit(m.conv2p2s2, m.bn2, b1, down[1], True)
+            b2 = self._stage(m.block2, x, p3[2], p1[2], out=cat6.cols(P[5], P[1]))
+            x = self._unit(m.conv3p4s2, m.bn3, b2, down[2], True)
+            b3 = self._stage(m.block3, x, p3[3], p1[3], out=cat5.cols(P[4], P[2]))
+            x = self._unit(m.conv4p8s2, m.bn4, b3, down[3], True)
+            x = self._stage(m.block4, x, p3[4], p1[4])
+            self._unit(m.convtr4p16s2, m.bntr4, x, up[3], True, out=cat5.cols(0, P[4]))
+            x = self._stage(m.block5, cat5, p3[3], p1[3])
+            self._unit(m.convtr5p8s2, m.bntr5, x, up[2], True, out=cat6.cols(0, P[5]))
+            x = self._stage(m.block6, cat6, p3[2], p1[2])
+            self._unit(m.convtr6p4s2, m.bntr6, x, up[1], True, out=cat7.cols(0, P[6]))
+            x = self._stage(m.block7, cat7, p3[1], p1[1])
+            self._unit(m.convtr7p2s2, m.bntr7, x, up[0], True, out=cat8.cols(0, P[7]))
+            x = self._stage(m.block8, cat8, p3[0], p1[0])
+            fin = m.final
+            out_t = torch.empty(n[0], fin.out_channels, dtype=torch.float32, device=dev)
+            out = Buf(out_t, out_t.data_ptr(), n[0], fin.out_channels, fin.out_channels)
+            self._conv(x, p1[0].fwd_tbl, None, fin, False, n[0], out, False,
+                       bias=fin.bias.detach().reshape(-1) if fin.bias is not None else None, plan=p1[0])
+            for bn in self.bns:
+                bn.num_batches_tracked += 1
+        ctx = (self.tape, x, p1[0], self.stats)
+        self.tape = None
+        return out_t, ctx
+
+    # ------------------------------------------------------------------------------------------ backward
+    def backward(self, ctx, d_out):
+        tape, x_last, p_final, _stats = ctx
+        m = self.model
+        d_out = d_out.contiguous()
+        dev = d_out.device
+        self.device = dev
+        with torch.cuda.device(dev):
+            fin = m.final
+            dfin = Buf(d_out, d_out.data_ptr(), d_out.shape[0], d_out.shape[1], d_out.shape[1])
+            if fin.bias is not None:
+                if fin.bias.grad is None:
+                    fin.bias.grad = torch.zeros_like(fin.bias)
+                fin.bias.grad += d_out.sum(0, keepdim=True)
+            self._wgrad(fin, p_final, x_last, dfin)
+            gx = x_last.grad()
+            self._conv(dfin, p_final.dg_tbl, _kmap(p_final.dg_kmap), fin, True, p_final.n_in, gx, False, plan=p_final)
+            x_last.slot[0] = True
+            st = stream()
+            for (conv, bn, a_in, z, out, mean, invstd, plan, relu, residual) in reversed(tape):
+                K, Cin, Cout = conv.kernel.shape
+                n = plan.n_out
+                g = out.grad()
+                assert out.slot[0], "gradient of a unit output was never produced"
+                dz = Buf.new(n, Cout, dev)
+                gout_p, gout_ld, gout_mode = None, 0, 0
+                if residual is not None and residual.slot[0] is not None:
+                    rg = residual.grad()
+                    gout_p, gout_ld = rg.p, rg.ld
+                    gout_mode = 2 if residual.slot[0] else 1
+                    residual.slot[0] = True
+                for prm in (bn.weight, bn.bias):
+                    if prm.grad is None:
+                        prm.grad = torch.zeros_like(prm)
+                wsb = lib.pcb_bn_ws_bytes(n, Cout)
+                ws = me.workspace(wsb, dev)
+                check(lib.pcb_bn_backward2(g.p, g.ld, z.p, z.ld, out.p if relu else None, out.ld, n, Cout, mean, invstd,
+                                           bn.weight.data_ptr(), dz.p, dz.ld, bn.weight.grad.data_ptr(), bn.bias.grad.data_ptr(), 1,
+                                           gout_p, gout_ld, gout_mode, ptr(ws), wsb, st))
+                self._wgrad(conv, plan, a_in, dz)
+                if a_in.slot[0] is not None:
+                    ga = a_in.grad()
+                    self._conv(dz, plan.dg_tbl, _kmap(plan.dg_kmap), conv, True, plan.n_in, ga, bool(a_in.slot[0]), plan=plan)
+                    a_in.slot[0] = True
+
+
+class _FusedFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, anchor, runner, sinput):
+        out, fctx = runner.forward(sinput)
+        ctx.runner, ctx.fctx = runner, fctx
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        ctx.runner.backward(ctx.fctx, d_out)
+        ctx.fctx = None
+        return None, None, None
+
+
+def applicable(model, sinput):
+    return (ENABLED and model.training and torch.is_grad_enabled() and sinput.F.is_cuda and me.CONV_IMPL == "tcgen05"
+            and not me.FORCE_SIMT)
+
+
+def run(model, sinput):
+    """Final-layer features [N, out_channels] (before the optional L2 normalisation) as ONE autograd node."""
+    runner = model.__dict__.get("_fused_runner")
+    if runner is None:
+        runner = Runner(model)
+        model.__dict__["_fused_runner"] = runner
+    return _FusedFunction.apply(runner.anchor, runner, sinput)

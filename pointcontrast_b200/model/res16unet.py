@@ -9,6 +9,7 @@ stage by stage.  Quirk kept on purpose: the norms inside r
 import torch
 import torch.nn as nn
 
+from .. import fused
 from .. import me as ME
 
 
@@ -98,6 +99,16 @@ class Res16UNetBase(ME.MinkowskiNetwork):
         return nn.Sequential(*layers)
 
     def forward(self, x):
+        if ME is fused.me and fused.applicable(self, x):      # training on CUDA: the whole graph as one fused autograd node
+            out = ME.SparseTensor(fused.run(self, x), coords_key=x.coords_key, coords_manager=x.coords_man)
+        else:
+            out = self._forward_modular(x)
+        if self.normalize_feature:               # `model/res16unet.py:262-266` (no epsilon)
+            return ME.SparseTensor(out.F / torch.norm(out.F, p=2, dim=1, keepdim=True), coords_key=out.coords_key,
+                                   coords_manager=out.coords_man)
+        return out
+
+    def _forward_modular(self, x):
         out_p1 = self.relu(self.bn0(self.conv0p1s1(x)))
         out_b1p2 = self.block1(self.relu(self.bn1(self.conv1p1s2(out_p1))))
         out_b2p4 = self.block2(self.relu(self.bn2(self.conv2p2s2(out_b1p2))))
@@ -107,11 +118,7 @@ class Res16UNetBase(ME.MinkowskiNetwork):
         out = self.block6(ME.cat(self.relu(self.bntr5(self.convtr5p8s2(out))), out_b2p4))
         out = self.block7(ME.cat(self.relu(self.bntr6(self.convtr6p4s2(out))), out_b1p2))
         out = self.block8(ME.cat(self.relu(self.bntr7(self.convtr7p2s2(out))), out_p1))
-        out = self.final(out)
-        if self.normalize_feature:               # `model/res16unet.py:262-266` (no epsilon)
-            return ME.SparseTensor(out.F / torch.norm(out.F, p=2, dim=1, keepdim=True), coords_key=out.coords_key,
-                                   coords_manager=out.coords_man)
-        return out
+        return self.final(out)
 
 
 class Res16UNet14(Res16UNetBase):

@@ -22,11 +22,11 @@ GOLD = os.path.join(os.path.dirname(__file__), "golden", "c0_res16unet34c.npz")
 
 
 def _grad_tol(floor, factor):
-    """Per-parameter gradient tolerance: max(1e-3, factor x fp32 floor), where a parameter's floor is never taken below a
-    tenth of the network-wide worst floor (the 2^-18 split error is amplified by the same BatchNorm cancellation that
-    amplifies fp32 rounding, but not parameter-by-parameter in the same ratio)."""
+    """Gradient tolerance: max(1e-3, factor x the network-wide fp32 floor).  The floor is the relative error of the SAME
+    graph evaluated in plain fp32 on the CPU against fp64 (worst parameter): 5e-3 .. 1e-2 on these problems, at any scene
+    size we could afford to evaluate in fp64 (measured up to 24k voxels/view)."""
     floor = np.asarray(floor, np.float64)
-    return np.maximum(1e-3, factor * np.maximum(floor, 0.1 * floor.max()))
+    return np.full_like(floor, max(1e-3, factor * float(floor.max())))
 
 
 def _gpu_net(seed=0, normalize=True):
@@ -142,3 +142,37 @@ def test_eval_mode_forward_matches_oracle_semseg_shape():
     with torch.no_grad():
         y = net(me.SparseTensor(torch.from_numpy(sc["feats"]), coords=torch.from_numpy(sc["coords"])).to("cuda")).F
     assert y.shape == (len(sc["coords"]), 13) and max_rel_err(y, yo) < 1e-3
+
+
+def test_fused_executor_matches_modular_path():
+    """One-autograd-node fused executor (pointcontrast_b200/fused.py) vs the per-module ME-style path: same kernels, so
+    features, every parameter gradient and the BatchNorm running statistics agree to fp32 rounding."""
+    from pointcontrast_b200 import fused, losses, me, synth
+    batch = synth.collate_pairs([synth.synth_pair(5, scale=0.15), synth.synth_pair(6, scale=0.12)])
+    rng = np.random.default_rng(1)
+    pairs = batch["correspondences"]
+    nq = len(np.unique(pairs[:, 0]))
+    q, k = loss_cpu.select_positives(pairs, rng.random(nq).astype(np.float32), 4096,
+                                     rng.choice(nq, 4096, replace=False) if nq > 4096 else None)
+    out = {}
+    for mode in (True, False):
+        fused.ENABLED = mode
+        try:
+            net = _gpu_net(4)
+            F = [net(me.SparseTensor(torch.from_numpy(batch[f"sinput{v}_F"]), coords=torch.from_numpy(batch[f"sinput{v}_C"])).to("cuda")).F
+                 for v in "01"]
+            loss = losses.point_nce_loss(F[0], F[1], q.cuda(), k.cuda(), 0.4)
+            loss.backward()
+            out[mode] = (F[0].detach(), F[1].detach(), float(loss.detach()), {n: p.grad.clone() for n, p in net.named_parameters()},
+                         {n: b.clone() for n, b in net.named_buffers()})
+        finally:
+            fused.ENABLED = True
+    a, b = out[True], out[False]
+    assert max_rel_err(a[0], b[0]) < 1e-5 and max_rel_err(a[1], b[1]) < 1e-5 and abs(a[2] - b[2]) < 1e-5 * abs(b[2])
+    worst = max((rel_err(a[3][n], b[3][n]), n) for n in b[3])
+    assert worst[0] < 2e-4, worst
+    for n in b[4]:
+        if b[4][n].dtype.is_floating_point:
+            assert rel_err(a[4][n], b[4][n]) < 1e-5, n
+        else:
+            assert (a[4][n] == b[4][n]).all(), n
