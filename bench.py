@@ -10,7 +10,7 @@ both views, 2x forward, loss, backward, gradient all-reduce (N > 1), fused SGD s
   value    : pairs/s with the batch already resident in HBM, CUDA-event timed, max over ranks.
   e2e      : pairs/s through the public trainer call (`Trainer._train_iter`) with the batch in pinned HOST memory,
              host->device copies and the loss read-back inside the timed region.
-  roofline : the dominant kernel (conv_mma_kernel: sparse-conv forward / data-gradient) -- algorithmic bytes
+  roofline : the dominant kernel (conv_tcgen05_kernel: sparse-conv forward / data-gradient) -- algorithmic bytes
               of all its launches in one step / their CUDA-event time, vs the measured HBM peak.
   cpu_baseline : the oracle (ME-0.4.3-algorithm CPU restatement) timed on this box's host cores, bounded sample.
 
@@ -263,7 +263,8 @@ def run_ours(args):
         for r in prof:
             b, f = conv_alg_bytes(r)
             t = r["ev0"].elapsed_time(r["ev1"])
-            key = ("conv_mma_kernel" if r["kind"] in ("fwd", "dgrad") else "wgrad_mma_kernel") if r["tc"] else "simt"
+            key = (("conv_tcgen05_kernel" if me.CONV_IMPL == "tcgen05" else "conv_mma_kernel") if r["kind"] in ("fwd", "dgrad")
+                   else "wgrad_mma_kernel") if r["tc"] else "simt"
             a = agg.setdefault(key, dict(bytes=0, flops=0, ms=0.0, launches=0))
             a["bytes"] += b; a["flops"] += f; a["ms"] += t; a["launches"] += 1
             r["bytes"], r["flops"], r["ms"] = b, f, t
