@@ -113,6 +113,18 @@ int pcb_conv_wgrad(const float* A, int lda, const float* B, int ldb, const int32
                    int64_t n_out, int Ca, int Cb, float* dW, int transpose_out, void* ws, size_t ws_bytes,
                    int flags, void* stream);
 
+/* Split-operand variants (tcgen05 only): the gathered / row-aligned operands are bf16 hi/lo planes (see pcb_split_rows),
+ * row strides lds/lda/ldb in ELEMENTS (multiples of 8).  Same semantics as pcb_conv_forward / pcb_conv_wgrad; the kernels'
+ * operand staging is then a pure asynchronous copy (cp.async, zero-filled where a neighbour is missing). */
+int pcb_conv_forward_split(const uint16_t* Xhi, const uint16_t* Xlo, int lds, const int32_t* tbl, int64_t tbl_stride,
+                           const int32_t* kmap, int K, int64_t n_out, int Cin, int Cout, const uint16_t* wk_hi,
+                           const uint16_t* wk_lo, const float* bias, float* Y, int ldy, void* ws, size_t ws_bytes, int flags,
+                           void* stream);
+size_t pcb_conv_wgrad_split_ws_bytes(int K, int64_t n_out, int Ca, int Cb);
+int pcb_conv_wgrad_split(const uint16_t* Ahi, const uint16_t* Alo, int lda, const uint16_t* Bhi, const uint16_t* Blo, int ldb,
+                         const int32_t* tbl, int64_t tbl_stride, int K, int64_t n_out, int Ca, int Cb, float* dW,
+                         int transpose_out, void* ws, size_t ws_bytes, int flags, void* stream);
+
 /* ----------------------------------------------------------------------------------------------- batch norm */
 /* Training-mode statistics over n rows: mean[C], invstd[C] = 1/sqrt(var_biased + eps); if running_* non-NULL:
  * running = (1-momentum)*running + momentum*{mean, var_unbiased}.  ws: pcb_bn_ws_bytes(n, C). */
@@ -136,11 +148,16 @@ int pcb_bn_backward(const float* dY, const float* X, int64_t n, int C, const flo
 int pcb_bn_stats2(const float* X, int ldx, int64_t n, int C, float eps, float momentum, float* mean, float* invstd,
                   float* running_mean, float* running_var, void* ws, size_t ws_bytes, void* stream);
 int pcb_bn_apply2(const float* X, int ldx, int64_t n, int C, const float* mean, const float* invstd, const float* gamma,
-                  const float* beta, const float* residual, int ldr, int relu, float* Y, int ldy, void* stream);
+                  const float* beta, const float* residual, int ldr, int relu, float* Y, int ldy, uint16_t* Yhi,
+                  uint16_t* Ylo, int lds, void* stream);
 int pcb_bn_backward2(const float* dY, int lddy, const float* X, int ldx, const float* relu_out, int ldm, int64_t n, int C,
                      const float* mean, const float* invstd, const float* gamma, float* dX, int lddx, float* dgamma,
-                     float* dbeta, int accumulate_param_grads, float* gout, int ldg, int gout_mode, void* ws,
-                     size_t ws_bytes, void* stream);
+                     float* dbeta, int accumulate_param_grads, float* gout, int ldg, int gout_mode, uint16_t* dXhi,
+                     uint16_t* dXlo, int lds, void* ws, size_t ws_bytes, void* stream);
+/* "Split" operand format of the tensor-core conv kernels: an fp32 matrix stored as two bf16 planes, x ~= hi + lo (2^-17);
+ * row stride lds in ELEMENTS.  The elementwise producers above can emit it directly (Yhi/Ylo, dXhi/dXlo; NULL = off; dX may
+ * then be NULL), so the conv kernels' gather becomes a pure asynchronous copy.  pcb_split_rows converts an fp32 matrix. */
+int pcb_split_rows(const float* X, int ldx, int64_t n, int C, uint16_t* hi, uint16_t* lo, int lds, void* stream);
 
 /* ----------------------------------------------------------------------------------------------- losses */
 /* PointInfoNCE on gathered rows q,k [n, D] (D % 4 == 0, D <= 128): loss = mean_i(logsumexp_j(q_i.k_j/T) - q_i.k_i/T).

@@ -10,6 +10,30 @@ namespace {
 
 constexpr int ROWS_PER_CHUNK = 512;
 
+// fp32 x4 -> bf16 hi x4 + bf16 lo x4 (x ~= hi + lo to 2^-17): the operand format of the tensor-core conv kernels
+__device__ __forceinline__ void store_split4(const float4& v, __nv_bfloat16* hi, __nv_bfloat16* lo) {
+  __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y);
+  __nv_bfloat162 h1 = __floats2bfloat162_rn(v.z, v.w);
+  float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+  __nv_bfloat162 l0 = __floats2bfloat162_rn(v.x - f0.x, v.y - f0.y);
+  __nv_bfloat162 l1 = __floats2bfloat162_rn(v.z - f1.x, v.w - f1.y);
+  uint2 H, L;
+  H.x = *reinterpret_cast<uint32_t*>(&h0); H.y = *reinterpret_cast<uint32_t*>(&h1);
+  L.x = *reinterpret_cast<uint32_t*>(&l0); L.y = *reinterpret_cast<uint32_t*>(&l1);
+  *reinterpret_cast<uint2*>(hi) = H;
+  *reinterpret_cast<uint2*>(lo) = L;
+}
+
+__global__ void split_rows_kernel(const float* __restrict__ X, int ldx, int64_t n4, int cv, __nv_bfloat16* __restrict__ hi,
+                                  __nv_bfloat16* __restrict__ lo, int lds) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  int c4 = (int)(i % cv);
+  const int64_t row = i / cv;
+  float4 x = __ldg(reinterpret_cast<const float4*>(X + row * ldx) + c4);
+  store_split4(x, hi + row * lds + c4 * 4, lo + row * lds + c4 * 4);
+}
+
 // partial[chunk][0][C] = sum(a), partial[chunk][1][C] = sum(a*b)    (b == a for the forward statistics)
 // block: (C/4) channel-vectors x RP row lanes; grid: one CTA per chunk of rows.
 // Strides: lda / ldb / ldm (floats).  Mask (backward only): a is zeroed where mask <= 0 (ReLU folded into the BN backward).
@@ -77,7 +101,8 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, int chunks
 
 __global__ void bn_apply_kernel(const float* __restrict__ X, int ldx, int64_t n4, int cv, const float* __restrict__ mean,
                                 const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                const float* __restrict__ residual, int ldr, int relu, float* __restrict__ Y, int ldy) {
+                                const float* __restrict__ residual, int ldr, int relu, float* __restrict__ Y, int ldy,
+                                __nv_bfloat16* __restrict__ Yhi, __nv_bfloat16* __restrict__ Ylo, int lds) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n4) return;
   int c4 = (int)(i % cv);
@@ -94,6 +119,7 @@ __global__ void bn_apply_kernel(const float* __restrict__ X, int ldx, int64_t n4
   }
   if (relu) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
   *reinterpret_cast<float4*>(Y + row * ldy + c4 * 4) = y;
+  if (Yhi) store_split4(y, Yhi + row * lds + c4 * 4, Ylo + row * lds + c4 * 4);
 }
 
 // dgamma = sum(dY*xhat), dbeta = sum(dY); also leaves them in ws for the apply pass
@@ -116,7 +142,7 @@ __global__ void bn_bwd_apply_kernel(const float* dY, int lddy, const float* __re
                                     const float* __restrict__ mean, const float* __restrict__ invstd,
                                     const float* __restrict__ gamma, const float* __restrict__ dgamma,
                                     const float* __restrict__ dbeta, float* __restrict__ dX, int lddx, float* gout, int ldg,
-                                    int gout_mode) {
+                                    int gout_mode, __nv_bfloat16* __restrict__ dXhi, __nv_bfloat16* __restrict__ dXlo, int lds) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n4) return;
   int c4 = (int)(i % cv);
@@ -141,7 +167,8 @@ __global__ void bn_bwd_apply_kernel(const float* dY, int lddy, const float* __re
   o.y = g.y * is.y * (dy.y - db.y * inv_n - (x.y - mu.y) * is.y * dg.y * inv_n);
   o.z = g.z * is.z * (dy.z - db.z * inv_n - (x.z - mu.z) * is.z * dg.z * inv_n);
   o.w = g.w * is.w * (dy.w - db.w * inv_n - (x.w - mu.w) * is.w * dg.w * inv_n);
-  *reinterpret_cast<float4*>(dX + row * lddx + c4 * 4) = o;
+  if (dX) *reinterpret_cast<float4*>(dX + row * lddx + c4 * 4) = o;
+  if (dXhi) store_split4(o, dXhi + row * lds + c4 * 4, dXlo + row * lds + c4 * 4);
 }
 
 inline int chunks_for(int64_t n) { return (int)((n + ROWS_PER_CHUNK - 1) / ROWS_PER_CHUNK); }
@@ -180,28 +207,42 @@ extern "C" int pcb_bn_stats(const float* X, int64_t n, int C, float eps, float m
   return pcb_bn_stats2(X, C, n, C, eps, momentum, mean, invstd, running_mean, running_var, ws, ws_bytes, stream);
 }
 
+extern "C" int pcb_split_rows(const float* X, int ldx, int64_t n, int C, uint16_t* hi, uint16_t* lo, int lds, void* stream) {
+  PCB_ARG(n >= 0 && C >= 4 && C % 4 == 0 && ldx >= C && ldx % 4 == 0 && lds >= C && lds % 4 == 0);
+  if (n == 0) return PCB_OK;
+  PCB_ARG(X && hi && lo);
+  int64_t n4 = n * (C / 4);
+  split_rows_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(X, ldx, n4, C / 4, (__nv_bfloat16*)hi,
+                                                                                   (__nv_bfloat16*)lo, lds);
+  return check_launch("split_rows_kernel");
+}
+
 extern "C" int pcb_bn_apply2(const float* X, int ldx, int64_t n, int C, const float* mean, const float* invstd, const float* gamma,
-                             const float* beta, const float* residual, int ldr, int relu, float* Y, int ldy, void* stream) {
+                             const float* beta, const float* residual, int ldr, int relu, float* Y, int ldy, uint16_t* Yhi,
+                             uint16_t* Ylo, int lds, void* stream) {
   PCB_ARG(n >= 0 && C >= 4 && C % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && ldx >= C && ldy >= C);
   if (n == 0) return PCB_OK;
   PCB_ARG(X && Y && mean && invstd && gamma && beta && (!residual || (ldr >= C && ldr % 4 == 0)));
+  PCB_ARG(!Yhi || (Ylo && lds >= C && lds % 4 == 0));
   int64_t n4 = n * (C / 4);
   bn_apply_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(X, ldx, n4, C / 4, mean, invstd, gamma, beta, residual,
-                                                                                 ldr, relu, Y, ldy);
+                                                                                 ldr, relu, Y, ldy, (__nv_bfloat16*)Yhi,
+                                                                                 (__nv_bfloat16*)Ylo, lds);
   return check_launch("bn_apply_kernel");
 }
 
 extern "C" int pcb_bn_apply(const float* X, int64_t n, int C, const float* mean, const float* invstd, const float* gamma,
                             const float* beta, const float* residual, int relu, float* Y, void* stream) {
-  return pcb_bn_apply2(X, C, n, C, mean, invstd, gamma, beta, residual, C, relu, Y, C, stream);
+  return pcb_bn_apply2(X, C, n, C, mean, invstd, gamma, beta, residual, C, relu, Y, C, nullptr, nullptr, 0, stream);
 }
 
 extern "C" int pcb_bn_backward2(const float* dY, int lddy, const float* X, int ldx, const float* relu_out, int ldm, int64_t n, int C,
                                 const float* mean, const float* invstd, const float* gamma, float* dX, int lddx, float* dgamma,
-                                float* dbeta, int accumulate_param_grads, float* gout, int ldg, int gout_mode, void* ws,
-                                size_t ws_bytes, void* stream) {
-  PCB_ARG(dY && X && mean && invstd && gamma && dX && dgamma && dbeta && ws && n >= 1 && C >= 4 && C % 4 == 0 && C <= 1024);
-  PCB_ARG(lddy >= C && ldx >= C && lddx >= C && lddy % 4 == 0 && ldx % 4 == 0 && lddx % 4 == 0);
+                                float* dbeta, int accumulate_param_grads, float* gout, int ldg, int gout_mode, uint16_t* dXhi,
+                                uint16_t* dXlo, int lds, void* ws, size_t ws_bytes, void* stream) {
+  PCB_ARG(dY && X && mean && invstd && gamma && (dX || dXhi) && dgamma && dbeta && ws && n >= 1 && C >= 4 && C % 4 == 0 && C <= 1024);
+  PCB_ARG(lddy >= C && ldx >= C && lddy % 4 == 0 && ldx % 4 == 0 && (!dX || (lddx >= C && lddx % 4 == 0)));
+  PCB_ARG(!dXhi || (dXlo && lds >= C && lds % 4 == 0));
   PCB_ARG(!relu_out || (ldm >= C && ldm % 4 == 0));
   PCB_ARG(gout_mode == 0 || (gout && ldg >= C && ldg % 4 == 0));
   PCB_ARG(ws_bytes >= pcb_bn_ws_bytes(n, C) - 256);
@@ -217,13 +258,14 @@ extern "C" int pcb_bn_backward2(const float* dY, int lddy, const float* X, int l
   if (int e = check_launch("bn_bwd_finalize_kernel")) return e;
   int64_t n4 = n * (C / 4);
   bn_bwd_apply_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(dY, lddy, X, ldx, relu_out, ldm, n4, C / 4, 1.0f / (float)n, mean,
-                                                                    invstd, gamma, sums + C, sums, dX, lddx, gout, ldg, gout_mode);
+                                                                    invstd, gamma, sums + C, sums, dX, lddx, gout, ldg, gout_mode,
+                                                                    (__nv_bfloat16*)dXhi, (__nv_bfloat16*)dXlo, lds);
   return check_launch("bn_bwd_apply_kernel");
 }
 
 extern "C" int pcb_bn_backward(const float* dY, const float* X, int64_t n, int C, const float* mean, const float* invstd,
                                const float* gamma, float* dX, float* dgamma, float* dbeta, void* ws, size_t ws_bytes,
                                void* stream) {
-  return pcb_bn_backward2(dY, C, X, C, nullptr, 0, n, C, mean, invstd, gamma, dX, C, dgamma, dbeta, 0, nullptr, 0, 0, ws, ws_bytes,
-                          stream);
+  return pcb_bn_backward2(dY, C, X, C, nullptr, 0, n, C, mean, invstd, gamma, dX, C, dgamma, dbeta, 0, nullptr, 0, 0, nullptr, nullptr,
+                          0, ws, ws_bytes, stream);
 }

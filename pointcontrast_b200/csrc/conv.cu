@@ -592,7 +592,11 @@ extern "C" int pcb_weight_prep(const float* W, int K, int Cin, int Cout, uint16_
 }
 
 namespace pcb {
-int launch_conv_tcgen05(const float* X, int ldx, const int32_t* tbl, int64_t tbl_stride, const int* kmap, int K, int64_t n_out,
+int launch_wgrad_tcgen05(const uint16_t* Ahi, const uint16_t* Alo, int lda, const uint16_t* Bhi, const uint16_t* Blo, int ldb,
+                         const int32_t* tbl, int64_t tbl_stride, int K, int64_t n_out, int Ca, int Cb, int rows_per_split, int splits,
+                         float* partial, int transpose_out, int tn, cudaStream_t st);
+int launch_conv_tcgen05(const float* X, int ldx, const uint16_t* Xhi, const uint16_t* Xlo, int lds, const int32_t* tbl,
+                        int64_t tbl_stride, const int* kmap, int K, int64_t n_out,
                         int Cin, int Cout, const uint16_t* wk_hi, const uint16_t* wk_lo, const float* bias, float* Y, int ldy,
                         float* partial, int nsplit, int bn, int accumulate, cudaStream_t st);
 }
@@ -634,7 +638,7 @@ extern "C" int pcb_conv_forward(const float* X, int ldx, const int32_t* tbl, int
   }
   const int accumulate = (flags & PCB_CONV_ACCUMULATE) ? 1 : 0;
   if ((flags & PCB_CONV_TCGEN05) && wk_hi && wk_lo && ldy % 4 == 0) {
-    if (int e = launch_conv_tcgen05(X, ldx, tbl, tbl_stride, km.v, K, n_out, Cin, Cout, wk_hi, wk_lo, bias, Y, ldy,
+    if (int e = launch_conv_tcgen05(X, ldx, nullptr, nullptr, 0, tbl, tbl_stride, km.v, K, n_out, Cin, Cout, wk_hi, wk_lo, bias, Y, ldy,
                                     nsplit > 1 ? (float*)ws : nullptr, nsplit, pick_tile(Cout), accumulate, st)) return e;
     if (nsplit > 1) {
       int64_t n4 = n_out * (Cout / 4);
@@ -697,6 +701,73 @@ extern "C" int pcb_conv_wgrad(const float* A, int lda, const float* B, int ldb, 
     WG_CASE(32, 128);  WG_CASE(32, 96);  WG_CASE(32, 64);  WG_CASE(32, 32);
   }
   if (rc) return rc;
+  wgrad_reduce_kernel<<<(unsigned)((nW + 255) / 256), 256, 0, st>>>((const float*)ws, splits, nW, dW,
+                                                                    (flags & PCB_CONV_ACCUMULATE) ? 1 : 0);
+  return check_launch("wgrad_reduce_kernel");
+}
+
+
+// ------------------------------------------------------------------------------------------------ split-operand entry points
+extern "C" int pcb_conv_forward_split(const uint16_t* Xhi, const uint16_t* Xlo, int lds, const int32_t* tbl, int64_t tbl_stride,
+                                      const int32_t* kmap, int K, int64_t n_out, int Cin, int Cout, const uint16_t* wk_hi,
+                                      const uint16_t* wk_lo, const float* bias, float* Y, int ldy, void* ws, size_t ws_bytes,
+                                      int flags, void* stream) {
+  PCB_ARG(K >= 1 && K <= PCB_MAX_KERNEL_VOLUME && n_out >= 0 && Cin % 32 == 0 && Cout % 32 == 0 && Cin >= 32 && Cout >= 32);
+  PCB_ARG(lds >= Cin && lds % 8 == 0 && ldy >= Cout && ldy % 4 == 0);
+  if (n_out == 0) return PCB_OK;
+  PCB_ARG(Xhi && Xlo && tbl && Y && wk_hi && wk_lo && tbl_stride >= n_out);
+  cudaStream_t st = (cudaStream_t)stream;
+  int km[PCB_MAX_KERNEL_VOLUME];
+  for (int k = 0; k < K; ++k) { km[k] = kmap ? kmap[k] : k; PCB_ARG(km[k] >= 0 && km[k] < PCB_MAX_KERNEL_VOLUME); }
+  const int accumulate = (flags & PCB_CONV_ACCUMULATE) ? 1 : 0;
+  const int nsplit = conv_splits(K, n_out, Cin, Cout);
+  if (nsplit > 1) PCB_ARG(ws && ws_bytes >= (size_t)nsplit * n_out * Cout * sizeof(float));
+  if (int e = launch_conv_tcgen05(nullptr, 0, Xhi, Xlo, lds, tbl, tbl_stride, km, K, n_out, Cin, Cout, wk_hi, wk_lo, bias, Y, ldy,
+                                  nsplit > 1 ? (float*)ws : nullptr, nsplit, pick_tile(Cout), accumulate, st)) return e;
+  if (nsplit > 1) {
+    int64_t n4 = n_out * (Cout / 4);
+    conv_split_reduce_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>((const float*)ws, nsplit, n_out, Cout, bias, Y, ldy, accumulate);
+    return check_launch("conv_split_reduce_kernel");
+  }
+  return PCB_OK;
+}
+
+namespace {
+int wgrad_split_splits(int K, int64_t n_out, int Ca, int Cb) {
+  int tn = pick_tile(Cb);
+  int64_t base = (int64_t)K * ((Ca + 127) / 128) * (Cb / tn);
+  int64_t s = (4ll * num_sms() + base - 1) / base;
+  int64_t max_s = (n_out + 255) / 256;
+  if (s > max_s) s = max_s;
+  if (s < 1) s = 1;
+  if (s > 64) s = 64;
+  return (int)s;
+}
+}  // namespace
+
+extern "C" size_t pcb_conv_wgrad_split_ws_bytes(int K, int64_t n_out, int Ca, int Cb) {
+  if (Ca % 32 || Cb % 32 || n_out <= 0) return 256;
+  return (size_t)wgrad_split_splits(K, n_out, Ca, Cb) * K * Ca * Cb * sizeof(float) + 256;
+}
+
+extern "C" int pcb_conv_wgrad_split(const uint16_t* Ahi, const uint16_t* Alo, int lda, const uint16_t* Bhi, const uint16_t* Blo, int ldb,
+                                    const int32_t* tbl, int64_t tbl_stride, int K, int64_t n_out, int Ca, int Cb, float* dW,
+                                    int transpose_out, void* ws, size_t ws_bytes, int flags, void* stream) {
+  PCB_ARG(K >= 1 && K <= PCB_MAX_KERNEL_VOLUME && n_out >= 0 && Ca % 32 == 0 && Cb % 32 == 0 && Ca >= 32 && Cb >= 32 && dW);
+  PCB_ARG(lda >= Ca && ldb >= Cb && lda % 8 == 0 && ldb % 8 == 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t nW = (int64_t)K * Ca * Cb;
+  if (n_out == 0) {
+    if (!(flags & PCB_CONV_ACCUMULATE)) PCB_CUDA(cudaMemsetAsync(dW, 0, nW * sizeof(float), st));
+    return PCB_OK;
+  }
+  PCB_ARG(Ahi && Alo && Bhi && Blo && tbl && ws && tbl_stride >= n_out);
+  const int splits = wgrad_split_splits(K, n_out, Ca, Cb);
+  PCB_ARG(ws_bytes >= (size_t)splits * nW * sizeof(float));
+  int64_t rps = (n_out + splits - 1) / splits;
+  rps = (rps + 31) / 32 * 32;
+  if (int e = launch_wgrad_tcgen05(Ahi, Alo, lda, Bhi, Blo, ldb, tbl, tbl_stride, K, n_out, Ca, Cb, (int)rps, splits, (float*)ws,
+                                   transpose_out, pick_tile(Cb), st)) return e;
   wgrad_reduce_kernel<<<(unsigned)((nW + 255) / 256), 256, 0, st>>>((const float*)ws, splits, nW, dW,
                                                                     (flags & PCB_CONV_ACCUMULATE) ? 1 : 0);
   return check_launch("wgrad_reduce_kernel");

@@ -23,6 +23,9 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src));
 }
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, uint32_t src_bytes) {   // src_bytes 16 or 0
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(src_bytes));
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
@@ -81,6 +84,7 @@ constexpr int A_PLANE = (BK / 8) * A_LBO;
 
 struct Args {
   const float* X; int ldx;
+  const __nv_bfloat16* Xhi; const __nv_bfloat16* Xlo; int lds;      // SPLIT kernels: the input as bf16 hi/lo planes
   const int32_t* tbl; int64_t tbl_stride;
   int kmap[PCB_MAX_KERNEL_VOLUME]; int K;
   int64_t n_out; int Cin; int Cout;
@@ -104,7 +108,7 @@ struct Smem {
   static constexpr int TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
 };
 
-template <int BN>
+template <int BN, bool SPLIT>
 __global__ void __launch_bounds__(NTHR, 2) conv_tcgen05_kernel(const Args p) {
   using S = Smem<BN>;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -175,6 +179,19 @@ __global__ void __launch_bounds__(NTHR, 2) conv_tcgen05_kernel(const Args p) {
   };
   auto load_A = [&](int it, float4 (&v)[4]) {
     const int k = s_klist[it / nkc], kc = it % nkc;
+    if (SPLIT) {       // pure asynchronous copy: 128 rows x 4 chunks x 2 planes, zero-filled where there is no neighbour
+      const int stage = (it - it0) % NS;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = tid + i * NTHR;
+        const int plane = c >> 9, rem = c & 511, r = rem >> 2, k8 = rem & 3;
+        const int idx = s_idx[k * BM + r];
+        const __nv_bfloat16* src = (plane ? p.Xlo : p.Xhi) + (int64_t)(idx >= 0 ? idx : 0) * p.lds + kc * BK + k8 * 8;
+        const uint32_t dst = smem_base + stage * S::STAGE + plane * A_PLANE + k8 * A_LBO + (r >> 3) * A_SBO + (r & 7) * 16;
+        cp_async16_zfill(dst, src, idx >= 0 ? 16u : 0u);
+      }
+      return;
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       int idx = s_idx[k * BM + a_row + 32 * i];
@@ -183,6 +200,7 @@ __global__ void __launch_bounds__(NTHR, 2) conv_tcgen05_kernel(const Args p) {
     }
   };
   auto store_A = [&](int stage, const float4 (&v)[4]) {
+    if (SPLIT) return;
     unsigned char* base = smem + stage * S::STAGE + (a_chunk >> 1) * A_LBO + (a_chunk & 1) * 8;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -197,8 +215,8 @@ __global__ void __launch_bounds__(NTHR, 2) conv_tcgen05_kernel(const Args p) {
 
   if (it1 > it0) {
     float4 v[4];
+    load_A(it0, v);          // SPLIT: cp.async into stage 0 (joins the commit group closed by load_B)
     load_B(0, it0);
-    load_A(it0, v);
     for (int it = it0; it < it1; ++it) {
       const int i = it - it0;
       const int s = i % NS;
@@ -207,8 +225,8 @@ __global__ void __launch_bounds__(NTHR, 2) conv_tcgen05_kernel(const Args p) {
       if (more) {
         const int s1 = (i + 1) % NS, u1 = (i + 1) / NS;
         if (u1 >= 1) mbar_wait(bar_base + 8 * s1, (u1 - 1) & 1);     // the MMAs that read stage s1 have retired
-        load_B(s1, it + 1);
         load_A(it + 1, v);
+        load_B(s1, it + 1);
         cp_async_wait<1>();
       } else {
         cp_async_wait<0>();
@@ -276,27 +294,34 @@ __global__ void __launch_bounds__(NTHR, 2) conv_tcgen05_kernel(const Args p) {
   }
 }
 
-template <int BN>
-int launch(const Args& a, int nsplit, cudaStream_t st) {
+template <int BN, bool SPLIT>
+int launch2(const Args& a, int nsplit, cudaStream_t st) {
   using S = Smem<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    PCB_CUDA(cudaFuncSetAttribute(conv_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    PCB_CUDA(cudaFuncSetAttribute(conv_tcgen05_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     attr_set = true;
   }
   dim3 grid((unsigned)((a.n_out + BM - 1) / BM), a.Cout / BN, nsplit);
-  conv_tcgen05_kernel<BN><<<grid, NTHR, S::TOTAL, st>>>(a);
-  return check_launch("conv_tcgen05_kernel");
+  conv_tcgen05_kernel<BN, SPLIT><<<grid, NTHR, S::TOTAL, st>>>(a);
+  return check_launch(SPLIT ? "conv_tcgen05_kernel<split>" : "conv_tcgen05_kernel");
+}
+
+template <int BN>
+int launch(const Args& a, int nsplit, cudaStream_t st) {
+  return a.Xhi ? launch2<BN, true>(a, nsplit, st) : launch2<BN, false>(a, nsplit, st);
 }
 
 }  // namespace tc5
 
 // Called by pcb_conv_forward (conv.cu).  wk_*: K-major split weights [K][Cout][Cin] for this call's roles.
-int launch_conv_tcgen05(const float* X, int ldx, const int32_t* tbl, int64_t tbl_stride, const int* kmap, int K, int64_t n_out,
+int launch_conv_tcgen05(const float* X, int ldx, const uint16_t* Xhi, const uint16_t* Xlo, int lds, const int32_t* tbl,
+                        int64_t tbl_stride, const int* kmap, int K, int64_t n_out,
                         int Cin, int Cout, const uint16_t* wk_hi, const uint16_t* wk_lo, const float* bias, float* Y, int ldy,
                         float* partial, int nsplit, int bn, int accumulate, cudaStream_t st) {
   tc5::Args a;
   a.accumulate = accumulate;
+  a.Xhi = (const __nv_bfloat16*)Xhi; a.Xlo = (const __nv_bfloat16*)Xlo; a.lds = lds;
   a.X = X; a.ldx = ldx; a.tbl = tbl; a.tbl_stride = tbl_stride; a.K = K; a.n_out = n_out; a.Cin = Cin; a.Cout = Cout;
   for (int k = 0; k < K; ++k) a.kmap[k] = kmap[k];
   a.wk_hi = (const __nv_bfloat16*)wk_hi; a.wk_lo = (const __nv_bfloat16*)wk_lo; a.bias = bias; a.Y = Y; a.ldy = ldy;
@@ -306,6 +331,201 @@ int launch_conv_tcgen05(const float* X, int ldx, const int32_t* tbl, int64_t tbl
     case 96: return tc5::launch<96>(a, nsplit, st);
     case 64: return tc5::launch<64>(a, nsplit, st);
     default: return tc5::launch<32>(a, nsplit, st);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ weight gradient
+// dW[k] (Ca x Cb) = sum_j A[tbl[k][j], :]^T . B[j, :] on split (bf16 hi/lo) operands.
+// UMMA view: D[M = Ca-block (padded to 128)][N = Cb-block] += A_op[M x K] . B_op[K x N] with K = table rows.
+// Both operands are MN-major in shared memory (a row of the gathered matrix is contiguous along channels):
+//   core matrix = 8 rows (K) x 16 B (8 channels); channel-chunk stride SBO = 128 B, 8-row-group stride LBO.
+// grid: x = K * mblocks * nblocks, y = row splits; partial tiles are reduced by wgrad_reduce_kernel (conv.cu).
+namespace wg {
+
+constexpr int WM = 128, WK = 32, NTHR = 256, NS = 3;
+constexpr int A_LBO = (WM / 8) * 128 + 16;
+constexpr int A_PLANE = (WK / 8) * A_LBO;
+
+struct Args {
+  const __nv_bfloat16* Ahi; const __nv_bfloat16* Alo; int lda;      // gathered operand (elements)
+  const __nv_bfloat16* Bhi; const __nv_bfloat16* Blo; int ldb;      // row-aligned operand
+  const int32_t* tbl; int64_t tbl_stride;
+  int K; int64_t n_out; int Ca; int Cb; int rows_per_split;
+  float* partial; int transpose_out;
+};
+
+template <int TN>
+struct Smem {
+  static constexpr int B_LBO = (TN / 8) * 128 + 16;
+  static constexpr int B_PLANE = (WK / 8) * B_LBO;
+  static constexpr int STAGE = 2 * A_PLANE + 2 * B_PLANE;
+  static constexpr int BAR_OFF = NS * STAGE;
+  static constexpr int TOTAL = BAR_OFF + (NS + 1) * 8 + 32;
+  static constexpr int TMEM_COLS = TN <= 32 ? 32 : (TN <= 64 ? 64 : 128);
+};
+
+template <int TN>
+__global__ void __launch_bounds__(NTHR, 2) wgrad_tcgen05_kernel(const Args p) {
+  using namespace tc5;
+  using S = Smem<TN>;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int mblocks = (p.Ca + WM - 1) / WM, nblocks = p.Cb / TN;
+  int bx = blockIdx.x;
+  const int nb = bx % nblocks; bx /= nblocks;
+  const int mb = bx % mblocks; bx /= mblocks;
+  const int k = bx;
+  const int m0 = mb * WM, n0 = nb * TN;
+  const int mrows = min(WM, p.Ca - m0);                 // valid M rows of this block (multiple of 32)
+  const int64_t r_begin = (int64_t)blockIdx.y * p.rows_per_split;
+  const int64_t r_end = min(p.n_out, r_begin + p.rows_per_split);
+  const int nsteps = r_end > r_begin ? (int)((r_end - r_begin + WK - 1) / WK) : 0;
+  const int32_t* trow = p.tbl + (int64_t)k * p.tbl_stride;
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bar_base = smem_base + S::BAR_OFF;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + S::BAR_OFF + (NS + 1) * 8);
+
+  if (tid == 0) {
+    for (int i = 0; i <= NS; ++i) mbar_init(bar_base + 8 * i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(s_tmem)), "r"(S::TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
+  }
+  // the A tile rows [mrows, 128) are never written by the copies: zero them once in every stage (finite inputs only)
+  for (int e = tid; e < NS * S::STAGE / 16; e += NTHR) reinterpret_cast<uint4*>(smem)[e] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = *s_tmem;
+  // MN-major A and B (bits 15, 16), bf16 inputs, fp32 accumulate, M = 128, N = TN
+  constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(TN >> 3) << 17) |
+                             ((uint32_t)(WM >> 4) << 24);
+  const int ach = mrows / 8;              // 16-byte chunks per gathered row
+  constexpr int BCH = TN / 8;
+
+  auto issue = [&](int stage, int step) {
+    const int64_t rbase = r_begin + (int64_t)step * WK;
+    const uint32_t sb = smem_base + stage * S::STAGE;
+    for (int c = tid; c < 2 * WK * ach; c += NTHR) {
+      const int plane = c / (WK * ach), rem = c - plane * (WK * ach);
+      const int r = rem / ach, mc = rem - r * ach;
+      const int64_t row = rbase + r;
+      const int idx = row < r_end ? trow[row] : -1;
+      const __nv_bfloat16* src = (plane ? p.Alo : p.Ahi) + (int64_t)(idx >= 0 ? idx : 0) * p.lda + m0 + mc * 8;
+      cp_async16_zfill(sb + plane * A_PLANE + (r >> 3) * A_LBO + mc * 128 + (r & 7) * 16, src, idx >= 0 ? 16u : 0u);
+    }
+    for (int c = tid; c < 2 * WK * BCH; c += NTHR) {
+      const int plane = c / (WK * BCH), rem = c - plane * (WK * BCH);
+      const int r = rem / BCH, nc = rem - r * BCH;
+      const int64_t row = rbase + r;
+      const bool ok = row < r_end && trow[row] >= 0;
+      const __nv_bfloat16* src = (plane ? p.Blo : p.Bhi) + (ok ? row : 0) * p.ldb + n0 + nc * 8;
+      cp_async16_zfill(sb + 2 * A_PLANE + plane * S::B_PLANE + (r >> 3) * S::B_LBO + nc * 128 + (r & 7) * 16, src, ok ? 16u : 0u);
+    }
+    cp_async_commit();
+  };
+
+  if (nsteps > 0) {
+    issue(0, 0);
+    for (int i = 0; i < nsteps; ++i) {
+      const int s = i % NS;
+      const bool more = i + 1 < nsteps;
+      if (more) {
+        const int s1 = (i + 1) % NS, u1 = (i + 1) / NS;
+        if (u1 >= 1) mbar_wait(bar_base + 8 * s1, (u1 - 1) & 1);
+        issue(s1, i + 1);
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        const uint32_t a_hi = smem_base + s * S::STAGE, a_lo = a_hi + A_PLANE;
+        const uint32_t b_hi = a_hi + 2 * A_PLANE, b_lo = b_hi + S::B_PLANE;
+#pragma unroll
+        for (int j = 0; j < WK / 16; ++j) {
+          const uint64_t dah = make_desc(a_hi + j * 2 * A_LBO, A_LBO, 128), dal = make_desc(a_lo + j * 2 * A_LBO, A_LBO, 128);
+          const uint64_t dbh = make_desc(b_hi + j * 2 * S::B_LBO, S::B_LBO, 128), dbl = make_desc(b_lo + j * 2 * S::B_LBO, S::B_LBO, 128);
+          tc_mma(tmem_acc, dal, dbh, IDESC, (i > 0 || j > 0) ? 1u : 0u);
+          tc_mma(tmem_acc, dah, dbl, IDESC, 1u);
+          tc_mma(tmem_acc, dah, dbh, IDESC, 1u);
+        }
+        tc_commit(bar_base + 8 * s);
+        if (!more) tc_commit(bar_base + 8 * NS);
+      }
+    }
+    mbar_wait(bar_base + 8 * NS, 0);
+    tc_fence_after();
+  }
+
+  // ---- epilogue: accumulator row m = TMEM lane, column n -> partial tile
+  float* out = p.partial + ((int64_t)blockIdx.y * p.K + k) * (int64_t)p.Ca * p.Cb;
+  const int q = warp & 3, half = warp >> 2;
+  const int m = q * 32 + lane;
+  constexpr int HALF = TN / 2;
+#pragma unroll
+  for (int c0 = 0; c0 < HALF; c0 += 16) {
+    const int col = half * HALF + c0;
+    uint32_t r[16];
+    if (nsteps > 0) {
+      tc_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)col, r);
+      tc_ld_wait();
+    } else {
+#pragma unroll
+      for (int e = 0; e < 16; ++e) r[e] = 0u;
+    }
+    if (m < mrows) {
+      if (!p.transpose_out) {
+        float* dst = out + (int64_t)(m0 + m) * p.Cb + n0 + col;
+#pragma unroll
+        for (int e = 0; e < 16; e += 4)
+          *reinterpret_cast<float4*>(dst + e) = make_float4(__uint_as_float(r[e]), __uint_as_float(r[e + 1]), __uint_as_float(r[e + 2]),
+                                                            __uint_as_float(r[e + 3]));
+      } else {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) out[(int64_t)(n0 + col + e) * p.Ca + m0 + m] = __uint_as_float(r[e]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_acc), "r"(S::TMEM_COLS));
+}
+
+template <int TN>
+int launch(const Args& a, int splits, cudaStream_t st) {
+  using S = Smem<TN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PCB_CUDA(cudaFuncSetAttribute(wgrad_tcgen05_kernel<TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)(a.K * ((a.Ca + WM - 1) / WM) * (a.Cb / TN)), splits);
+  wgrad_tcgen05_kernel<TN><<<grid, NTHR, S::TOTAL, st>>>(a);
+  return check_launch("wgrad_tcgen05_kernel");
+}
+
+}  // namespace wg
+
+int launch_wgrad_tcgen05(const uint16_t* Ahi, const uint16_t* Alo, int lda, const uint16_t* Bhi, const uint16_t* Blo, int ldb,
+                         const int32_t* tbl, int64_t tbl_stride, int K, int64_t n_out, int Ca, int Cb, int rows_per_split, int splits,
+                         float* partial, int transpose_out, int tn, cudaStream_t st) {
+  wg::Args a;
+  a.Ahi = (const __nv_bfloat16*)Ahi; a.Alo = (const __nv_bfloat16*)Alo; a.lda = lda;
+  a.Bhi = (const __nv_bfloat16*)Bhi; a.Blo = (const __nv_bfloat16*)Blo; a.ldb = ldb;
+  a.tbl = tbl; a.tbl_stride = tbl_stride; a.K = K; a.n_out = n_out; a.Ca = Ca; a.Cb = Cb; a.rows_per_split = rows_per_split;
+  a.partial = partial; a.transpose_out = transpose_out;
+  switch (tn) {
+    case 128: return wg::launch<128>(a, splits, st);
+    case 96: return wg::launch<96>(a, splits, st);
+    case 64: return wg::launch<64>(a, splits, st);
+    default: return wg::launch<32>(a, splits, st);
   }
 }
 

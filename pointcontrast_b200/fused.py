@@ -24,31 +24,40 @@ ENABLED = True
 
 
 class Buf:
-    """fp32 matrix [n, C] with row stride ld (floats); `owner` keeps the storage alive."""
-    __slots__ = ("owner", "p", "n", "C", "ld", "slot", "_grad", "parent", "col")
+    """Matrix [n, C] with row stride ld.  `p`: fp32 storage (or 0), `hi`/`lo`: the same values as bf16 split planes (or 0)
+    -- the operand format of the tensor-core kernels.  `owner` keeps the storages alive."""
+    __slots__ = ("owner", "p", "hi", "lo", "n", "C", "ld", "slot", "_grad", "parent", "col", "device")
 
-    def __init__(self, owner, p, n, C, ld, parent=None, col=0):
-        self.owner, self.p, self.n, self.C, self.ld = owner, p, n, C, ld
+    def __init__(self, owner, p, n, C, ld, device, hi=0, lo=0, parent=None, col=0):
+        self.owner, self.p, self.hi, self.lo, self.n, self.C, self.ld, self.device = owner, p, hi, lo, n, C, ld, device
         self.parent, self.col = parent, col
         self._grad = None
         self.slot = parent.slot if parent is not None else [False]     # [gradient buffer initialised?]
 
     @staticmethod
-    def new(n, C, device):
-        t = torch.empty(n * C, dtype=torch.float32, device=device)
-        return Buf(t, t.data_ptr(), n, C, C)
+    def new(n, C, device, fp32=True, split=False):
+        own, p, hi, lo = [], 0, 0, 0
+        if fp32:
+            t = torch.empty(n * C, dtype=torch.float32, device=device)
+            own.append(t); p = t.data_ptr()
+        if split:
+            t2 = torch.empty(2, n * C, dtype=torch.bfloat16, device=device)
+            own.append(t2); hi = t2.data_ptr(); lo = hi + 2 * n * C
+        return Buf(own, p, n, C, C, device, hi, lo)
 
     def cols(self, c0, C):
-        return Buf(self.owner, self.p + 4 * c0, self.n, C, self.ld, parent=self, col=c0)
+        return Buf(self.owner, self.p + 4 * c0 if self.p else 0, self.n, C, self.ld, self.device, self.hi + 2 * c0 if self.hi else 0,
+                   self.lo + 2 * c0 if self.lo else 0, parent=self, col=c0)
 
     def grad(self):
+        """fp32 gradient buffer with the same geometry (column slices share their parent's buffer)."""
         if self._grad is None:
             if self.parent is not None:
                 g = self.parent.grad()
-                self._grad = Buf(g.owner, g.p + 4 * self.col, self.n, self.C, g.ld)
+                self._grad = Buf(g.owner, g.p + 4 * self.col, self.n, self.C, g.ld, self.device)
             else:
-                t = torch.empty(self.n * self.ld, dtype=torch.float32, device=self.owner.device)
-                self._grad = Buf(t, t.data_ptr(), self.n, self.C, self.ld)
+                t = torch.empty(self.n * self.ld, dtype=torch.float32, device=self.device)
+                self._grad = Buf([t], t.data_ptr(), self.n, self.C, self.ld, self.device)
         return self._grad
 
 
@@ -79,12 +88,13 @@ class Runner:
         st = stream()
         if Cin % 32 == 0 and Cout % 32 == 0:
             pl = conv._prepared.get(kern)
-            hi, lo, khi, klo = (pl[2], pl[3], pl[0], pl[1]) if transposed_roles else (pl[0], pl[1], pl[2], pl[3])
-            flags = 2 | (4 if accumulate else 0)
+            khi, klo = (pl[0], pl[1]) if transposed_roles else (pl[2], pl[3])       # K-major planes for this call's roles
+            flags = 4 if accumulate else 0
             wsb = lib.pcb_conv_forward_ws_bytes(K, n_out, Cin, Cout)
             ws = me.workspace(wsb, self.device, slot=2)
-            check(lib.pcb_conv_forward(x.p, x.ld, ptr(tbl), tbl.shape[1], kmap, K, n_out, Cin, Cout, ptr(hi), ptr(lo), ptr(khi),
-                                       ptr(klo), None, ptr(bias), out.p, out.ld, ptr(ws), wsb, flags, st))
+            assert x.hi, "tensor-core conv needs the split planes of its input"
+            check(lib.pcb_conv_forward_split(x.hi, x.lo, x.ld, ptr(tbl), tbl.shape[1], kmap, K, n_out, Cin, Cout, ptr(khi), ptr(klo),
+                                             ptr(bias), out.p, out.ld, ptr(ws), wsb, flags, st))
         else:
             assert not accumulate and not transposed_roles
             check(lib.pcb_conv_forward(x.p, x.ld, ptr(tbl), tbl.shape[1], kmap, K, n_out, Cin, Cout, None, None, None, None,
@@ -99,11 +109,17 @@ class Runner:
             A, B, Ca, Cb, tr, rows = a_in, dz, Cin, Cout, 0, plan.n_out
         else:
             A, B, Ca, Cb, tr, rows = dz, a_in, Cout, Cin, 1, plan.n_in
-        wsb = lib.pcb_conv_wgrad_ws_bytes(K, rows, Ca, Cb)
-        ws = me.workspace(wsb, self.device)
         ev = me._prof_begin()
-        check(lib.pcb_conv_wgrad(A.p, A.ld, B.p, B.ld, ptr(plan.wg_tbl), plan.wg_tbl.shape[1], K, rows, Ca, Cb, kern.grad.data_ptr(),
-                                 tr, ptr(ws), wsb, 4, stream()))
+        if Ca % 32 == 0 and Cb % 32 == 0:
+            wsb = lib.pcb_conv_wgrad_split_ws_bytes(K, rows, Ca, Cb)
+            ws = me.workspace(wsb, self.device)
+            check(lib.pcb_conv_wgrad_split(A.hi, A.lo, A.ld, B.hi, B.lo, B.ld, ptr(plan.wg_tbl), plan.wg_tbl.shape[1], K, rows, Ca, Cb,
+                                           kern.grad.data_ptr(), tr, ptr(ws), wsb, 4, stream()))
+        else:
+            wsb = lib.pcb_conv_wgrad_ws_bytes(K, rows, Ca, Cb)
+            ws = me.workspace(wsb, self.device)
+            check(lib.pcb_conv_wgrad(A.p, A.ld, B.p, B.ld, ptr(plan.wg_tbl), plan.wg_tbl.shape[1], K, rows, Ca, Cb, kern.grad.data_ptr(),
+                                     tr, ptr(ws), wsb, 4, stream()))
         me._prof_end(ev, "wgrad", plan, K, Cin, Cout, Ca % 32 == 0 and Cb % 32 == 0)
 
     # ------------------------------------------------------------------------------------------ forward
@@ -115,7 +131,7 @@ class Runner:
         z = Buf.new(n, Cout, self.device)
         self._conv(a_in, plan.fwd_tbl, _kmap(plan.fwd_kmap), conv, False, n, z, False, plan=plan)
         if out is None:
-            out = Buf.new(n, Cout, self.device)
+            out = Buf.new(n, Cout, self.device, split=True)
         mean = self._stat(Cout)
         invstd = self._stat(Cout)
         wsb = lib.pcb_bn_ws_bytes(n, Cout)
@@ -125,7 +141,7 @@ class Runner:
                                 bn.running_var.data_ptr(), ptr(ws), wsb, st))
         check(lib.pcb_bn_apply2(z.p, z.ld, n, Cout, mean, invstd, bn.weight.data_ptr(), bn.bias.data_ptr(),
                                 residual.p if residual is not None else None, residual.ld if residual is not None else 0,
-                                1 if relu else 0, out.p, out.ld, st))
+                                1 if relu else 0, out.p, out.ld, out.hi or None, out.lo or None, out.ld, st))
         self.bns.append(bn)
         self.tape.append((conv, bn, a_in, z, out, mean, invstd, plan, relu, residual))
         return out
@@ -171,14 +187,14 @@ class Runner:
             p0 = cm.conv_plan(keys[0], keys[0], m.conv0p1s1.kernel_generator, False)
             P = m.PLANES
             x_in = feats.detach().contiguous().float()
-            a0 = Buf(x_in, x_in.data_ptr(), n[0], x_in.shape[1], x_in.shape[1])
+            a0 = Buf([x_in], x_in.data_ptr(), n[0], x_in.shape[1], x_in.shape[1], self.device)
             a0.slot[0] = None                    # network input: no gradient wanted
             dev = self.device
             # concatenation buffers (left = decoder branch, right = encoder skip)
-            cat8 = Buf.new(n[0], P[7] + m.INIT_DIM, dev)
-            cat7 = Buf.new(n[1], P[6] + P[0], dev)
-            cat6 = Buf.new(n[2], P[5] + P[1], dev)
-            cat5 = Buf.new(n[3], P[4] + P[2], dev)
+            cat8 = Buf.new(n[0], P[7] + m.INIT_DIM, dev, split=True)
+            cat7 = Buf.new(n[1], P[6] + P[0], dev, split=True)
+            cat6 = Buf.new(n[2], P[5] + P[1], dev, split=True)
+            cat5 = Buf.new(n[3], P[4] + P[2], dev, split=True)
             out_p1 = self._unit(m.conv0p1s1, m.bn0, a0, p0, True, out=cat8.cols(P[7], m.INIT_DIM))
             x = self._unit(m.conv1p1s2, m.bn1, out_p1, down[0], True)
             b1 = self._stage(m.block1, x, p3[1], p1[1], out=cat7.cols(P[6], P[0]))
@@ -198,7 +214,7 @@ class Runner:
             x = self._stage(m.block8, cat8, p3[0], p1[0])
             fin = m.final
             out_t = torch.empty(n[0], fin.out_channels, dtype=torch.float32, device=dev)
-            out = Buf(out_t, out_t.data_ptr(), n[0], fin.out_channels, fin.out_channels)
+            out = Buf([out_t], out_t.data_ptr(), n[0], fin.out_channels, fin.out_channels, dev)
             self._conv(x, p1[0].fwd_tbl, None, fin, False, n[0], out, False,
                        bias=fin.bias.detach().reshape(-1) if fin.bias is not None else None, plan=p1[0])
             for bn in self.bns:
@@ -216,7 +232,8 @@ class Runner:
         self.device = dev
         with torch.cuda.device(dev):
             fin = m.final
-            dfin = Buf(d_out, d_out.data_ptr(), d_out.shape[0], d_out.shape[1], d_out.shape[1])
+            dfin = Buf.new(d_out.shape[0], d_out.shape[1], dev, fp32=False, split=True)
+            check(lib.pcb_split_rows(d_out.data_ptr(), d_out.shape[1], d_out.shape[0], d_out.shape[1], dfin.hi, dfin.lo, dfin.ld, stream()))
             if fin.bias is not None:
                 if fin.bias.grad is None:
                     fin.bias.grad = torch.zeros_like(fin.bias)
@@ -231,7 +248,8 @@ class Runner:
                 n = plan.n_out
                 g = out.grad()
                 assert out.slot[0], "gradient of a unit output was never produced"
-                dz = Buf.new(n, Cout, dev)
+                tc = Cin % 32 == 0 and Cout % 32 == 0
+                dz = Buf.new(n, Cout, dev, fp32=not tc, split=tc)       # consumed only by the conv kernels: split planes suffice
                 gout_p, gout_ld, gout_mode = None, 0, 0
                 if residual is not None and residual.slot[0] is not None:
                     rg = residual.grad()
@@ -244,8 +262,8 @@ class Runner:
                 wsb = lib.pcb_bn_ws_bytes(n, Cout)
                 ws = me.workspace(wsb, dev)
                 check(lib.pcb_bn_backward2(g.p, g.ld, z.p, z.ld, out.p if relu else None, out.ld, n, Cout, mean, invstd,
-                                           bn.weight.data_ptr(), dz.p, dz.ld, bn.weight.grad.data_ptr(), bn.bias.grad.data_ptr(), 1,
-                                           gout_p, gout_ld, gout_mode, ptr(ws), wsb, st))
+                                           bn.weight.data_ptr(), dz.p or None, dz.ld, bn.weight.grad.data_ptr(), bn.bias.grad.data_ptr(), 1,
+                                           gout_p, gout_ld, gout_mode, dz.hi or None, dz.lo or None, dz.ld, ptr(ws), wsb, st))
                 self._wgrad(conv, plan, a_in, dz)
                 if a_in.slot[0] is not None:
                     ga = a_in.grad()

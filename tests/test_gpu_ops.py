@@ -243,3 +243,67 @@ def test_sgd_matches_torch():
             assert torch.allclose(m.detach().cpu(), r.detach(), rtol=1e-6, atol=1e-7)
     sd = o.state_dict()
     assert sd["param_groups"][0]["momentum"] == 0.8 and len(sd["state"]) == len(shapes)
+
+
+def _split(x):
+    from pointcontrast_b200._lib import check, lib, ptr, stream
+    n, C = x.shape
+    planes = torch.empty(2, n * C, dtype=torch.bfloat16, device="cuda")
+    check(lib.pcb_split_rows(ptr(x), C, n, C, planes[0].data_ptr(), planes[1].data_ptr(), C, stream()))
+    return planes
+
+
+@pytest.mark.parametrize("Ca,Cb,tr", [(96, 96, 0), (128, 96, 0), (32, 32, 0), (64, 64, 1), (256, 256, 0), (384, 256, 0),
+                                       (192, 128, 1), (96, 32, 0), (256, 128, 1), (32, 96, 0)])
+def test_split_operand_wgrad_tcgen05_matches_fp32_input_kernels(Ca, Cb, tr):
+    """tcgen05 weight-gradient on bf16 hi/lo planes (MN-major UMMA operands) vs the mma.sync kernel on fp32 inputs."""
+    from pointcontrast_b200 import me
+    from pointcontrast_b200._lib import check, lib, ptr, stream
+    rng = np.random.default_rng(Ca + Cb)
+    coords = surface_coords(rng, 5000 if Ca * Cb <= 128 * 128 else 1500)
+    st = me.SparseTensor(torch.zeros(len(coords), 1, device="cuda"), coords=torch.from_numpy(coords))
+    kg = me.KernelGenerator(3, 1, 1, region_type=me.RegionType.HYBRID, axis_types=[me.RegionType.HYPERCUBE] * 3, dimension=3)
+    plan = st.coords_man.conv_plan(st.coords_key, st.coords_key, kg, False)
+    n = plan.n_out
+    A = torch.randn(n, Ca, device="cuda"); B = torch.randn(n, Cb, device="cuda")
+    K = 27
+    shape = (K, Cb, Ca) if tr else (K, Ca, Cb)
+    ref = torch.empty(shape, device="cuda"); got = torch.full(shape, 0.5, device="cuda")
+    wsb = lib.pcb_conv_wgrad_ws_bytes(K, n, Ca, Cb); ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+    check(lib.pcb_conv_wgrad(ptr(A), Ca, ptr(B), Cb, ptr(plan.wg_tbl), plan.wg_tbl.shape[1], K, n, Ca, Cb, ptr(ref), tr, ptr(ws), wsb, 0, stream()))
+    As, Bs = _split(A), _split(B)
+    wsb = lib.pcb_conv_wgrad_split_ws_bytes(K, n, Ca, Cb); ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+    check(lib.pcb_conv_wgrad_split(As[0].data_ptr(), As[1].data_ptr(), Ca, Bs[0].data_ptr(), Bs[1].data_ptr(), Cb, ptr(plan.wg_tbl),
+                                   plan.wg_tbl.shape[1], K, n, Ca, Cb, ptr(got), tr, ptr(ws), wsb, 4, stream()))      # accumulate onto 0.5
+    torch.cuda.synchronize()
+    assert max_rel_err(got - 0.5, ref) < 2e-5
+    # and against fp64
+    tbl = plan.wg_tbl.long()
+    k = 5
+    ok = tbl[k] >= 0
+    exact = A.double()[tbl[k][ok]].t() @ B.double()[ok]
+    mine = (got[k] - 0.5).double()
+    assert max_rel_err(mine.t() if tr else mine, exact) < 1e-4
+
+
+@pytest.mark.parametrize("cin,cout", [(96, 96), (128, 96), (32, 64), (256, 256), (384, 256)])
+def test_split_operand_conv_forward_matches_fp32_input_kernel(cin, cout):
+    from pointcontrast_b200 import me
+    from pointcontrast_b200._lib import check, lib, ptr, stream
+    rng = np.random.default_rng(cin + cout)
+    coords = surface_coords(rng, 4000 if cin * cout <= 128 * 128 else 1200)
+    st = me.SparseTensor(torch.zeros(len(coords), 1, device="cuda"), coords=torch.from_numpy(coords))
+    kg = me.KernelGenerator(3, 1, 1, region_type=me.RegionType.HYBRID, axis_types=[me.RegionType.HYPERCUBE] * 3, dimension=3)
+    plan = st.coords_man.conv_plan(st.coords_key, st.coords_key, kg, False)
+    n = plan.n_out
+    X = torch.randn(n, cin, device="cuda"); W = torch.randn(27, cin, cout, device="cuda") * 0.05
+    planes = torch.empty(4, 27 * cin * cout, dtype=torch.int16, device="cuda")
+    check(lib.pcb_weight_prep(ptr(W), 27, cin, cout, ptr(planes[0]), ptr(planes[1]), ptr(planes[2]), ptr(planes[3]), stream()))
+    ref = me._conv_forward_raw(X, plan.fwd_tbl, None, 27, n, cin, cout, planes[0], planes[1], W, None, planes[2], planes[3])
+    Xs = _split(X)
+    got = torch.full((n, cout), 0.25, device="cuda")
+    wsb = lib.pcb_conv_forward_ws_bytes(27, n, cin, cout); ws = torch.empty(max(wsb, 256), dtype=torch.uint8, device="cuda")
+    check(lib.pcb_conv_forward_split(Xs[0].data_ptr(), Xs[1].data_ptr(), cin, ptr(plan.fwd_tbl), plan.fwd_tbl.shape[1], None, 27, n, cin,
+                                     cout, ptr(planes[2]), ptr(planes[3]), None, ptr(got), cout, ptr(ws), wsb, 4, stream()))
+    torch.cuda.synchronize()
+    assert max_rel_err(got - 0.25, ref) < 1e-5
