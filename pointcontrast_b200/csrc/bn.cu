@@ -8,7 +8,7 @@ using namespace pcb;
 
 namespace {
 
-constexpr int ROWS_PER_CHUNK = 512;
+constexpr int ROWS_PER_CHUNK = 128;
 
 // fp32 x4 -> bf16 hi x4 + bf16 lo x4 (x ~= hi + lo to 2^-17): the operand format of the tensor-core conv kernels
 __device__ __forceinline__ void store_split4(const float4& v, __nv_bfloat16* hi, __nv_bfloat16* lo) {
@@ -81,12 +81,21 @@ __global__ void colsum_kernel(const float* __restrict__ A, int lda, const float*
   }
 }
 
+// one warp per channel: lanes stride over the row chunks, fp64 shuffle reduction (fixed order: deterministic)
+__device__ __forceinline__ void warp_sum2(const float* __restrict__ partial, int chunks, int C, int c, double& s1, double& s2) {
+  const int lane = threadIdx.x & 31;
+  s1 = 0.0; s2 = 0.0;
+  for (int k = lane; k < chunks; k += 32) { s1 += partial[(int64_t)k * 2 * C + c]; s2 += partial[(int64_t)k * 2 * C + C + c]; }
+  for (int o = 16; o; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+}
+
 __global__ void bn_finalize_kernel(const float* __restrict__ partial, int chunks, int64_t n, int C, float eps, float momentum,
                                    float* __restrict__ mean, float* __restrict__ invstd, float* running_mean, float* running_var) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (c >= C) return;
-  double s1 = 0.0, s2 = 0.0;
-  for (int k = 0; k < chunks; ++k) { s1 += partial[(int64_t)k * 2 * C + c]; s2 += partial[(int64_t)k * 2 * C + C + c]; }
+  double s1, s2;
+  warp_sum2(partial, chunks, C, c, s1, s2);
+  if ((threadIdx.x & 31) != 0) return;
   double m = s1 / (double)n;
   double var = s2 / (double)n - m * m;
   if (var < 0.0) var = 0.0;
@@ -126,10 +135,11 @@ __global__ void bn_apply_kernel(const float* __restrict__ X, int ldx, int64_t n4
 // sums[0][C] = dbeta, sums[1][C] = dgamma for the apply pass; the parameter gradients are written or accumulated
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int chunks, int C, float* __restrict__ dgamma,
                                        float* __restrict__ dbeta, int accumulate, float* __restrict__ sums) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (c >= C) return;
-  double s1 = 0.0, s2 = 0.0;
-  for (int k = 0; k < chunks; ++k) { s1 += partial[(int64_t)k * 2 * C + c]; s2 += partial[(int64_t)k * 2 * C + C + c]; }
+  double s1, s2;
+  warp_sum2(partial, chunks, C, c, s1, s2);
+  if ((threadIdx.x & 31) != 0) return;
   sums[c] = (float)s1;
   sums[C + c] = (float)s2;
   if (accumulate) { dbeta[c] += (float)s1; dgamma[c] += (float)s2; }
@@ -197,7 +207,7 @@ extern "C" int pcb_bn_stats2(const float* X, int ldx, int64_t n, int C, float ep
   colsum_kernel<false><<<chunks, thr, (size_t)rp * 2 * C * sizeof(float), st>>>(X, ldx, nullptr, 0, nullptr, 0, n, C, nullptr, nullptr,
                                                                                  (float*)ws);
   if (int e = check_launch("colsum_kernel")) return e;
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>((const float*)ws, chunks, n, C, eps, momentum, mean, invstd, running_mean,
+  bn_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>((const float*)ws, chunks, n, C, eps, momentum, mean, invstd, running_mean,
                                                       running_var);
   return check_launch("bn_finalize_kernel");
 }
@@ -254,7 +264,7 @@ extern "C" int pcb_bn_backward2(const float* dY, int lddy, const float* X, int l
   float* sums = partial + (size_t)chunks * 2 * C;        // [2][C]: dbeta, dgamma of THIS call (the apply pass needs them)
   colsum_kernel<true><<<chunks, thr, (size_t)rp * 2 * C * sizeof(float), st>>>(dY, lddy, X, ldx, relu_out, ldm, n, C, mean, invstd, partial);
   if (int e = check_launch("colsum_kernel<bwd>")) return e;
-  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(partial, chunks, C, dgamma, dbeta, accumulate_param_grads, sums);
+  bn_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(partial, chunks, C, dgamma, dbeta, accumulate_param_grads, sums);
   if (int e = check_launch("bn_bwd_finalize_kernel")) return e;
   int64_t n4 = n * (C / 4);
   bn_bwd_apply_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(dY, lddy, X, ldx, relu_out, ldm, n4, C / 4, 1.0f / (float)n, mean,

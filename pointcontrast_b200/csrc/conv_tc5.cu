@@ -43,6 +43,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
                  : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
   } while (!ok);
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
 }
@@ -294,6 +297,197 @@ __global__ void __launch_bounds__(NTHR, 2) conv_tcgen05_kernel(const Args p) {
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ split-operand forward, deep pipeline
+// Warp-specialised: warps 0-7 are copy producers (cp.async of the gathered hi/lo rows + the weight tile, DEPTH stages in
+// flight, never blocked by MMA issue), warp 8 issues the tcgen05.mma's.  Hand-off through mbarriers only:
+//   full[s]  : 256 producer arrivals (each after its own copies of stage s have landed + fence.proxy.async)
+//   empty[s] : tcgen05.commit of the MMAs that read stage s
+// One CTA per SM (the 6-stage ring fills the shared memory), accumulators in TMEM, same epilogue as above.
+constexpr int DNS = 6, DEPTH = 4, DTHR = 288;
+
+template <int BN>
+struct DSmem {
+  static constexpr int B_SBO = 128;
+  static constexpr int B_LBO = (BN / 8) * 128 + 16;
+  static constexpr int B_PLANE = (BK / 8) * B_LBO;
+  static constexpr int STAGE = 2 * A_PLANE + 2 * B_PLANE;
+  static constexpr int IDX_OFF = DNS * STAGE;
+  static constexpr int META_OFF = IDX_OFF + PCB_MAX_KERNEL_VOLUME * BM * 4;
+  static constexpr int BAR_OFF = META_OFF + 72 * 4;
+  static constexpr int TOTAL = BAR_OFF + (2 * DNS + 1) * 8 + 16;
+  static constexpr int TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
+};
+
+template <int BN>
+__global__ void __launch_bounds__(DTHR, 1) conv_tcgen05_split_kernel(const Args p) {
+  using S = DSmem<BN>;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t row0 = (int64_t)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  int* s_idx = reinterpret_cast<int*>(smem + S::IDX_OFF);
+  int* s_flag = reinterpret_cast<int*>(smem + S::META_OFF);
+  int* s_klist = s_flag + 32;
+  int* s_nk = s_klist + 32;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_nk + 1);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t full_bar = smem_base + S::BAR_OFF, empty_bar = full_bar + 8 * DNS, done_bar = empty_bar + 8 * DNS;
+
+  if (tid == 0) {
+    for (int i = 0; i < DNS; ++i) { mbar_init(full_bar + 8 * i, 256); mbar_init(empty_bar + 8 * i, 1); }
+    mbar_init(done_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(s_tmem)), "r"(S::TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
+  }
+  for (int e = tid; e < p.K * BM; e += DTHR) {
+    int k = e / BM, r = e - k * BM;
+    int64_t row = row0 + r;
+    int v = -1;
+    if (row < p.n_out) v = p.tbl[(int64_t)p.kmap[k] * p.tbl_stride + row];
+    s_idx[e] = v;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = *s_tmem;
+  for (int k = warp; k < p.K; k += DTHR / 32) {
+    unsigned any = 0;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) any |= __ballot_sync(0xffffffffu, s_idx[k * BM + s * 32 + lane] >= 0);
+    if (lane == 0) s_flag[k] = any ? 1 : 0;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int nk = 0;
+    for (int k = 0; k < p.K; ++k) if (s_flag[k]) s_klist[nk++] = k;
+    *s_nk = nk;
+  }
+  __syncthreads();
+  const int nk = *s_nk;
+  const int nkc = p.Cin / BK;
+  const int T = nk * nkc;
+  const int it0 = (int)((int64_t)T * blockIdx.z / gridDim.z);
+  const int it1 = (int)((int64_t)T * (blockIdx.z + 1) / gridDim.z);
+  const int n_it = it1 - it0;
+  constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+  if (warp < 8) {
+    // ===== copy producers =====
+    auto issue = [&](int stage, int it) {
+      const int k = s_klist[it / nkc], kc = it % nkc;
+      const uint32_t sb = smem_base + stage * S::STAGE;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {                 // A: 128 rows x 4 chunks x 2 planes
+        const int c = tid + i * 256;
+        const int plane = c >> 9, rem = c & 511, r = rem >> 2, k8 = rem & 3;
+        const int idx = s_idx[k * BM + r];
+        const __nv_bfloat16* src = (plane ? p.Xlo : p.Xhi) + (int64_t)(idx >= 0 ? idx : 0) * p.lds + kc * BK + k8 * 8;
+        cp_async16_zfill(sb + plane * A_PLANE + k8 * A_LBO + (r >> 3) * A_SBO + (r & 7) * 16, src, idx >= 0 ? 16u : 0u);
+      }
+      constexpr int PER_PLANE = BN * (BK / 8);
+      for (int c = tid; c < 2 * PER_PLANE; c += 256) {    // B: BN rows x 4 chunks x 2 planes
+        const int plane = c / PER_PLANE, rem = c - plane * PER_PLANE;
+        const int n = rem >> 2, k8 = rem & 3;
+        const __nv_bfloat16* src = (plane ? p.wk_lo : p.wk_hi) + ((int64_t)k * p.Cout + n0 + n) * p.Cin + kc * BK + k8 * 8;
+        cp_async16(sb + 2 * A_PLANE + plane * S::B_PLANE + k8 * S::B_LBO + (n >> 3) * S::B_SBO + (n & 7) * 16, src);
+      }
+    };
+    for (int j = 0; j < DEPTH; ++j) {
+      if (j < n_it) issue(j, it0 + j);
+      cp_async_commit();
+    }
+    for (int i = 0; i < n_it; ++i) {
+      const int nxt = i + DEPTH;
+      if (nxt < n_it) {
+        const int s2 = nxt % DNS, u2 = nxt / DNS;
+        if (u2 >= 1) mbar_wait(empty_bar + 8 * s2, (u2 - 1) & 1);
+        issue(s2, it0 + nxt);
+      }
+      cp_async_commit();
+      cp_async_wait<DEPTH>();            // this thread's copies of stage i have landed
+      fence_proxy_async();
+      mbar_arrive(full_bar + 8 * (i % DNS));
+    }
+  } else if (lane == 0) {
+    // ===== MMA issuer =====
+    for (int i = 0; i < n_it; ++i) {
+      const int s = i % DNS;
+      mbar_wait(full_bar + 8 * s, (i / DNS) & 1);
+      tc_fence_after();
+      const uint32_t a_hi = smem_base + s * S::STAGE, a_lo = a_hi + A_PLANE;
+      const uint32_t b_hi = a_hi + 2 * A_PLANE, b_lo = b_hi + S::B_PLANE;
+#pragma unroll
+      for (int j = 0; j < BK / 16; ++j) {
+        const uint64_t dah = make_desc(a_hi + j * 2 * A_LBO, A_LBO, A_SBO), dal = make_desc(a_lo + j * 2 * A_LBO, A_LBO, A_SBO);
+        const uint64_t dbh = make_desc(b_hi + j * 2 * S::B_LBO, S::B_LBO, S::B_SBO);
+        const uint64_t dbl = make_desc(b_lo + j * 2 * S::B_LBO, S::B_LBO, S::B_SBO);
+        tc_mma(tmem_acc, dal, dbh, IDESC, (i > 0 || j > 0) ? 1u : 0u);
+        tc_mma(tmem_acc, dah, dbl, IDESC, 1u);
+        tc_mma(tmem_acc, dah, dbh, IDESC, 1u);
+      }
+      tc_commit(empty_bar + 8 * s);
+      if (i == n_it - 1) tc_commit(done_bar);
+    }
+  }
+  if (n_it > 0) {
+    mbar_wait(done_bar, 0);
+    tc_fence_after();
+  }
+  if (warp < 8) {
+    float* outp = p.partial ? p.partial + (int64_t)blockIdx.z * p.n_out * p.Cout : p.Y;
+    const int ldo = p.partial ? p.Cout : p.ldy;
+    const float* bias = p.partial ? nullptr : p.bias;
+    const int q = warp & 3, half = warp >> 2;
+    const int64_t row = row0 + q * 32 + lane;
+    constexpr int HALF = BN / 2;
+#pragma unroll
+    for (int c0 = 0; c0 < HALF; c0 += 16) {
+      const int col = half * HALF + c0;
+      uint32_t r[16];
+      if (n_it > 0) {
+        tc_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)col, r);
+        tc_ld_wait();
+      } else {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) r[e] = 0u;
+      }
+      if (row < p.n_out) {
+        float* dst = outp + row * ldo + n0 + col;
+#pragma unroll
+        for (int e = 0; e < 16; e += 4) {
+          float4 o = make_float4(__uint_as_float(r[e]), __uint_as_float(r[e + 1]), __uint_as_float(r[e + 2]), __uint_as_float(r[e + 3]));
+          if (bias) { o.x += bias[n0 + col + e]; o.y += bias[n0 + col + e + 1]; o.z += bias[n0 + col + e + 2]; o.w += bias[n0 + col + e + 3]; }
+          if (p.accumulate && !p.partial) {
+            float4 old = *reinterpret_cast<const float4*>(dst + e);
+            o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+          }
+          *reinterpret_cast<float4*>(dst + e) = o;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_acc), "r"(S::TMEM_COLS));
+}
+
+template <int BN>
+int launch_split(const Args& a, int nsplit, cudaStream_t st) {
+  using S = DSmem<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PCB_CUDA(cudaFuncSetAttribute(conv_tcgen05_split_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)((a.n_out + BM - 1) / BM), a.Cout / BN, nsplit);
+  conv_tcgen05_split_kernel<BN><<<grid, DTHR, S::TOTAL, st>>>(a);
+  return check_launch("conv_tcgen05_split_kernel");
+}
+
 template <int BN, bool SPLIT>
 int launch2(const Args& a, int nsplit, cudaStream_t st) {
   using S = Smem<BN>;
@@ -309,7 +503,7 @@ int launch2(const Args& a, int nsplit, cudaStream_t st) {
 
 template <int BN>
 int launch(const Args& a, int nsplit, cudaStream_t st) {
-  return a.Xhi ? launch2<BN, true>(a, nsplit, st) : launch2<BN, false>(a, nsplit, st);
+  return a.Xhi ? launch_split<BN>(a, nsplit, st) : launch2<BN, false>(a, nsplit, st);
 }
 
 }  // namespace tc5
@@ -342,7 +536,7 @@ int launch_conv_tcgen05(const float* X, int ldx, const uint16_t* Xhi, const uint
 // grid: x = K * mblocks * nblocks, y = row splits; partial tiles are reduced by wgrad_reduce_kernel (conv.cu).
 namespace wg {
 
-constexpr int WM = 128, WK = 32, NTHR = 256, NS = 3;
+constexpr int WM = 128, WK = 32, NTHR = 288, NS = 6, DEPTH = 4;
 constexpr int A_LBO = (WM / 8) * 128 + 16;
 constexpr int A_PLANE = (WK / 8) * A_LBO;
 
@@ -360,12 +554,13 @@ struct Smem {
   static constexpr int B_PLANE = (WK / 8) * B_LBO;
   static constexpr int STAGE = 2 * A_PLANE + 2 * B_PLANE;
   static constexpr int BAR_OFF = NS * STAGE;
-  static constexpr int TOTAL = BAR_OFF + (NS + 1) * 8 + 32;
+  static constexpr int TOTAL = BAR_OFF + (2 * NS + 1) * 8 + 32;
   static constexpr int TMEM_COLS = TN <= 32 ? 32 : (TN <= 64 ? 64 : 128);
 };
 
+// warps 0-7: copy producers (DEPTH stages in flight); warp 8: MMA issuer; 1 CTA per SM (6-stage ring).
 template <int TN>
-__global__ void __launch_bounds__(NTHR, 2) wgrad_tcgen05_kernel(const Args p) {
+__global__ void __launch_bounds__(NTHR, 1) wgrad_tcgen05_kernel(const Args p) {
   using namespace tc5;
   using S = Smem<TN>;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -382,18 +577,19 @@ __global__ void __launch_bounds__(NTHR, 2) wgrad_tcgen05_kernel(const Args p) {
   const int nsteps = r_end > r_begin ? (int)((r_end - r_begin + WK - 1) / WK) : 0;
   const int32_t* trow = p.tbl + (int64_t)k * p.tbl_stride;
   const uint32_t smem_base = smem_u32(smem);
-  const uint32_t bar_base = smem_base + S::BAR_OFF;
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + S::BAR_OFF + (NS + 1) * 8);
+  const uint32_t full_bar = smem_base + S::BAR_OFF, empty_bar = full_bar + 8 * NS, done_bar = empty_bar + 8 * NS;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + S::BAR_OFF + (2 * NS + 1) * 8);
 
   if (tid == 0) {
-    for (int i = 0; i <= NS; ++i) mbar_init(bar_base + 8 * i, 1);
+    for (int i = 0; i < NS; ++i) { mbar_init(full_bar + 8 * i, 256); mbar_init(empty_bar + 8 * i, 1); }
+    mbar_init(done_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(s_tmem)), "r"(S::TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
   }
-  // the A tile rows [mrows, 128) are never written by the copies: zero them once in every stage (finite inputs only)
+  // the A-tile channel chunks [mrows/8, 16) are never written by the copies: zero every stage once
   for (int e = tid; e < NS * S::STAGE / 16; e += NTHR) reinterpret_cast<uint4*>(smem)[e] = make_uint4(0, 0, 0, 0);
   fence_proxy_async();
   tc_fence_before();
@@ -406,90 +602,95 @@ __global__ void __launch_bounds__(NTHR, 2) wgrad_tcgen05_kernel(const Args p) {
   const int ach = mrows / 8;              // 16-byte chunks per gathered row
   constexpr int BCH = TN / 8;
 
-  auto issue = [&](int stage, int step) {
-    const int64_t rbase = r_begin + (int64_t)step * WK;
-    const uint32_t sb = smem_base + stage * S::STAGE;
-    for (int c = tid; c < 2 * WK * ach; c += NTHR) {
-      const int plane = c / (WK * ach), rem = c - plane * (WK * ach);
-      const int r = rem / ach, mc = rem - r * ach;
-      const int64_t row = rbase + r;
-      const int idx = row < r_end ? trow[row] : -1;
-      const __nv_bfloat16* src = (plane ? p.Alo : p.Ahi) + (int64_t)(idx >= 0 ? idx : 0) * p.lda + m0 + mc * 8;
-      cp_async16_zfill(sb + plane * A_PLANE + (r >> 3) * A_LBO + mc * 128 + (r & 7) * 16, src, idx >= 0 ? 16u : 0u);
+  if (warp < 8) {
+    auto issue = [&](int stage, int step) {
+      const int64_t rbase = r_begin + (int64_t)step * WK;
+      const uint32_t sb = smem_base + stage * S::STAGE;
+      for (int c = tid; c < 2 * WK * ach; c += 256) {
+        const int plane = c / (WK * ach), rem = c - plane * (WK * ach);
+        const int r = rem / ach, mc = rem - r * ach;
+        const int64_t row = rbase + r;
+        const int idx = row < r_end ? trow[row] : -1;
+        const __nv_bfloat16* src = (plane ? p.Alo : p.Ahi) + (int64_t)(idx >= 0 ? idx : 0) * p.lda + m0 + mc * 8;
+        cp_async16_zfill(sb + plane * A_PLANE + (r >> 3) * A_LBO + mc * 128 + (r & 7) * 16, src, idx >= 0 ? 16u : 0u);
+      }
+      for (int c = tid; c < 2 * WK * BCH; c += 256) {
+        const int plane = c / (WK * BCH), rem = c - plane * (WK * BCH);
+        const int r = rem / BCH, nc = rem - r * BCH;
+        const int64_t row = rbase + r;
+        const bool ok = row < r_end && trow[row] >= 0;
+        const __nv_bfloat16* src = (plane ? p.Blo : p.Bhi) + (ok ? row : 0) * p.ldb + n0 + nc * 8;
+        cp_async16_zfill(sb + 2 * A_PLANE + plane * S::B_PLANE + (r >> 3) * S::B_LBO + nc * 128 + (r & 7) * 16, src, ok ? 16u : 0u);
+      }
+    };
+    for (int j = 0; j < DEPTH; ++j) {
+      if (j < nsteps) issue(j, j);
+      cp_async_commit();
     }
-    for (int c = tid; c < 2 * WK * BCH; c += NTHR) {
-      const int plane = c / (WK * BCH), rem = c - plane * (WK * BCH);
-      const int r = rem / BCH, nc = rem - r * BCH;
-      const int64_t row = rbase + r;
-      const bool ok = row < r_end && trow[row] >= 0;
-      const __nv_bfloat16* src = (plane ? p.Blo : p.Bhi) + (ok ? row : 0) * p.ldb + n0 + nc * 8;
-      cp_async16_zfill(sb + 2 * A_PLANE + plane * S::B_PLANE + (r >> 3) * S::B_LBO + nc * 128 + (r & 7) * 16, src, ok ? 16u : 0u);
+    for (int i = 0; i < nsteps; ++i) {
+      const int nxt = i + DEPTH;
+      if (nxt < nsteps) {
+        const int s2 = nxt % NS, u2 = nxt / NS;
+        if (u2 >= 1) mbar_wait(empty_bar + 8 * s2, (u2 - 1) & 1);
+        issue(s2, nxt);
+      }
+      cp_async_commit();
+      cp_async_wait<DEPTH>();
+      fence_proxy_async();
+      mbar_arrive(full_bar + 8 * (i % NS));
     }
-    cp_async_commit();
-  };
-
-  if (nsteps > 0) {
-    issue(0, 0);
+  } else if (lane == 0) {
     for (int i = 0; i < nsteps; ++i) {
       const int s = i % NS;
-      const bool more = i + 1 < nsteps;
-      if (more) {
-        const int s1 = (i + 1) % NS, u1 = (i + 1) / NS;
-        if (u1 >= 1) mbar_wait(bar_base + 8 * s1, (u1 - 1) & 1);
-        issue(s1, i + 1);
-        cp_async_wait<1>();
-      } else {
-        cp_async_wait<0>();
-      }
-      fence_proxy_async();
-      tc_fence_before();
-      __syncthreads();
-      if (tid == 0) {
-        tc_fence_after();
-        const uint32_t a_hi = smem_base + s * S::STAGE, a_lo = a_hi + A_PLANE;
-        const uint32_t b_hi = a_hi + 2 * A_PLANE, b_lo = b_hi + S::B_PLANE;
+      mbar_wait(full_bar + 8 * s, (i / NS) & 1);
+      tc_fence_after();
+      const uint32_t a_hi = smem_base + s * S::STAGE, a_lo = a_hi + A_PLANE;
+      const uint32_t b_hi = a_hi + 2 * A_PLANE, b_lo = b_hi + S::B_PLANE;
 #pragma unroll
-        for (int j = 0; j < WK / 16; ++j) {
-          const uint64_t dah = make_desc(a_hi + j * 2 * A_LBO, A_LBO, 128), dal = make_desc(a_lo + j * 2 * A_LBO, A_LBO, 128);
-          const uint64_t dbh = make_desc(b_hi + j * 2 * S::B_LBO, S::B_LBO, 128), dbl = make_desc(b_lo + j * 2 * S::B_LBO, S::B_LBO, 128);
-          tc_mma(tmem_acc, dal, dbh, IDESC, (i > 0 || j > 0) ? 1u : 0u);
-          tc_mma(tmem_acc, dah, dbl, IDESC, 1u);
-          tc_mma(tmem_acc, dah, dbh, IDESC, 1u);
-        }
-        tc_commit(bar_base + 8 * s);
-        if (!more) tc_commit(bar_base + 8 * NS);
+      for (int j = 0; j < WK / 16; ++j) {
+        const uint64_t dah = make_desc(a_hi + j * 2 * A_LBO, A_LBO, 128), dal = make_desc(a_lo + j * 2 * A_LBO, A_LBO, 128);
+        const uint64_t dbh = make_desc(b_hi + j * 2 * S::B_LBO, S::B_LBO, 128), dbl = make_desc(b_lo + j * 2 * S::B_LBO, S::B_LBO, 128);
+        tc_mma(tmem_acc, dal, dbh, IDESC, (i > 0 || j > 0) ? 1u : 0u);
+        tc_mma(tmem_acc, dah, dbl, IDESC, 1u);
+        tc_mma(tmem_acc, dah, dbh, IDESC, 1u);
       }
+      tc_commit(empty_bar + 8 * s);
+      if (i == nsteps - 1) tc_commit(done_bar);
     }
-    mbar_wait(bar_base + 8 * NS, 0);
+  }
+  if (nsteps > 0) {
+    mbar_wait(done_bar, 0);
     tc_fence_after();
   }
 
   // ---- epilogue: accumulator row m = TMEM lane, column n -> partial tile
-  float* out = p.partial + ((int64_t)blockIdx.y * p.K + k) * (int64_t)p.Ca * p.Cb;
-  const int q = warp & 3, half = warp >> 2;
-  const int m = q * 32 + lane;
-  constexpr int HALF = TN / 2;
+  if (warp < 8) {
+    float* out = p.partial + ((int64_t)blockIdx.y * p.K + k) * (int64_t)p.Ca * p.Cb;
+    const int q = warp & 3, half = warp >> 2;
+    const int m = q * 32 + lane;
+    constexpr int HALF = TN / 2;
 #pragma unroll
-  for (int c0 = 0; c0 < HALF; c0 += 16) {
-    const int col = half * HALF + c0;
-    uint32_t r[16];
-    if (nsteps > 0) {
-      tc_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)col, r);
-      tc_ld_wait();
-    } else {
-#pragma unroll
-      for (int e = 0; e < 16; ++e) r[e] = 0u;
-    }
-    if (m < mrows) {
-      if (!p.transpose_out) {
-        float* dst = out + (int64_t)(m0 + m) * p.Cb + n0 + col;
-#pragma unroll
-        for (int e = 0; e < 16; e += 4)
-          *reinterpret_cast<float4*>(dst + e) = make_float4(__uint_as_float(r[e]), __uint_as_float(r[e + 1]), __uint_as_float(r[e + 2]),
-                                                            __uint_as_float(r[e + 3]));
+    for (int c0 = 0; c0 < HALF; c0 += 16) {
+      const int col = half * HALF + c0;
+      uint32_t r[16];
+      if (nsteps > 0) {
+        tc_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)col, r);
+        tc_ld_wait();
       } else {
 #pragma unroll
-        for (int e = 0; e < 16; ++e) out[(int64_t)(n0 + col + e) * p.Ca + m0 + m] = __uint_as_float(r[e]);
+        for (int e = 0; e < 16; ++e) r[e] = 0u;
+      }
+      if (m < mrows) {
+        if (!p.transpose_out) {
+          float* dst = out + (int64_t)(m0 + m) * p.Cb + n0 + col;
+#pragma unroll
+          for (int e = 0; e < 16; e += 4)
+            *reinterpret_cast<float4*>(dst + e) = make_float4(__uint_as_float(r[e]), __uint_as_float(r[e + 1]), __uint_as_float(r[e + 2]),
+                                                              __uint_as_float(r[e + 3]));
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) out[(int64_t)(n0 + col + e) * p.Ca + m0 + m] = __uint_as_float(r[e]);
+        }
       }
     }
   }
