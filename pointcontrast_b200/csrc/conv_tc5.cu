@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(NTHR, 2) conv_tcgen05_kernel(const Args p) {
 //   full[s]  : 256 producer arrivals (each after its own copies of stage s have landed + fence.proxy.async)
 //   empty[s] : tcgen05.commit of the MMAs that read stage s
 // One CTA per SM (the 6-stage ring fills the shared memory), accumulators in TMEM, same epilogue as above.
-constexpr int DNS = 6, DEPTH = 4, DTHR = 288;
+constexpr int DNS = 6, DEPTH = 4, DPROD = 512, DTHR = DPROD + 32;
 
 template <int BN>
 struct DSmem {
@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(DTHR, 1) conv_tcgen05_split_kernel(const Args 
   const uint32_t full_bar = smem_base + S::BAR_OFF, empty_bar = full_bar + 8 * DNS, done_bar = empty_bar + 8 * DNS;
 
   if (tid == 0) {
-    for (int i = 0; i < DNS; ++i) { mbar_init(full_bar + 8 * i, 256); mbar_init(empty_bar + 8 * i, 1); }
+    for (int i = 0; i < DNS; ++i) { mbar_init(full_bar + 8 * i, DPROD); mbar_init(empty_bar + 8 * i, 1); }
     mbar_init(done_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
@@ -375,26 +375,43 @@ __global__ void __launch_bounds__(DTHR, 1) conv_tcgen05_split_kernel(const Args 
   const int n_it = it1 - it0;
   constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
-  if (warp < 8) {
-    // ===== copy producers =====
-    auto issue = [&](int stage, int it) {
-      const int k = s_klist[it / nkc], kc = it % nkc;
-      const uint32_t sb = smem_base + stage * S::STAGE;
+  if (warp < DPROD / 32) {
+    // ===== copy producers: thread t always moves the same two A chunks (row t>>2, 16-byte chunk t&3, hi and lo plane)
+    // and the same <= 2 weight chunks; per step only the source offsets change.
+    const int ar = tid >> 2, ak8 = tid & 3;
+    const uint32_t a_dst = ak8 * A_LBO + (ar >> 3) * A_SBO + (ar & 7) * 16;
+    constexpr int BCH = 2 * BN * (BK / 8);             // weight chunks per stage (both planes)
+    constexpr int BV = (BCH + DPROD - 1) / DPROD;
+    uint32_t b_dst[BV]; int64_t b_off[BV]; bool b_lo[BV]; bool b_on[BV];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {                 // A: 128 rows x 4 chunks x 2 planes
-        const int c = tid + i * 256;
-        const int plane = c >> 9, rem = c & 511, r = rem >> 2, k8 = rem & 3;
-        const int idx = s_idx[k * BM + r];
-        const __nv_bfloat16* src = (plane ? p.Xlo : p.Xhi) + (int64_t)(idx >= 0 ? idx : 0) * p.lds + kc * BK + k8 * 8;
-        cp_async16_zfill(sb + plane * A_PLANE + k8 * A_LBO + (r >> 3) * A_SBO + (r & 7) * 16, src, idx >= 0 ? 16u : 0u);
+    for (int j = 0; j < BV; ++j) {
+      const int c = tid + j * DPROD;
+      b_on[j] = c < BCH;
+      const int cc = b_on[j] ? c : 0;
+      const int plane = cc / (BN * 4), rem = cc - plane * (BN * 4);
+      const int n = rem >> 2, k8 = rem & 3;
+      b_lo[j] = plane != 0;
+      b_off[j] = (int64_t)(n0 + n) * p.Cin + k8 * 8;
+      b_dst[j] = 2 * A_PLANE + plane * S::B_PLANE + k8 * S::B_LBO + (n >> 3) * S::B_SBO + (n & 7) * 16;
+    }
+    int cur_k = -1;
+    int64_t a_off = 0; uint32_t a_bytes = 0; int64_t w_off = 0;
+    auto issue = [&](int stage, int it) {
+      const int kq = it / nkc, kc = it - kq * nkc;
+      const int k = s_klist[kq];
+      if (k != cur_k) {
+        cur_k = k;
+        const int idx = s_idx[k * BM + ar];
+        a_bytes = idx >= 0 ? 16u : 0u;
+        a_off = (int64_t)(idx >= 0 ? idx : 0) * p.lds + ak8 * 8;
+        w_off = (int64_t)k * p.Cout * p.Cin;
       }
-      constexpr int PER_PLANE = BN * (BK / 8);
-      for (int c = tid; c < 2 * PER_PLANE; c += 256) {    // B: BN rows x 4 chunks x 2 planes
-        const int plane = c / PER_PLANE, rem = c - plane * PER_PLANE;
-        const int n = rem >> 2, k8 = rem & 3;
-        const __nv_bfloat16* src = (plane ? p.wk_lo : p.wk_hi) + ((int64_t)k * p.Cout + n0 + n) * p.Cin + kc * BK + k8 * 8;
-        cp_async16(sb + 2 * A_PLANE + plane * S::B_PLANE + k8 * S::B_LBO + (n >> 3) * S::B_SBO + (n & 7) * 16, src);
-      }
+      const uint32_t sb = smem_base + stage * S::STAGE;
+      cp_async16_zfill(sb + a_dst, p.Xhi + a_off + kc * BK, a_bytes);
+      cp_async16_zfill(sb + A_PLANE + a_dst, p.Xlo + a_off + kc * BK, a_bytes);
+#pragma unroll
+      for (int j = 0; j < BV; ++j)
+        if (b_on[j]) cp_async16(sb + b_dst[j], (b_lo[j] ? p.wk_lo : p.wk_hi) + w_off + b_off[j] + kc * BK);
     };
     for (int j = 0; j < DEPTH; ++j) {
       if (j < n_it) issue(j, it0 + j);
@@ -536,7 +553,7 @@ int launch_conv_tcgen05(const float* X, int ldx, const uint16_t* Xhi, const uint
 // grid: x = K * mblocks * nblocks, y = row splits; partial tiles are reduced by wgrad_reduce_kernel (conv.cu).
 namespace wg {
 
-constexpr int WM = 128, WK = 32, NTHR = 288, NS = 6, DEPTH = 4;
+constexpr int WM = 128, WK = 32, WPROD = 512, NTHR = WPROD + 32, NS = 6, DEPTH = 4;
 constexpr int A_LBO = (WM / 8) * 128 + 16;
 constexpr int A_PLANE = (WK / 8) * A_LBO;
 
@@ -581,7 +598,7 @@ __global__ void __launch_bounds__(NTHR, 1) wgrad_tcgen05_kernel(const Args p) {
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + S::BAR_OFF + (2 * NS + 1) * 8);
 
   if (tid == 0) {
-    for (int i = 0; i < NS; ++i) { mbar_init(full_bar + 8 * i, 256); mbar_init(empty_bar + 8 * i, 1); }
+    for (int i = 0; i < NS; ++i) { mbar_init(full_bar + 8 * i, WPROD); mbar_init(empty_bar + 8 * i, 1); }
     mbar_init(done_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
@@ -602,27 +619,55 @@ __global__ void __launch_bounds__(NTHR, 1) wgrad_tcgen05_kernel(const Args p) {
   const int ach = mrows / 8;              // 16-byte chunks per gathered row
   constexpr int BCH = TN / 8;
 
-  if (warp < 8) {
+  if (warp < WPROD / 32) {
+    // thread t always fills the same <= 2 A chunks and <= 2 B chunks of a stage; per step only the table row changes.
+    // The table entries of the NEXT step are fetched while the current step's copies are in flight.
+    constexpr int AV = 2, BV = (2 * WK * BCH + WPROD - 1) / WPROD;
+    bool a_on[AV]; int a_r[AV]; uint32_t a_dst[AV]; const __nv_bfloat16* a_src[AV]; int a_idx[AV];
+    bool b_on[BV]; int b_r[BV]; uint32_t b_dst[BV]; const __nv_bfloat16* b_src[BV]; int b_idx[BV];
+#pragma unroll
+    for (int j = 0; j < AV; ++j) {
+      const int c = tid + j * WPROD;
+      a_on[j] = c < 2 * WK * ach;
+      const int cc = a_on[j] ? c : 0;
+      const int plane = cc / (WK * ach), rem = cc - plane * (WK * ach);
+      const int r = rem / ach, mc = rem - r * ach;
+      a_r[j] = r;
+      a_src[j] = (plane ? p.Alo : p.Ahi) + m0 + mc * 8;
+      a_dst[j] = plane * A_PLANE + (r >> 3) * A_LBO + mc * 128 + (r & 7) * 16;
+      a_idx[j] = -1;
+    }
+#pragma unroll
+    for (int j = 0; j < BV; ++j) {
+      const int c = tid + j * WPROD;
+      b_on[j] = c < 2 * WK * BCH;
+      const int cc = b_on[j] ? c : 0;
+      const int plane = cc / (WK * BCH), rem = cc - plane * (WK * BCH);
+      const int r = rem / BCH, nc = rem - r * BCH;
+      b_r[j] = r;
+      b_src[j] = (plane ? p.Blo : p.Bhi) + n0 + nc * 8;
+      b_dst[j] = 2 * A_PLANE + plane * S::B_PLANE + (r >> 3) * S::B_LBO + nc * 128 + (r & 7) * 16;
+      b_idx[j] = -1;
+    }
+    auto fetch = [&](int step) {
+      const int64_t rbase = r_begin + (int64_t)step * WK;
+#pragma unroll
+      for (int j = 0; j < AV; ++j) { const int64_t row = rbase + a_r[j]; a_idx[j] = (a_on[j] && row < r_end) ? __ldg(trow + row) : -1; }
+#pragma unroll
+      for (int j = 0; j < BV; ++j) { const int64_t row = rbase + b_r[j]; b_idx[j] = (b_on[j] && row < r_end) ? __ldg(trow + row) : -1; }
+    };
     auto issue = [&](int stage, int step) {
       const int64_t rbase = r_begin + (int64_t)step * WK;
       const uint32_t sb = smem_base + stage * S::STAGE;
-      for (int c = tid; c < 2 * WK * ach; c += 256) {
-        const int plane = c / (WK * ach), rem = c - plane * (WK * ach);
-        const int r = rem / ach, mc = rem - r * ach;
-        const int64_t row = rbase + r;
-        const int idx = row < r_end ? trow[row] : -1;
-        const __nv_bfloat16* src = (plane ? p.Alo : p.Ahi) + (int64_t)(idx >= 0 ? idx : 0) * p.lda + m0 + mc * 8;
-        cp_async16_zfill(sb + plane * A_PLANE + (r >> 3) * A_LBO + mc * 128 + (r & 7) * 16, src, idx >= 0 ? 16u : 0u);
-      }
-      for (int c = tid; c < 2 * WK * BCH; c += 256) {
-        const int plane = c / (WK * BCH), rem = c - plane * (WK * BCH);
-        const int r = rem / BCH, nc = rem - r * BCH;
-        const int64_t row = rbase + r;
-        const bool ok = row < r_end && trow[row] >= 0;
-        const __nv_bfloat16* src = (plane ? p.Blo : p.Bhi) + (ok ? row : 0) * p.ldb + n0 + nc * 8;
-        cp_async16_zfill(sb + 2 * A_PLANE + plane * S::B_PLANE + (r >> 3) * S::B_LBO + nc * 128 + (r & 7) * 16, src, ok ? 16u : 0u);
-      }
+#pragma unroll
+      for (int j = 0; j < AV; ++j)
+        if (a_on[j]) cp_async16_zfill(sb + a_dst[j], a_src[j] + (int64_t)(a_idx[j] >= 0 ? a_idx[j] : 0) * p.lda, a_idx[j] >= 0 ? 16u : 0u);
+#pragma unroll
+      for (int j = 0; j < BV; ++j)
+        if (b_on[j]) cp_async16_zfill(sb + b_dst[j], b_src[j] + (b_idx[j] >= 0 ? rbase + b_r[j] : 0) * p.ldb, b_idx[j] >= 0 ? 16u : 0u);
+      if (step + 1 < nsteps) fetch(step + 1);
     };
+    if (nsteps > 0) fetch(0);
     for (int j = 0; j < DEPTH; ++j) {
       if (j < nsteps) issue(j, j);
       cp_async_commit();
