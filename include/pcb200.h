@@ -116,10 +116,14 @@ int pcb_conv_wgrad(const float* A, int lda, const float* B, int ldb, const int32
 /* Split-operand variants (tcgen05 only): the gathered / row-aligned operands are bf16 hi/lo planes (see pcb_split_rows),
  * row strides lds/lda/ldb in ELEMENTS (multiples of 8).  Same semantics as pcb_conv_forward / pcb_conv_wgrad; the kernels'
  * operand staging is then a pure asynchronous copy (cp.async, zero-filled where a neighbour is missing). */
+/* pcb_weight_tile: fp32 W[K][Cin][Cout] -> split weights pre-tiled as the shared-memory images of the split conv kernel (one
+ * contiguous blob per (offset, 32-channel chunk, column block), fetched by ONE TMA bulk copy per pipeline stage):
+ * `fwd_tiles` for the forward roles, `dgrad_tiles` for the data-gradient roles (Cin/Cout swapped). */
+size_t pcb_weight_tile_bytes(int K, int Cin, int Cout, int dgrad_roles);
+int pcb_weight_tile(const float* W, int K, int Cin, int Cout, void* fwd_tiles, void* dgrad_tiles, void* stream);
 int pcb_conv_forward_split(const uint16_t* Xhi, const uint16_t* Xlo, int lds, const int32_t* tbl, int64_t tbl_stride,
-                           const int32_t* kmap, int K, int64_t n_out, int Cin, int Cout, const uint16_t* wk_hi,
-                           const uint16_t* wk_lo, const float* bias, float* Y, int ldy, void* ws, size_t ws_bytes, int flags,
-                           void* stream);
+                           const int32_t* kmap, int K, int64_t n_out, int Cin, int Cout, const void* w_tiles,
+                           const float* bias, float* Y, int ldy, void* ws, size_t ws_bytes, int flags, void* stream);
 size_t pcb_conv_wgrad_split_ws_bytes(int K, int64_t n_out, int Ca, int Cb);
 int pcb_conv_wgrad_split(const uint16_t* Ahi, const uint16_t* Alo, int lda, const uint16_t* Bhi, const uint16_t* Blo, int ldb,
                          const int32_t* tbl, int64_t tbl_stride, int K, int64_t n_out, int Ca, int Cb, float* dW,

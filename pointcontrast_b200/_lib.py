@@ -41,7 +41,9 @@ _SIGS = {
     "pcb_conv_forward": (_i, [_p, _i, _p, _l, _p, _i, _l, _i, _i, _p, _p, _p, _p, _p, _p, _p, _i, _p, _sz, _i, _p]),
     "pcb_conv_wgrad_ws_bytes": (_sz, [_i, _l, _i, _i]),
     "pcb_conv_wgrad": (_i, [_p, _i, _p, _i, _p, _l, _i, _l, _i, _i, _p, _i, _p, _sz, _i, _p]),
-    "pcb_conv_forward_split": (_i, [_p, _p, _i, _p, _l, _p, _i, _l, _i, _i, _p, _p, _p, _p, _i, _p, _sz, _i, _p]),
+    "pcb_weight_tile_bytes": (_sz, [_i, _i, _i, _i]),
+    "pcb_weight_tile": (_i, [_p, _i, _i, _i, _p, _p, _p]),
+    "pcb_conv_forward_split": (_i, [_p, _p, _i, _p, _l, _p, _i, _l, _i, _i, _p, _p, _p, _i, _p, _sz, _i, _p]),
     "pcb_conv_wgrad_split_ws_bytes": (_sz, [_i, _l, _i, _i]),
     "pcb_conv_wgrad_split": (_i, [_p, _p, _i, _p, _p, _i, _p, _l, _i, _l, _i, _i, _p, _i, _p, _sz, _i, _p]),
     "pcb_bn_ws_bytes": (_sz, [_l, _i]),

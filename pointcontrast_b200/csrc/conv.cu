@@ -595,7 +595,7 @@ namespace pcb {
 int launch_wgrad_tcgen05(const uint16_t* Ahi, const uint16_t* Alo, int lda, const uint16_t* Bhi, const uint16_t* Blo, int ldb,
                          const int32_t* tbl, int64_t tbl_stride, int K, int64_t n_out, int Ca, int Cb, int rows_per_split, int splits,
                          float* partial, int transpose_out, int tn, cudaStream_t st);
-int launch_conv_tcgen05(const float* X, int ldx, const uint16_t* Xhi, const uint16_t* Xlo, int lds, const int32_t* tbl,
+int launch_conv_tcgen05(const float* X, int ldx, const uint16_t* Xhi, const uint16_t* Xlo, int lds, const void* wt, const int32_t* tbl,
                         int64_t tbl_stride, const int* kmap, int K, int64_t n_out,
                         int Cin, int Cout, const uint16_t* wk_hi, const uint16_t* wk_lo, const float* bias, float* Y, int ldy,
                         float* partial, int nsplit, int bn, int accumulate, cudaStream_t st);
@@ -638,7 +638,7 @@ extern "C" int pcb_conv_forward(const float* X, int ldx, const int32_t* tbl, int
   }
   const int accumulate = (flags & PCB_CONV_ACCUMULATE) ? 1 : 0;
   if ((flags & PCB_CONV_TCGEN05) && wk_hi && wk_lo && ldy % 4 == 0) {
-    if (int e = launch_conv_tcgen05(X, ldx, nullptr, nullptr, 0, tbl, tbl_stride, km.v, K, n_out, Cin, Cout, wk_hi, wk_lo, bias, Y, ldy,
+    if (int e = launch_conv_tcgen05(X, ldx, nullptr, nullptr, 0, nullptr, tbl, tbl_stride, km.v, K, n_out, Cin, Cout, wk_hi, wk_lo, bias, Y, ldy,
                                     nsplit > 1 ? (float*)ws : nullptr, nsplit, pick_tile(Cout), accumulate, st)) return e;
     if (nsplit > 1) {
       int64_t n4 = n_out * (Cout / 4);
@@ -708,21 +708,72 @@ extern "C" int pcb_conv_wgrad(const float* A, int lda, const float* B, int ldb, 
 
 
 // ------------------------------------------------------------------------------------------------ split-operand entry points
+// Weights as shared-memory images for the split conv kernel: per (offset k, 32-channel chunk kc, BN-column block nb) one blob
+//   [hi plane | lo plane], plane = 4 k8-groups x (BN/8 core matrices x 128 B + 16 B pad)   (UMMA K-major, no swizzle)
+// so that a pipeline stage's weight tile is ONE contiguous TMA bulk copy.
+namespace {
+__host__ __device__ inline int64_t tile_plane_bytes(int bn) { return 4ll * ((bn / 8) * 128 + 16); }
+
+__global__ void weight_tile_kernel(const float* __restrict__ W, int K, int Cin, int Cout, int bn_f, int bn_d,
+                                   unsigned char* __restrict__ fwd, unsigned char* __restrict__ dg) {
+  int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= (int64_t)K * Cin * Cout) return;
+  const float w = W[e];
+  const __nv_bfloat16 h = __float2bfloat16_rn(w);
+  const __nv_bfloat16 l = __float2bfloat16_rn(w - __bfloat162float(h));
+  const int co = (int)(e % Cout);
+  const int64_t r = e / Cout;
+  const int ci = (int)(r % Cin);
+  const int k = (int)(r / Cin);
+  {   // forward roles: N = Cout, contraction = Cin
+    const int64_t plane = tile_plane_bytes(bn_f);
+    const int64_t blob = ((int64_t)(k * (Cin / 32) + ci / 32) * (Cout / bn_f) + co / bn_f) * 2 * plane;
+    const int n = co % bn_f, c = ci % 32;
+    const int64_t off = blob + (c / 8) * (plane / 4) + (n / 8) * 128 + (n % 8) * 16 + (c % 8) * 2;
+    *reinterpret_cast<__nv_bfloat16*>(fwd + off) = h;
+    *reinterpret_cast<__nv_bfloat16*>(fwd + off + plane) = l;
+  }
+  {   // data-gradient roles: N = Cin, contraction = Cout
+    const int64_t plane = tile_plane_bytes(bn_d);
+    const int64_t blob = ((int64_t)(k * (Cout / 32) + co / 32) * (Cin / bn_d) + ci / bn_d) * 2 * plane;
+    const int n = ci % bn_d, c = co % 32;
+    const int64_t off = blob + (c / 8) * (plane / 4) + (n / 8) * 128 + (n % 8) * 16 + (c % 8) * 2;
+    *reinterpret_cast<__nv_bfloat16*>(dg + off) = h;
+    *reinterpret_cast<__nv_bfloat16*>(dg + off + plane) = l;
+  }
+}
+}  // namespace
+
+extern "C" size_t pcb_weight_tile_bytes(int K, int Cin, int Cout, int dgrad_roles) {
+  if (Cin % 32 || Cout % 32) return 0;
+  const int N = dgrad_roles ? Cin : Cout, Kc = dgrad_roles ? Cout : Cin;
+  const int bn = pick_tile(N);
+  return (size_t)K * (Kc / 32) * (N / bn) * 2 * tile_plane_bytes(bn);
+}
+
+extern "C" int pcb_weight_tile(const float* W, int K, int Cin, int Cout, void* fwd_tiles, void* dgrad_tiles, void* stream) {
+  PCB_ARG(W && fwd_tiles && dgrad_tiles && K >= 1 && Cin % 32 == 0 && Cout % 32 == 0 && Cin >= 32 && Cout >= 32);
+  int64_t n = (int64_t)K * Cin * Cout;
+  weight_tile_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(W, K, Cin, Cout, pick_tile(Cout), pick_tile(Cin),
+                                                                                   (unsigned char*)fwd_tiles, (unsigned char*)dgrad_tiles);
+  return check_launch("weight_tile_kernel");
+}
+
 extern "C" int pcb_conv_forward_split(const uint16_t* Xhi, const uint16_t* Xlo, int lds, const int32_t* tbl, int64_t tbl_stride,
-                                      const int32_t* kmap, int K, int64_t n_out, int Cin, int Cout, const uint16_t* wk_hi,
-                                      const uint16_t* wk_lo, const float* bias, float* Y, int ldy, void* ws, size_t ws_bytes,
+                                      const int32_t* kmap, int K, int64_t n_out, int Cin, int Cout, const void* w_tiles,
+                                      const float* bias, float* Y, int ldy, void* ws, size_t ws_bytes,
                                       int flags, void* stream) {
   PCB_ARG(K >= 1 && K <= PCB_MAX_KERNEL_VOLUME && n_out >= 0 && Cin % 32 == 0 && Cout % 32 == 0 && Cin >= 32 && Cout >= 32);
   PCB_ARG(lds >= Cin && lds % 8 == 0 && ldy >= Cout && ldy % 4 == 0);
   if (n_out == 0) return PCB_OK;
-  PCB_ARG(Xhi && Xlo && tbl && Y && wk_hi && wk_lo && tbl_stride >= n_out);
+  PCB_ARG(Xhi && Xlo && tbl && Y && w_tiles && tbl_stride >= n_out);
   cudaStream_t st = (cudaStream_t)stream;
   int km[PCB_MAX_KERNEL_VOLUME];
   for (int k = 0; k < K; ++k) { km[k] = kmap ? kmap[k] : k; PCB_ARG(km[k] >= 0 && km[k] < PCB_MAX_KERNEL_VOLUME); }
   const int accumulate = (flags & PCB_CONV_ACCUMULATE) ? 1 : 0;
   const int nsplit = conv_splits(K, n_out, Cin, Cout);
   if (nsplit > 1) PCB_ARG(ws && ws_bytes >= (size_t)nsplit * n_out * Cout * sizeof(float));
-  if (int e = launch_conv_tcgen05(nullptr, 0, Xhi, Xlo, lds, tbl, tbl_stride, km, K, n_out, Cin, Cout, wk_hi, wk_lo, bias, Y, ldy,
+  if (int e = launch_conv_tcgen05(nullptr, 0, Xhi, Xlo, lds, w_tiles, tbl, tbl_stride, km, K, n_out, Cin, Cout, nullptr, nullptr, bias, Y, ldy,
                                   nsplit > 1 ? (float*)ws : nullptr, nsplit, pick_tile(Cout), accumulate, st)) return e;
   if (nsplit > 1) {
     int64_t n4 = n_out * (Cout / 4);

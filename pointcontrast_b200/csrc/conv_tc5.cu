@@ -11,6 +11,7 @@
 //
 // Same arguments, kernel-offset skipping and split-reduce mode as conv_mma_kernel; results agree with it to fp32
 // rounding (same 3-term bf16 split, fp32 accumulation).
+#include <stdlib.h>
 #include "common.cuh"
 
 using namespace pcb;
@@ -45,6 +46,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+// TMA 1-D bulk copy global -> shared (async proxy), completion signalled on an mbarrier
+__device__ __forceinline__ void tma_bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
@@ -92,10 +101,12 @@ struct Args {
   int kmap[PCB_MAX_KERNEL_VOLUME]; int K;
   int64_t n_out; int Cin; int Cout;
   const __nv_bfloat16* wk_hi; const __nv_bfloat16* wk_lo;      // K-major weights: [K][Cout][Cin]
+  const unsigned char* wt;                                      // split kernel: weights pre-tiled as shared-memory images
   const float* bias;
   float* Y; int ldy;
   float* partial;
   int accumulate;       // Y += result (direct mode only; the split mode accumulates in the reduce kernel)
+  int debug;            // timing experiments only (PCB_TC5_DEBUG): 1 skip A copies, 2 skip B copies, 4 skip MMAs, 8 skip proxy fence
 };
 
 template <int BN>
@@ -335,7 +346,7 @@ __global__ void __launch_bounds__(DTHR, 1) conv_tcgen05_split_kernel(const Args 
   const uint32_t full_bar = smem_base + S::BAR_OFF, empty_bar = full_bar + 8 * DNS, done_bar = empty_bar + 8 * DNS;
 
   if (tid == 0) {
-    for (int i = 0; i < DNS; ++i) { mbar_init(full_bar + 8 * i, DPROD); mbar_init(empty_bar + 8 * i, 1); }
+    for (int i = 0; i < DNS; ++i) { mbar_init(full_bar + 8 * i, DPROD / 32 + 1); mbar_init(empty_bar + 8 * i, 1); }
     mbar_init(done_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
@@ -372,73 +383,81 @@ __global__ void __launch_bounds__(DTHR, 1) conv_tcgen05_split_kernel(const Args 
   const int T = nk * nkc;
   const int it0 = (int)((int64_t)T * blockIdx.z / gridDim.z);
   const int it1 = (int)((int64_t)T * (blockIdx.z + 1) / gridDim.z);
-  const int n_it = it1 - it0;
+  const int n_it = (p.debug & 16) ? 0 : it1 - it0;
   constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
   if (warp < DPROD / 32) {
-    // ===== copy producers: thread t always moves the same two A chunks (row t>>2, 16-byte chunk t&3, hi and lo plane)
-    // and the same <= 2 weight chunks; per step only the source offsets change.
+    // ===== producers.  Thread t always owns the same two 16-byte chunks of the A tile (row t>>2, chunk t&3, hi + lo
+    // plane): 128-bit global loads into registers PF stages ahead, 128-bit shared stores when the slot is free.
+    // The weight tile of a stage is ONE TMA bulk copy (the weights are pre-tiled as shared-memory images), issued by
+    // thread 0 and completed on the same "full" barrier through its transaction count.
+    constexpr int PF = 3;
+    constexpr uint32_t BLOB = 2 * S::B_PLANE;
     const int ar = tid >> 2, ak8 = tid & 3;
     const uint32_t a_dst = ak8 * A_LBO + (ar >> 3) * A_SBO + (ar & 7) * 16;
-    constexpr int BCH = 2 * BN * (BK / 8);             // weight chunks per stage (both planes)
-    constexpr int BV = (BCH + DPROD - 1) / DPROD;
-    uint32_t b_dst[BV]; int64_t b_off[BV]; bool b_lo[BV]; bool b_on[BV];
-#pragma unroll
-    for (int j = 0; j < BV; ++j) {
-      const int c = tid + j * DPROD;
-      b_on[j] = c < BCH;
-      const int cc = b_on[j] ? c : 0;
-      const int plane = cc / (BN * 4), rem = cc - plane * (BN * 4);
-      const int n = rem >> 2, k8 = rem & 3;
-      b_lo[j] = plane != 0;
-      b_off[j] = (int64_t)(n0 + n) * p.Cin + k8 * 8;
-      b_dst[j] = 2 * A_PLANE + plane * S::B_PLANE + k8 * S::B_LBO + (n >> 3) * S::B_SBO + (n & 7) * 16;
-    }
-    int cur_k = -1;
-    int64_t a_off = 0; uint32_t a_bytes = 0; int64_t w_off = 0;
-    auto issue = [&](int stage, int it) {
-      const int kq = it / nkc, kc = it - kq * nkc;
-      const int k = s_klist[kq];
-      if (k != cur_k) {
-        cur_k = k;
-        const int idx = s_idx[k * BM + ar];
-        a_bytes = idx >= 0 ? 16u : 0u;
-        a_off = (int64_t)(idx >= 0 ? idx : 0) * p.lds + ak8 * 8;
-        w_off = (int64_t)k * p.Cout * p.Cin;
-      }
-      const uint32_t sb = smem_base + stage * S::STAGE;
-      cp_async16_zfill(sb + a_dst, p.Xhi + a_off + kc * BK, a_bytes);
-      cp_async16_zfill(sb + A_PLANE + a_dst, p.Xlo + a_off + kc * BK, a_bytes);
-#pragma unroll
-      for (int j = 0; j < BV; ++j)
-        if (b_on[j]) cp_async16(sb + b_dst[j], (b_lo[j] ? p.wk_lo : p.wk_hi) + w_off + b_off[j] + kc * BK);
+    const int nblk = p.Cout / BN;
+    // load cursor (runs PF stages ahead of the store cursor)
+    int l_kq = it0 / nkc, l_kc = it0 - l_kq * nkc, loaded = 0;
+    const __nv_bfloat16* l_hi = p.Xhi; const __nv_bfloat16* l_lo = p.Xlo; bool l_on = false;
+    auto set_k = [&]() {
+      const int idx = s_idx[s_klist[l_kq] * BM + ar];
+      l_on = idx >= 0;
+      const int64_t off = (int64_t)(l_on ? idx : 0) * p.lds + ak8 * 8;
+      l_hi = p.Xhi + off; l_lo = p.Xlo + off;
     };
-    for (int j = 0; j < DEPTH; ++j) {
-      if (j < n_it) issue(j, it0 + j);
-      cp_async_commit();
-    }
-    for (int i = 0; i < n_it; ++i) {
-      const int nxt = i + DEPTH;
-      if (nxt < n_it) {
-        const int s2 = nxt % DNS, u2 = nxt / DNS;
-        if (u2 >= 1) mbar_wait(empty_bar + 8 * s2, (u2 - 1) & 1);
-        issue(s2, it0 + nxt);
+    if (n_it > 0) set_k();
+    auto load = [&](uint4& vh, uint4& vl) {
+      if (loaded < n_it) {
+        if (l_on && !(p.debug & 1)) {
+          vh = __ldg(reinterpret_cast<const uint4*>(l_hi + l_kc * BK));
+          vl = __ldg(reinterpret_cast<const uint4*>(l_lo + l_kc * BK));
+        } else {
+          vh = make_uint4(0, 0, 0, 0); vl = make_uint4(0, 0, 0, 0);
+        }
+        ++loaded;
+        if (++l_kc == nkc) { l_kc = 0; ++l_kq; if (loaded < n_it) set_k(); }
       }
-      cp_async_commit();
-      cp_async_wait<DEPTH>();            // this thread's copies of stage i have landed
-      fence_proxy_async();
-      mbar_arrive(full_bar + 8 * (i % DNS));
+    };
+    // store cursor
+    int is = 0, iround = 0, s_kq = l_kq, s_kc = l_kc;
+    auto store = [&](const uint4& vh, const uint4& vl) {
+      if (iround >= 1) {                 // slot reuse: one poller per warp waits for the MMAs that read it
+        if (lane == 0) mbar_wait(empty_bar + 8 * is, (iround - 1) & 1);
+        __syncwarp();
+      }
+      const uint32_t sb = smem_base + is * S::STAGE;
+      if (tid == 0) {
+        const int k = s_klist[s_kq];
+        mbar_arrive_expect_tx(full_bar + 8 * is, (p.debug & 2) ? 0u : BLOB);
+        if (!(p.debug & 2))
+          tma_bulk_load(sb + 2 * A_PLANE, p.wt + ((int64_t)(k * nkc + s_kc) * nblk + blockIdx.y) * BLOB, BLOB, full_bar + 8 * is);
+      }
+      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};\n" ::"r"(sb + a_dst), "r"(vh.x), "r"(vh.y), "r"(vh.z), "r"(vh.w) : "memory");
+      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};\n" ::"r"(sb + A_PLANE + a_dst), "r"(vl.x), "r"(vl.y), "r"(vl.z), "r"(vl.w) : "memory");
+      if (!(p.debug & 8)) fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full_bar + 8 * is);
+      if (++is == DNS) { is = 0; ++iround; }
+      if (++s_kc == nkc) { s_kc = 0; ++s_kq; }
+    };
+    uint4 h0, l0, h1, l1, h2, l2;
+    load(h0, l0); load(h1, l1); load(h2, l2);
+    for (int i = 0; i < n_it; i += PF) {
+      store(h0, l0); load(h0, l0);
+      if (i + 1 < n_it) { store(h1, l1); load(h1, l1); }
+      if (i + 2 < n_it) { store(h2, l2); load(h2, l2); }
     }
   } else if (lane == 0) {
     // ===== MMA issuer =====
+    int s = 0, par = 0;
     for (int i = 0; i < n_it; ++i) {
-      const int s = i % DNS;
-      mbar_wait(full_bar + 8 * s, (i / DNS) & 1);
+      mbar_wait(full_bar + 8 * s, par);
       tc_fence_after();
       const uint32_t a_hi = smem_base + s * S::STAGE, a_lo = a_hi + A_PLANE;
       const uint32_t b_hi = a_hi + 2 * A_PLANE, b_lo = b_hi + S::B_PLANE;
 #pragma unroll
       for (int j = 0; j < BK / 16; ++j) {
+        if (p.debug & 4) break;
         const uint64_t dah = make_desc(a_hi + j * 2 * A_LBO, A_LBO, A_SBO), dal = make_desc(a_lo + j * 2 * A_LBO, A_LBO, A_SBO);
         const uint64_t dbh = make_desc(b_hi + j * 2 * S::B_LBO, S::B_LBO, S::B_SBO);
         const uint64_t dbl = make_desc(b_lo + j * 2 * S::B_LBO, S::B_LBO, S::B_SBO);
@@ -448,6 +467,7 @@ __global__ void __launch_bounds__(DTHR, 1) conv_tcgen05_split_kernel(const Args 
       }
       tc_commit(empty_bar + 8 * s);
       if (i == n_it - 1) tc_commit(done_bar);
+      if (++s == DNS) { s = 0; par ^= 1; }
     }
   }
   if (n_it > 0) {
@@ -526,13 +546,17 @@ int launch(const Args& a, int nsplit, cudaStream_t st) {
 }  // namespace tc5
 
 // Called by pcb_conv_forward (conv.cu).  wk_*: K-major split weights [K][Cout][Cin] for this call's roles.
-int launch_conv_tcgen05(const float* X, int ldx, const uint16_t* Xhi, const uint16_t* Xlo, int lds, const int32_t* tbl,
+int launch_conv_tcgen05(const float* X, int ldx, const uint16_t* Xhi, const uint16_t* Xlo, int lds, const void* wt, const int32_t* tbl,
                         int64_t tbl_stride, const int* kmap, int K, int64_t n_out,
                         int Cin, int Cout, const uint16_t* wk_hi, const uint16_t* wk_lo, const float* bias, float* Y, int ldy,
                         float* partial, int nsplit, int bn, int accumulate, cudaStream_t st) {
   tc5::Args a;
   a.accumulate = accumulate;
+  static int dbg = -1;
+  if (dbg < 0) { const char* e = getenv("PCB_TC5_DEBUG"); dbg = e ? atoi(e) : 0; }
+  a.debug = dbg;
   a.Xhi = (const __nv_bfloat16*)Xhi; a.Xlo = (const __nv_bfloat16*)Xlo; a.lds = lds;
+  a.wt = (const unsigned char*)wt;
   a.X = X; a.ldx = ldx; a.tbl = tbl; a.tbl_stride = tbl_stride; a.K = K; a.n_out = n_out; a.Cin = Cin; a.Cout = Cout;
   for (int k = 0; k < K; ++k) a.kmap[k] = kmap[k];
   a.wk_hi = (const __nv_bfloat16*)wk_hi; a.wk_lo = (const __nv_bfloat16*)wk_lo; a.bias = bias; a.Y = Y; a.ldy = ldy;
@@ -598,7 +622,7 @@ __global__ void __launch_bounds__(NTHR, 1) wgrad_tcgen05_kernel(const Args p) {
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + S::BAR_OFF + (2 * NS + 1) * 8);
 
   if (tid == 0) {
-    for (int i = 0; i < NS; ++i) { mbar_init(full_bar + 8 * i, WPROD); mbar_init(empty_bar + 8 * i, 1); }
+    for (int i = 0; i < NS; ++i) { mbar_init(full_bar + 8 * i, WPROD / 32); mbar_init(empty_bar + 8 * i, 1); }
     mbar_init(done_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
@@ -668,26 +692,33 @@ __global__ void __launch_bounds__(NTHR, 1) wgrad_tcgen05_kernel(const Args p) {
       if (step + 1 < nsteps) fetch(step + 1);
     };
     if (nsteps > 0) fetch(0);
+    int is = 0, iround = 0, issued = 0;
     for (int j = 0; j < DEPTH; ++j) {
-      if (j < nsteps) issue(j, j);
+      if (issued < nsteps) { issue(is, issued); ++issued; if (++is == NS) { is = 0; ++iround; } }
       cp_async_commit();
     }
+    int as = 0;
     for (int i = 0; i < nsteps; ++i) {
-      const int nxt = i + DEPTH;
-      if (nxt < nsteps) {
-        const int s2 = nxt % NS, u2 = nxt / NS;
-        if (u2 >= 1) mbar_wait(empty_bar + 8 * s2, (u2 - 1) & 1);
-        issue(s2, nxt);
+      if (issued < nsteps) {
+        if (iround >= 1) {
+          if (lane == 0) mbar_wait(empty_bar + 8 * is, (iround - 1) & 1);
+          __syncwarp();
+        }
+        issue(is, issued);
+        ++issued;
+        if (++is == NS) { is = 0; ++iround; }
       }
       cp_async_commit();
       cp_async_wait<DEPTH>();
       fence_proxy_async();
-      mbar_arrive(full_bar + 8 * (i % NS));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full_bar + 8 * as);
+      if (++as == NS) as = 0;
     }
   } else if (lane == 0) {
+    int s = 0, par = 0;
     for (int i = 0; i < nsteps; ++i) {
-      const int s = i % NS;
-      mbar_wait(full_bar + 8 * s, (i / NS) & 1);
+      mbar_wait(full_bar + 8 * s, par);
       tc_fence_after();
       const uint32_t a_hi = smem_base + s * S::STAGE, a_lo = a_hi + A_PLANE;
       const uint32_t b_hi = a_hi + 2 * A_PLANE, b_lo = b_hi + S::B_PLANE;
@@ -701,6 +732,7 @@ __global__ void __launch_bounds__(NTHR, 1) wgrad_tcgen05_kernel(const Args p) {
       }
       tc_commit(empty_bar + 8 * s);
       if (i == nsteps - 1) tc_commit(done_bar);
+      if (++s == NS) { s = 0; par ^= 1; }
     }
   }
   if (nsteps > 0) {

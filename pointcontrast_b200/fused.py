@@ -87,13 +87,12 @@ class Runner:
             Cin, Cout = Cout, Cin
         st = stream()
         if Cin % 32 == 0 and Cout % 32 == 0:
-            pl = conv._prepared.get(kern)
-            khi, klo = (pl[0], pl[1]) if transposed_roles else (pl[2], pl[3])       # K-major planes for this call's roles
+            wt = conv._prepared.tiles(kern)[1 if transposed_roles else 0]          # pre-tiled split weights for these roles
             flags = 4 if accumulate else 0
             wsb = lib.pcb_conv_forward_ws_bytes(K, n_out, Cin, Cout)
             ws = me.workspace(wsb, self.device, slot=2)
             assert x.hi, "tensor-core conv needs the split planes of its input"
-            check(lib.pcb_conv_forward_split(x.hi, x.lo, x.ld, ptr(tbl), tbl.shape[1], kmap, K, n_out, Cin, Cout, ptr(khi), ptr(klo),
+            check(lib.pcb_conv_forward_split(x.hi, x.lo, x.ld, ptr(tbl), tbl.shape[1], kmap, K, n_out, Cin, Cout, ptr(wt),
                                              ptr(bias), out.p, out.ld, ptr(ws), wsb, flags, st))
         else:
             assert not accumulate and not transposed_roles

@@ -407,6 +407,19 @@ class _PreparedWeights:
     def __init__(self):
         self.tag = None
         self.planes = None
+        self.tile_tag = None
+        self._tiles = None
+
+    def tiles(self, kernel):
+        """(forward, data-gradient) weights pre-tiled as shared-memory images for the split tcgen05 kernel (TMA bulk loads)."""
+        tag = (kernel.data_ptr(), kernel._version, tuple(kernel.shape))
+        if tag != self.tile_tag:
+            K, Cin, Cout = kernel.shape
+            f = torch.empty(lib.pcb_weight_tile_bytes(K, Cin, Cout, 0), dtype=torch.uint8, device=kernel.device)
+            d = torch.empty(lib.pcb_weight_tile_bytes(K, Cin, Cout, 1), dtype=torch.uint8, device=kernel.device)
+            check(lib.pcb_weight_tile(ptr(kernel.detach()), K, Cin, Cout, ptr(f), ptr(d), stream()))
+            self._tiles, self.tile_tag = (f, d), tag
+        return self._tiles
 
     def get(self, kernel):
         tag = (kernel.data_ptr(), kernel._version, tuple(kernel.shape))

@@ -50,13 +50,16 @@ def main():
             planes = torch.empty(4, 27 * cin * cout, dtype=torch.int16, device="cuda")
             check(lib.pcb_weight_prep(ptr(W), 27, cin, cout, ptr(planes[0]), ptr(planes[1]), ptr(planes[2]), ptr(planes[3]), stream()))
             Xs, dYs = split(X), split(dY)
+            ft = torch.empty(lib.pcb_weight_tile_bytes(27, cin, cout, 0), dtype=torch.uint8, device="cuda")
+            dt = torch.empty(lib.pcb_weight_tile_bytes(27, cin, cout, 1), dtype=torch.uint8, device="cuda")
+            check(lib.pcb_weight_tile(ptr(W), 27, cin, cout, ptr(ft), ptr(dt), stream()))
             Y = torch.empty(n, cout, device="cuda"); dW = torch.empty(27, cin, cout, device="cuda")
             wsb = max(256, lib.pcb_conv_forward_ws_bytes(27, n, cin, cout)); ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
             wsb2 = lib.pcb_conv_wgrad_split_ws_bytes(27, n, cin, cout); ws2 = torch.empty(wsb2, dtype=torch.uint8, device="cuda")
 
             def fwd():
                 check(lib.pcb_conv_forward_split(Xs[0].data_ptr(), Xs[1].data_ptr(), cin, ptr(plan.fwd_tbl), plan.fwd_tbl.shape[1], None, 27,
-                                                 n, cin, cout, ptr(planes[2]), ptr(planes[3]), None, ptr(Y), cout, ptr(ws), wsb, 0, stream()))
+                                                 n, cin, cout, ptr(ft), None, ptr(Y), cout, ptr(ws), wsb, 0, stream()))
 
             def wgrad():
                 check(lib.pcb_conv_wgrad_split(Xs[0].data_ptr(), Xs[1].data_ptr(), cin, dYs[0].data_ptr(), dYs[1].data_ptr(), cout,

@@ -303,7 +303,21 @@ def test_split_operand_conv_forward_matches_fp32_input_kernel(cin, cout):
     Xs = _split(X)
     got = torch.full((n, cout), 0.25, device="cuda")
     wsb = lib.pcb_conv_forward_ws_bytes(27, n, cin, cout); ws = torch.empty(max(wsb, 256), dtype=torch.uint8, device="cuda")
+    ft = torch.empty(lib.pcb_weight_tile_bytes(27, cin, cout, 0), dtype=torch.uint8, device="cuda")
+    dt = torch.empty(lib.pcb_weight_tile_bytes(27, cin, cout, 1), dtype=torch.uint8, device="cuda")
+    check(lib.pcb_weight_tile(ptr(W), 27, cin, cout, ptr(ft), ptr(dt), stream()))
     check(lib.pcb_conv_forward_split(Xs[0].data_ptr(), Xs[1].data_ptr(), cin, ptr(plan.fwd_tbl), plan.fwd_tbl.shape[1], None, 27, n, cin,
-                                     cout, ptr(planes[2]), ptr(planes[3]), None, ptr(got), cout, ptr(ws), wsb, 4, stream()))
+                                     cout, ptr(ft), None, ptr(got), cout, ptr(ws), wsb, 4, stream()))
     torch.cuda.synchronize()
     assert max_rel_err(got - 0.25, ref) < 1e-5
+    # data-gradient roles: dX = sum_k dY[tbl[opp k]] W[k]^T through the dgrad tiles vs the fp32-input kernel
+    dY = torch.randn(n, cout, device="cuda")
+    opp = plan.dg_kmap
+    ref_dx = me._conv_forward_raw(dY, plan.dg_tbl, opp, 27, n, cout, cin, planes[2], planes[3], None, None, planes[0], planes[1])
+    dYs = _split(dY)
+    got_dx = torch.empty(n, cin, device="cuda")
+    wsb = lib.pcb_conv_forward_ws_bytes(27, n, cout, cin); ws = torch.empty(max(wsb, 256), dtype=torch.uint8, device="cuda")
+    check(lib.pcb_conv_forward_split(dYs[0].data_ptr(), dYs[1].data_ptr(), cout, ptr(plan.dg_tbl), plan.dg_tbl.shape[1],
+                                     me._c_int_array(opp), 27, n, cout, cin, ptr(dt), None, ptr(got_dx), cin, ptr(ws), wsb, 0, stream()))
+    torch.cuda.synchronize()
+    assert max_rel_err(got_dx, ref_dx) < 1e-5
