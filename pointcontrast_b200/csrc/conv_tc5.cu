@@ -315,9 +315,9 @@ __global__ void __launch_bounds__(NTHR, 2) conv_tcgen05_kernel(const Args p) {
 //   full[s]  : 256 producer arrivals (each after its own copies of stage s have landed + fence.proxy.async)
 //   empty[s] : tcgen05.commit of the MMAs that read stage s
 // One CTA per SM (the 6-stage ring fills the shared memory), accumulators in TMEM, same epilogue as above.
-constexpr int DNS = 6, DEPTH = 4, DPROD = 512, DTHR = DPROD + 32;
+constexpr int DEPTH = 4;
 
-template <int BN>
+template <int BN, int DNS>
 struct DSmem {
   static constexpr int B_SBO = 128;
   static constexpr int B_LBO = (BN / 8) * 128 + 16;
@@ -330,9 +330,13 @@ struct DSmem {
   static constexpr int TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
 };
 
-template <int BN>
-__global__ void __launch_bounds__(DTHR, 1) conv_tcgen05_split_kernel(const Args p) {
-  using S = DSmem<BN>;
+// <DNS, DPROD, CTAS>: <6, 512, 1> = one CTA per SM with a 6-slot ring; <3, 256, 2> = two CTAs per SM with 3 slots each --
+// every hand-off (mbarrier wake-up ~260 cycles, smem store -> fence -> arrive, MMA issue) is a serial chain inside a CTA,
+// so two co-resident CTAs hide each other's chains.
+template <int BN, int DNS, int DPROD, int CTAS>
+__global__ void __launch_bounds__(DPROD + 32, CTAS) conv_tcgen05_split_kernel(const Args p) {
+  using S = DSmem<BN, DNS>;
+  constexpr int DTHR = DPROD + 32;
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t row0 = (int64_t)blockIdx.x * BM;
@@ -392,27 +396,40 @@ __global__ void __launch_bounds__(DTHR, 1) conv_tcgen05_split_kernel(const Args 
     // The weight tile of a stage is ONE TMA bulk copy (the weights are pre-tiled as shared-memory images), issued by
     // thread 0 and completed on the same "full" barrier through its transaction count.
     constexpr int PF = 3;
+    constexpr int RP = BM * 4 / DPROD;                  // (row, chunk) pairs per thread: rows ar + j * (DPROD / 4)
     constexpr uint32_t BLOB = 2 * S::B_PLANE;
     const int ar = tid >> 2, ak8 = tid & 3;
-    const uint32_t a_dst = ak8 * A_LBO + (ar >> 3) * A_SBO + (ar & 7) * 16;
+    uint32_t a_dst[RP];
+#pragma unroll
+    for (int j = 0; j < RP; ++j) { const int r = ar + j * (DPROD / 4); a_dst[j] = ak8 * A_LBO + (r >> 3) * A_SBO + (r & 7) * 16; }
     const int nblk = p.Cout / BN;
     // load cursor (runs PF stages ahead of the store cursor)
     int l_kq = it0 / nkc, l_kc = it0 - l_kq * nkc, loaded = 0;
-    const __nv_bfloat16* l_hi = p.Xhi; const __nv_bfloat16* l_lo = p.Xlo; bool l_on = false;
+    const __nv_bfloat16* l_hi[RP]; const __nv_bfloat16* l_lo[RP]; bool l_on[RP];
     auto set_k = [&]() {
-      const int idx = s_idx[s_klist[l_kq] * BM + ar];
-      l_on = idx >= 0;
-      const int64_t off = (int64_t)(l_on ? idx : 0) * p.lds + ak8 * 8;
-      l_hi = p.Xhi + off; l_lo = p.Xlo + off;
+      const int kb = s_klist[l_kq] * BM;
+#pragma unroll
+      for (int j = 0; j < RP; ++j) {
+        const int idx = s_idx[kb + ar + j * (DPROD / 4)];
+        l_on[j] = idx >= 0;
+        const int64_t off = (int64_t)(l_on[j] ? idx : 0) * p.lds + ak8 * 8;
+        l_hi[j] = p.Xhi + off; l_lo[j] = p.Xlo + off;
+      }
     };
+#pragma unroll
+    for (int j = 0; j < RP; ++j) { l_hi[j] = p.Xhi; l_lo[j] = p.Xlo; l_on[j] = false; }
     if (n_it > 0) set_k();
-    auto load = [&](uint4& vh, uint4& vl) {
+    struct Regs { uint4 h[RP]; uint4 l[RP]; };
+    auto load = [&](Regs& v) {
       if (loaded < n_it) {
-        if (l_on && !(p.debug & 1)) {
-          vh = __ldg(reinterpret_cast<const uint4*>(l_hi + l_kc * BK));
-          vl = __ldg(reinterpret_cast<const uint4*>(l_lo + l_kc * BK));
-        } else {
-          vh = make_uint4(0, 0, 0, 0); vl = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int j = 0; j < RP; ++j) {
+          if (l_on[j] && !(p.debug & 1)) {
+            v.h[j] = __ldg(reinterpret_cast<const uint4*>(l_hi[j] + l_kc * BK));
+            v.l[j] = __ldg(reinterpret_cast<const uint4*>(l_lo[j] + l_kc * BK));
+          } else {
+            v.h[j] = make_uint4(0, 0, 0, 0); v.l[j] = make_uint4(0, 0, 0, 0);
+          }
         }
         ++loaded;
         if (++l_kc == nkc) { l_kc = 0; ++l_kq; if (loaded < n_it) set_k(); }
@@ -420,7 +437,7 @@ __global__ void __launch_bounds__(DTHR, 1) conv_tcgen05_split_kernel(const Args 
     };
     // store cursor
     int is = 0, iround = 0, s_kq = l_kq, s_kc = l_kc;
-    auto store = [&](const uint4& vh, const uint4& vl) {
+    auto store = [&](const Regs& v) {
       if (iround >= 1) {                 // slot reuse: one poller per warp waits for the MMAs that read it
         if (lane == 0) mbar_wait(empty_bar + 8 * is, (iround - 1) & 1);
         __syncwarp();
@@ -432,20 +449,23 @@ __global__ void __launch_bounds__(DTHR, 1) conv_tcgen05_split_kernel(const Args 
         if (!(p.debug & 2))
           tma_bulk_load(sb + 2 * A_PLANE, p.wt + ((int64_t)(k * nkc + s_kc) * nblk + blockIdx.y) * BLOB, BLOB, full_bar + 8 * is);
       }
-      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};\n" ::"r"(sb + a_dst), "r"(vh.x), "r"(vh.y), "r"(vh.z), "r"(vh.w) : "memory");
-      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};\n" ::"r"(sb + A_PLANE + a_dst), "r"(vl.x), "r"(vl.y), "r"(vl.z), "r"(vl.w) : "memory");
+#pragma unroll
+      for (int j = 0; j < RP; ++j) {
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};\n" ::"r"(sb + a_dst[j]), "r"(v.h[j].x), "r"(v.h[j].y), "r"(v.h[j].z), "r"(v.h[j].w) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};\n" ::"r"(sb + A_PLANE + a_dst[j]), "r"(v.l[j].x), "r"(v.l[j].y), "r"(v.l[j].z), "r"(v.l[j].w) : "memory");
+      }
       if (!(p.debug & 8)) fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(full_bar + 8 * is);
       if (++is == DNS) { is = 0; ++iround; }
       if (++s_kc == nkc) { s_kc = 0; ++s_kq; }
     };
-    uint4 h0, l0, h1, l1, h2, l2;
-    load(h0, l0); load(h1, l1); load(h2, l2);
+    Regs v0, v1, v2;
+    load(v0); load(v1); load(v2);
     for (int i = 0; i < n_it; i += PF) {
-      store(h0, l0); load(h0, l0);
-      if (i + 1 < n_it) { store(h1, l1); load(h1, l1); }
-      if (i + 2 < n_it) { store(h2, l2); load(h2, l2); }
+      store(v0); load(v0);
+      if (i + 1 < n_it) { store(v1); load(v1); }
+      if (i + 2 < n_it) { store(v2); load(v2); }
     }
   } else if (lane == 0) {
     // ===== MMA issuer =====
@@ -512,17 +532,26 @@ __global__ void __launch_bounds__(DTHR, 1) conv_tcgen05_split_kernel(const Args 
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_acc), "r"(S::TMEM_COLS));
 }
 
-template <int BN>
-int launch_split(const Args& a, int nsplit, cudaStream_t st) {
-  using S = DSmem<BN>;
+template <int BN, int DNS, int DPROD, int CTAS>
+int launch_split_cfg(const Args& a, int nsplit, cudaStream_t st) {
+  using S = DSmem<BN, DNS>;
   static bool attr_set = false;
   if (!attr_set) {
-    PCB_CUDA(cudaFuncSetAttribute(conv_tcgen05_split_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    PCB_CUDA(cudaFuncSetAttribute(conv_tcgen05_split_kernel<BN, DNS, DPROD, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     attr_set = true;
   }
   dim3 grid((unsigned)((a.n_out + BM - 1) / BM), a.Cout / BN, nsplit);
-  conv_tcgen05_split_kernel<BN><<<grid, DTHR, S::TOTAL, st>>>(a);
+  conv_tcgen05_split_kernel<BN, DNS, DPROD, CTAS><<<grid, DPROD + 32, S::TOTAL, st>>>(a);
   return check_launch("conv_tcgen05_split_kernel");
+}
+
+template <int BN>
+int launch_split(const Args& a, int nsplit, cudaStream_t st) {
+  static int cfg = -1;
+  if (cfg < 0) { const char* e = getenv("PCB_TC5_CFG"); cfg = e ? atoi(e) : 2; }
+  if (cfg == 1) return launch_split_cfg<BN, 6, 512, 1>(a, nsplit, st);
+  if (cfg == 3) return launch_split_cfg<BN, 2, 256, 3>(a, nsplit, st);
+  return launch_split_cfg<BN, 3, 256, 2>(a, nsplit, st);
 }
 
 template <int BN, bool SPLIT>
