@@ -274,8 +274,9 @@ def run_ours(args):
     roof = None
     if rank == 0:
         me.PROFILE = []
-        trainer.train_step(dev_batches[0])
-        torch.cuda.synchronize()
+    trainer.train_step(dev_batches[0])          # every rank runs it (the step contains the gradient all-reduce); rank 0 records
+    sync_all()
+    if rank == 0:
         prof, me.PROFILE = me.PROFILE, None
         peak, peak_src = peaks()
         agg = {}
