@@ -786,12 +786,12 @@ extern "C" int pcb_conv_forward_split(const uint16_t* Xhi, const uint16_t* Xlo, 
 namespace {
 int wgrad_split_splits(int K, int64_t n_out, int Ca, int Cb) {
   int tn = pick_tile(Cb);
-  int64_t base = (int64_t)K * ((Ca + 127) / 128) * (Cb / tn);
-  int64_t s = (4ll * num_sms() + base - 1) / base;
-  int64_t max_s = (n_out + 255) / 256;
+  int64_t base = (int64_t)((K + 3) / 4) * ((Ca + 127) / 128) * (Cb / tn);      // CTAs per split: offset groups x channel blocks
+  int64_t s = (2ll * num_sms()) / base;       // one CTA per SM: two full waves, never a nearly-empty third one
+  int64_t max_s = (n_out + 511) / 512;
   if (s > max_s) s = max_s;
   if (s < 1) s = 1;
-  if (s > 64) s = 64;
+  if (s > 96) s = 96;
   return (int)s;
 }
 }  // namespace
@@ -816,7 +816,7 @@ extern "C" int pcb_conv_wgrad_split(const uint16_t* Ahi, const uint16_t* Alo, in
   const int splits = wgrad_split_splits(K, n_out, Ca, Cb);
   PCB_ARG(ws_bytes >= (size_t)splits * nW * sizeof(float));
   int64_t rps = (n_out + splits - 1) / splits;
-  rps = (rps + 31) / 32 * 32;
+  rps = (rps + 15) / 16 * 16;
   if (int e = launch_wgrad_tcgen05(Ahi, Alo, lda, Bhi, Blo, ldb, tbl, tbl_stride, K, n_out, Ca, Cb, (int)rps, splits, (float*)ws,
                                    transpose_out, pick_tile(Cb), st)) return e;
   wgrad_reduce_kernel<<<(unsigned)((nW + 255) / 256), 256, 0, st>>>((const float*)ws, splits, nW, dW,

@@ -600,15 +600,17 @@ int launch_conv_tcgen05(const float* X, int ldx, const uint16_t* Xhi, const uint
 
 // ------------------------------------------------------------------------------------------------ weight gradient
 // dW[k] (Ca x Cb) = sum_j A[tbl[k][j], :]^T . B[j, :] on split (bf16 hi/lo) operands.
-// UMMA view: D[M = Ca-block (padded to 128)][N = Cb-block] += A_op[M x K] . B_op[K x N] with K = table rows.
-// Both operands are MN-major in shared memory (a row of the gathered matrix is contiguous along channels):
-//   core matrix = 8 rows (K) x 16 B (8 channels); channel-chunk stride SBO = 128 B, 8-row-group stride LBO.
-// grid: x = K * mblocks * nblocks, y = row splits; partial tiles are reduced by wgrad_reduce_kernel (conv.cu).
+// UMMA view: D_k[M = Ca-block (padded to 128)][N = Cb-block] += A_k[M x 16 rows] . B[16 rows x N]; both operands MN-major
+// (a matrix row is contiguous along channels): core matrix = 8 rows (K) x 16 B (8 channels), channel-chunk stride 128 B,
+// 8-row-group stride LBO.
+// A CTA owns a GROUP of up to 4 kernel offsets and a range of table rows: the row-aligned operand B is staged ONCE per
+// 16-row step and shared by the 4 gathered operands A_k, each accumulating into its own TMEM accumulator (4 x TN columns).
+// 16 producer warps (thread = one row, one 16-byte channel chunk, two of the four offsets, both planes; table entries prefetched one step ahead of
+// the 128-bit data loads, which are two steps ahead of the 128-bit shared stores) + 1 MMA-issuer warp, one CTA per SM.
+// grid: x = groups * mblocks * nblocks, y = row splits; partial tiles are reduced by wgrad_reduce_kernel (conv.cu).
 namespace wg {
 
-constexpr int WM = 128, WK = 32, WPROD = 512, NTHR = WPROD + 32, NS = 6, DEPTH = 4;
-constexpr int A_LBO = (WM / 8) * 128 + 16;
-constexpr int A_PLANE = (WK / 8) * A_LBO;
+constexpr int WM = 128, WK = 16, WPROD = 512, NTHR = WPROD + 32, GK = 4;
 
 struct Args {
   const __nv_bfloat16* Ahi; const __nv_bfloat16* Alo; int lda;      // gathered operand (elements)
@@ -616,39 +618,39 @@ struct Args {
   const int32_t* tbl; int64_t tbl_stride;
   int K; int64_t n_out; int Ca; int Cb; int rows_per_split;
   float* partial; int transpose_out;
+  int ns;               // ring depth (host-chosen to fill shared memory)
 };
 
-template <int TN>
-struct Smem {
-  static constexpr int B_LBO = (TN / 8) * 128 + 16;
-  static constexpr int B_PLANE = (WK / 8) * B_LBO;
-  static constexpr int STAGE = 2 * A_PLANE + 2 * B_PLANE;
-  static constexpr int BAR_OFF = NS * STAGE;
-  static constexpr int TOTAL = BAR_OFF + (2 * NS + 1) * 8 + 32;
-  static constexpr int TMEM_COLS = TN <= 32 ? 32 : (TN <= 64 ? 64 : 128);
-};
+__host__ __device__ inline int a_lbo(int mrows) { return (mrows / 8) * 128 + 16; }
+__host__ __device__ inline int b_lbo(int tn) { return (tn / 8) * 128 + 16; }
+__host__ __device__ inline int stage_bytes(int mrows, int tn) { return 4 * b_lbo(tn) + GK * 4 * a_lbo(mrows); }
 
-// warps 0-7: copy producers (DEPTH stages in flight); warp 8: MMA issuer; 1 CTA per SM (6-stage ring).
 template <int TN>
 __global__ void __launch_bounds__(NTHR, 1) wgrad_tcgen05_kernel(const Args p) {
   using namespace tc5;
-  using S = Smem<TN>;
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int mblocks = (p.Ca + WM - 1) / WM, nblocks = p.Cb / TN;
   int bx = blockIdx.x;
   const int nb = bx % nblocks; bx /= nblocks;
   const int mb = bx % mblocks; bx /= mblocks;
-  const int k = bx;
+  const int k0 = bx * GK;
+  const int nk = min(GK, p.K - k0);
   const int m0 = mb * WM, n0 = nb * TN;
   const int mrows = min(WM, p.Ca - m0);                 // valid M rows of this block (multiple of 32)
+  const int ach = mrows / 8;
+  constexpr int BCH = TN / 8;
+  const int A_LBO = a_lbo(mrows), B_LBO = b_lbo(TN);
+  const int STAGE = stage_bytes(mrows, TN);
+  const int NS = p.ns;
   const int64_t r_begin = (int64_t)blockIdx.y * p.rows_per_split;
   const int64_t r_end = min(p.n_out, r_begin + p.rows_per_split);
   const int nsteps = r_end > r_begin ? (int)((r_end - r_begin + WK - 1) / WK) : 0;
-  const int32_t* trow = p.tbl + (int64_t)k * p.tbl_stride;
   const uint32_t smem_base = smem_u32(smem);
-  const uint32_t full_bar = smem_base + S::BAR_OFF, empty_bar = full_bar + 8 * NS, done_bar = empty_bar + 8 * NS;
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + S::BAR_OFF + (2 * NS + 1) * 8);
+  const uint32_t full_bar = smem_base + NS * STAGE + 2048, empty_bar = full_bar + 8 * NS, done_bar = empty_bar + 8 * NS;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + NS * STAGE + 2048 + (2 * NS + 1) * 8);
+  constexpr int ACC_STRIDE = TN <= 32 ? 32 : (TN <= 64 ? 64 : 128);
+  constexpr int TMEM_COLS = GK * ACC_STRIDE;
 
   if (tid == 0) {
     for (int i = 0; i < NS; ++i) { mbar_init(full_bar + 8 * i, WPROD / 32); mbar_init(empty_bar + 8 * i, 1); }
@@ -656,108 +658,99 @@ __global__ void __launch_bounds__(NTHR, 1) wgrad_tcgen05_kernel(const Args p) {
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(s_tmem)), "r"(S::TMEM_COLS));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(s_tmem)), "r"(TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
   }
-  // the A-tile channel chunks [mrows/8, 16) are never written by the copies: zero every stage once
-  for (int e = tid; e < NS * S::STAGE / 16; e += NTHR) reinterpret_cast<uint4*>(smem)[e] = make_uint4(0, 0, 0, 0);
-  fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_acc = *s_tmem;
-  // MN-major A and B (bits 15, 16), bf16 inputs, fp32 accumulate, M = 128, N = TN
+  // MN-major A and B (bits 15, 16), bf16 inputs, fp32 accumulate, M = 128, N = TN.  The A descriptor spans 16 channel
+  // chunks although only `ach` are staged: rows >= mrows of D are garbage and never read back.
   constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(TN >> 3) << 17) |
                              ((uint32_t)(WM >> 4) << 24);
-  const int ach = mrows / 8;              // 16-byte chunks per gathered row
-  constexpr int BCH = TN / 8;
 
   if (warp < WPROD / 32) {
-    // thread t always fills the same <= 2 A chunks and <= 2 B chunks of a stage; per step only the table row changes.
-    // The table entries of the NEXT step are fetched while the current step's copies are in flight.
-    constexpr int AV = 2, BV = (2 * WK * BCH + WPROD - 1) / WPROD;
-    bool a_on[AV]; int a_r[AV]; uint32_t a_dst[AV]; const __nv_bfloat16* a_src[AV]; int a_idx[AV];
-    bool b_on[BV]; int b_r[BV]; uint32_t b_dst[BV]; const __nv_bfloat16* b_src[BV]; int b_idx[BV];
-#pragma unroll
-    for (int j = 0; j < AV; ++j) {
-      const int c = tid + j * WPROD;
-      a_on[j] = c < 2 * WK * ach;
-      const int cc = a_on[j] ? c : 0;
-      const int plane = cc / (WK * ach), rem = cc - plane * (WK * ach);
-      const int r = rem / ach, mc = rem - r * ach;
-      a_r[j] = r;
-      a_src[j] = (plane ? p.Alo : p.Ahi) + m0 + mc * 8;
-      a_dst[j] = plane * A_PLANE + (r >> 3) * A_LBO + mc * 128 + (r & 7) * 16;
-      a_idx[j] = -1;
-    }
-#pragma unroll
-    for (int j = 0; j < BV; ++j) {
-      const int c = tid + j * WPROD;
-      b_on[j] = c < 2 * WK * BCH;
-      const int cc = b_on[j] ? c : 0;
-      const int plane = cc / (WK * BCH), rem = cc - plane * (WK * BCH);
-      const int r = rem / BCH, nc = rem - r * BCH;
-      b_r[j] = r;
-      b_src[j] = (plane ? p.Blo : p.Bhi) + n0 + nc * 8;
-      b_dst[j] = 2 * A_PLANE + plane * S::B_PLANE + (r >> 3) * S::B_LBO + nc * 128 + (r & 7) * 16;
-      b_idx[j] = -1;
-    }
-    auto fetch = [&](int step) {
-      const int64_t rbase = r_begin + (int64_t)step * WK;
-#pragma unroll
-      for (int j = 0; j < AV; ++j) { const int64_t row = rbase + a_r[j]; a_idx[j] = (a_on[j] && row < r_end) ? __ldg(trow + row) : -1; }
-#pragma unroll
-      for (int j = 0; j < BV; ++j) { const int64_t row = rbase + b_r[j]; b_idx[j] = (b_on[j] && row < r_end) ? __ldg(trow + row) : -1; }
+    constexpr int PF = 2;
+    const int r = tid >> 5, kh = (tid >> 4) & 1, ch = tid & 15;   // row of the step, offset pair (2kh, 2kh+1), 16-byte channel chunk
+    const bool a_on = ch < ach, b_on = (ch < BCH) && kh == 0;
+    const uint32_t a_dst = kh * 8 * A_LBO + (r >> 3) * A_LBO + ch * 128 + (r & 7) * 16;   // A block of offset 2kh, hi plane
+    const uint32_t b_dst = (r >> 3) * B_LBO + ch * 128 + (r & 7) * 16;
+    const int64_t a_col = m0 + ch * 8, b_col = n0 + ch * 8;
+    const int32_t* trow = p.tbl + (int64_t)(k0 + 2 * kh) * p.tbl_stride;
+    const int32_t* trow_other = p.tbl + (int64_t)(k0 + 2 * (1 - kh)) * p.tbl_stride;
+    const bool g0 = 2 * kh < nk, g1 = 2 * kh + 1 < nk, o0 = 2 * (1 - kh) < nk, o1 = 2 * (1 - kh) + 1 < nk;
+    int n0i = -1, n1i = -1, n2i = -1, n3i = -1;      // table entries of the next step: own offset pair + (B loaders) the other pair
+    int fetched = 0, loaded = 0;
+    auto fetch = [&]() {                               // independent loads only: nothing here waits on a previous load
+      const int64_t row = r_begin + (int64_t)fetched * WK + r;
+      const bool live = fetched < nsteps && row < r_end;
+      n0i = (live && g0) ? __ldg(trow + row) : -1;
+      n1i = (live && g1) ? __ldg(trow + p.tbl_stride + row) : -1;
+      n2i = (live && b_on && o0) ? __ldg(trow_other + row) : -1;
+      n3i = (live && b_on && o1) ? __ldg(trow_other + p.tbl_stride + row) : -1;
+      ++fetched;
     };
-    auto issue = [&](int stage, int step) {
-      const int64_t rbase = r_begin + (int64_t)step * WK;
-      const uint32_t sb = smem_base + stage * S::STAGE;
-#pragma unroll
-      for (int j = 0; j < AV; ++j)
-        if (a_on[j]) cp_async16_zfill(sb + a_dst[j], a_src[j] + (int64_t)(a_idx[j] >= 0 ? a_idx[j] : 0) * p.lda, a_idx[j] >= 0 ? 16u : 0u);
-#pragma unroll
-      for (int j = 0; j < BV; ++j)
-        if (b_on[j]) cp_async16_zfill(sb + b_dst[j], b_src[j] + (b_idx[j] >= 0 ? rbase + b_r[j] : 0) * p.ldb, b_idx[j] >= 0 ? 16u : 0u);
-      if (step + 1 < nsteps) fetch(step + 1);
+    struct Regs { uint4 h0, l0, h1, l1, hb, lb; };
+    const uint4 Z = make_uint4(0, 0, 0, 0);
+    auto ldrow = [&](const __nv_bfloat16* base, int64_t off, bool on) {
+      return on ? __ldg(reinterpret_cast<const uint4*>(base + off)) : Z;
     };
-    if (nsteps > 0) fetch(0);
-    int is = 0, iround = 0, issued = 0;
-    for (int j = 0; j < DEPTH; ++j) {
-      if (issued < nsteps) { issue(is, issued); ++issued; if (++is == NS) { is = 0; ++iround; } }
-      cp_async_commit();
-    }
-    int as = 0;
-    for (int i = 0; i < nsteps; ++i) {
-      if (issued < nsteps) {
-        if (iround >= 1) {
-          if (lane == 0) mbar_wait(empty_bar + 8 * is, (iround - 1) & 1);
-          __syncwarp();
-        }
-        issue(is, issued);
-        ++issued;
-        if (++is == NS) { is = 0; ++iround; }
+    auto load = [&](Regs& v) {
+      if (loaded < nsteps) {
+        const int64_t row = r_begin + (int64_t)loaded * WK + r;
+        const int c0 = n0i, c1 = n1i;
+        const bool any = (c0 >= 0) | (c1 >= 0) | (n2i >= 0) | (n3i >= 0);      // the B row is needed if ANY of the four offsets has a neighbour
+        fetch();
+        const int64_t q0 = (int64_t)c0 * p.lda + a_col, q1 = (int64_t)c1 * p.lda + a_col;
+        v.h0 = ldrow(p.Ahi, q0, a_on && c0 >= 0); v.l0 = ldrow(p.Alo, q0, a_on && c0 >= 0);
+        v.h1 = ldrow(p.Ahi, q1, a_on && c1 >= 0); v.l1 = ldrow(p.Alo, q1, a_on && c1 >= 0);
+        v.hb = ldrow(p.Bhi, row * p.ldb + b_col, b_on && any); v.lb = ldrow(p.Blo, row * p.ldb + b_col, b_on && any);
+        ++loaded;
       }
-      cp_async_commit();
-      cp_async_wait<DEPTH>();
+    };
+    int is = 0, iround = 0;
+    auto sts = [&](uint32_t addr, const uint4& x) {
+      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};\n" ::"r"(addr), "r"(x.x), "r"(x.y), "r"(x.z), "r"(x.w) : "memory");
+    };
+    auto store = [&](const Regs& v) {
+      if (iround >= 1) {
+        if (lane == 0) mbar_wait(empty_bar + 8 * is, (iround - 1) & 1);
+        __syncwarp();
+      }
+      const uint32_t sb = smem_base + is * STAGE;
+      if (b_on) { sts(sb + b_dst, v.hb); sts(sb + 2 * B_LBO + b_dst, v.lb); }
+      if (a_on) {
+        const uint32_t ab = sb + 4 * B_LBO + a_dst;
+        sts(ab, v.h0); sts(ab + 2 * A_LBO, v.l0);
+        sts(ab + 4 * A_LBO, v.h1); sts(ab + 6 * A_LBO, v.l1);
+      }
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive(full_bar + 8 * as);
-      if (++as == NS) as = 0;
+      if (lane == 0) mbar_arrive(full_bar + 8 * is);
+      if (++is == NS) { is = 0; ++iround; }
+    };
+    Regs v0, v1;
+    fetch();
+    load(v0); load(v1);
+    for (int i = 0; i < nsteps; i += PF) {
+      store(v0); load(v0);
+      if (i + 1 < nsteps) { store(v1); load(v1); }
     }
   } else if (lane == 0) {
     int s = 0, par = 0;
     for (int i = 0; i < nsteps; ++i) {
       mbar_wait(full_bar + 8 * s, par);
       tc_fence_after();
-      const uint32_t a_hi = smem_base + s * S::STAGE, a_lo = a_hi + A_PLANE;
-      const uint32_t b_hi = a_hi + 2 * A_PLANE, b_lo = b_hi + S::B_PLANE;
-#pragma unroll
-      for (int j = 0; j < WK / 16; ++j) {
-        const uint64_t dah = make_desc(a_hi + j * 2 * A_LBO, A_LBO, 128), dal = make_desc(a_lo + j * 2 * A_LBO, A_LBO, 128);
-        const uint64_t dbh = make_desc(b_hi + j * 2 * S::B_LBO, S::B_LBO, 128), dbl = make_desc(b_lo + j * 2 * S::B_LBO, S::B_LBO, 128);
-        tc_mma(tmem_acc, dal, dbh, IDESC, (i > 0 || j > 0) ? 1u : 0u);
-        tc_mma(tmem_acc, dah, dbl, IDESC, 1u);
-        tc_mma(tmem_acc, dah, dbh, IDESC, 1u);
+      const uint32_t sb = smem_base + s * STAGE;
+      const uint64_t dbh = make_desc(sb, B_LBO, 128), dbl = make_desc(sb + 2 * B_LBO, B_LBO, 128);
+      for (int g = 0; g < nk; ++g) {
+        const uint32_t ab = sb + 4 * B_LBO + g * 4 * A_LBO;
+        const uint64_t dah = make_desc(ab, A_LBO, 128), dal = make_desc(ab + 2 * A_LBO, A_LBO, 128);
+        const uint32_t acc = tmem_acc + g * ACC_STRIDE;
+        tc_mma(acc, dal, dbh, IDESC, i > 0 ? 1u : 0u);
+        tc_mma(acc, dah, dbl, IDESC, 1u);
+        tc_mma(acc, dah, dbh, IDESC, 1u);
       }
       tc_commit(empty_bar + 8 * s);
       if (i == nsteps - 1) tc_commit(done_bar);
@@ -769,52 +762,62 @@ __global__ void __launch_bounds__(NTHR, 1) wgrad_tcgen05_kernel(const Args p) {
     tc_fence_after();
   }
 
-  // ---- epilogue: accumulator row m = TMEM lane, column n -> partial tile
+  // ---- epilogue: accumulator g, row m = TMEM lane, column n -> partial tile of offset k0 + g
   if (warp < 8) {
-    float* out = p.partial + ((int64_t)blockIdx.y * p.K + k) * (int64_t)p.Ca * p.Cb;
     const int q = warp & 3, half = warp >> 2;
     const int m = q * 32 + lane;
     constexpr int HALF = TN / 2;
-#pragma unroll
-    for (int c0 = 0; c0 < HALF; c0 += 16) {
-      const int col = half * HALF + c0;
-      uint32_t r[16];
-      if (nsteps > 0) {
-        tc_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)col, r);
-        tc_ld_wait();
-      } else {
-#pragma unroll
-        for (int e = 0; e < 16; ++e) r[e] = 0u;
-      }
-      if (m < mrows) {
-        if (!p.transpose_out) {
-          float* dst = out + (int64_t)(m0 + m) * p.Cb + n0 + col;
-#pragma unroll
-          for (int e = 0; e < 16; e += 4)
-            *reinterpret_cast<float4*>(dst + e) = make_float4(__uint_as_float(r[e]), __uint_as_float(r[e + 1]), __uint_as_float(r[e + 2]),
-                                                              __uint_as_float(r[e + 3]));
+    for (int g = 0; g < nk; ++g) {
+      float* out = p.partial + ((int64_t)blockIdx.y * p.K + k0 + g) * (int64_t)p.Ca * p.Cb;
+#pragma unroll 1
+      for (int c0 = 0; c0 < HALF; c0 += 16) {
+        const int col = half * HALF + c0;
+        uint32_t r[16];
+        if (nsteps > 0) {
+          tc_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * ACC_STRIDE + col), r);
+          tc_ld_wait();
         } else {
 #pragma unroll
-          for (int e = 0; e < 16; ++e) out[(int64_t)(n0 + col + e) * p.Ca + m0 + m] = __uint_as_float(r[e]);
+          for (int e = 0; e < 16; ++e) r[e] = 0u;
+        }
+        if (m < mrows) {
+          if (!p.transpose_out) {
+            float* dst = out + (int64_t)(m0 + m) * p.Cb + n0 + col;
+#pragma unroll
+            for (int e = 0; e < 16; e += 4)
+              *reinterpret_cast<float4*>(dst + e) = make_float4(__uint_as_float(r[e]), __uint_as_float(r[e + 1]), __uint_as_float(r[e + 2]),
+                                                                __uint_as_float(r[e + 3]));
+          } else {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) out[(int64_t)(n0 + col + e) * p.Ca + m0 + m] = __uint_as_float(r[e]);
+          }
         }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_acc), "r"(S::TMEM_COLS));
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_acc), "r"(TMEM_COLS));
 }
 
 template <int TN>
-int launch(const Args& a, int splits, cudaStream_t st) {
-  using S = Smem<TN>;
+int launch(Args a, int splits, cudaStream_t st) {
   static bool attr_set = false;
+  constexpr int MAX_SMEM = 220 * 1024;
   if (!attr_set) {
-    PCB_CUDA(cudaFuncSetAttribute(wgrad_tcgen05_kernel<TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    PCB_CUDA(cudaFuncSetAttribute(wgrad_tcgen05_kernel<TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
     attr_set = true;
   }
-  dim3 grid((unsigned)(a.K * ((a.Ca + WM - 1) / WM) * (a.Cb / TN)), splits);
-  wgrad_tcgen05_kernel<TN><<<grid, NTHR, S::TOTAL, st>>>(a);
+  const int mrows_max = a.Ca < WM ? a.Ca : WM;
+  const int stage = stage_bytes(mrows_max, TN);
+  int ns = (MAX_SMEM - 4096) / stage;
+  if (ns > 8) ns = 8;
+  if (ns < 2) { set_error("wgrad_tcgen05: stage does not fit"); return PCB_ERR_ARG; }
+  a.ns = ns;
+  const int groups = (a.K + GK - 1) / GK;
+  dim3 grid((unsigned)(groups * ((a.Ca + WM - 1) / WM) * (a.Cb / TN)), splits);
+  // + 2 KB: the M = 128 descriptor of a 96-channel block reads (and ignores) up to 512 B past the last staged chunk
+  wgrad_tcgen05_kernel<TN><<<grid, NTHR, ns * stage + (2 * ns + 1) * 8 + 64 + 2048, st>>>(a);
   return check_launch("wgrad_tcgen05_kernel");
 }
 

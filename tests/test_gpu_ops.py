@@ -276,7 +276,7 @@ def test_split_operand_wgrad_tcgen05_matches_fp32_input_kernels(Ca, Cb, tr):
     check(lib.pcb_conv_wgrad_split(As[0].data_ptr(), As[1].data_ptr(), Ca, Bs[0].data_ptr(), Bs[1].data_ptr(), Cb, ptr(plan.wg_tbl),
                                    plan.wg_tbl.shape[1], K, n, Ca, Cb, ptr(got), tr, ptr(ws), wsb, 4, stream()))      # accumulate onto 0.5
     torch.cuda.synchronize()
-    assert max_rel_err(got - 0.5, ref) < 2e-5
+    assert max_rel_err(got - 0.5, ref) < 5e-5          # two kernels, different partial-sum partitions: fp32 rounding only
     # and against fp64
     tbl = plan.wg_tbl.long()
     k = 5
