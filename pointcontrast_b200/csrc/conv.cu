@@ -487,6 +487,47 @@ __global__ void wgrad_simt_kernel(const WgradArgs p) {
   }
 }
 
+// Stem layer (3 input channels -> 32): exact fp32.  One warp per table row, lane = output channel, all K offsets of the row
+// handled in registers (K x Ca accumulators per lane), block-level reduction in shared memory, one partial tile per CTA.
+template <int CA>
+__global__ void __launch_bounds__(256) wgrad_stem_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
+                                                         const int32_t* __restrict__ tbl, int64_t tbl_stride, int K, int64_t n_out,
+                                                         int rows_per_block, float* __restrict__ partial) {
+  __shared__ float s_acc[PCB_MAX_KERNEL_VOLUME * CA * 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int e = threadIdx.x; e < K * CA * 32; e += 256) s_acc[e] = 0.f;
+  __syncthreads();
+  float acc[PCB_MAX_KERNEL_VOLUME][CA];
+#pragma unroll
+  for (int k = 0; k < PCB_MAX_KERNEL_VOLUME; ++k)
+#pragma unroll
+    for (int c = 0; c < CA; ++c) acc[k][c] = 0.f;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r1 = min(n_out, r0 + rows_per_block);
+  for (int64_t j = r0 + warp; j < r1; j += 8) {
+    const float dy = __ldg(B + j * ldb + lane);
+#pragma unroll
+    for (int k = 0; k < PCB_MAX_KERNEL_VOLUME; ++k) {
+      if (k < K) {
+        const int idx = __ldg(tbl + (int64_t)k * tbl_stride + j);
+        if (idx >= 0) {
+#pragma unroll
+          for (int c = 0; c < CA; ++c) acc[k][c] = fmaf(__ldg(A + (int64_t)idx * lda + c), dy, acc[k][c]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < PCB_MAX_KERNEL_VOLUME; ++k)
+    if (k < K) {
+#pragma unroll
+      for (int c = 0; c < CA; ++c) atomicAdd(&s_acc[(k * CA + c) * 32 + lane], acc[k][c]);
+    }
+  __syncthreads();
+  float* out = partial + (int64_t)blockIdx.x * K * CA * 32;
+  for (int e = threadIdx.x; e < K * CA * 32; e += 256) out[e] = s_acc[e];
+}
+
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int64_t n, float* __restrict__ dW, int accumulate) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -658,6 +699,7 @@ extern "C" int pcb_conv_forward(const float* X, int ldx, const int32_t* tbl, int
 }
 
 extern "C" size_t pcb_conv_wgrad_ws_bytes(int K, int64_t n_out, int Ca, int Cb) {
+  if (Ca == 3 && Cb == 32) return (size_t)2 * num_sms() * K * Ca * Cb * sizeof(float) + 256;
   int tm = pick_tile(Ca), tn = pick_tile(Cb);
   if (!tm || !tn) { tm = 0; tn = 0; }
   int s = wgrad_splits(K, n_out, Ca, Cb, tm, tn);
@@ -677,6 +719,18 @@ extern "C" int pcb_conv_wgrad(const float* A, int lda, const float* B, int ldb, 
     return PCB_OK;
   }
   PCB_ARG(A && B && tbl && ws && tbl_stride >= n_out);
+  if (Ca == 3 && Cb == 32 && !transpose_out && !(flags & PCB_CONV_FORCE_SIMT)) {      // the stem layer: dedicated exact-fp32 kernel
+    const int blocks = (int)((size_t)ws_bytes / ((size_t)nW * sizeof(float)));
+    PCB_ARG(blocks >= 1);
+    int nb = blocks < 2 * num_sms() ? blocks : 2 * num_sms();
+    int64_t rpb = (n_out + nb - 1) / nb;
+    rpb = (rpb + 7) / 8 * 8;
+    nb = (int)((n_out + rpb - 1) / rpb);
+    wgrad_stem_kernel<3><<<nb, 256, 0, st>>>(A, lda, B, ldb, tbl, tbl_stride, K, n_out, (int)rpb, (float*)ws);
+    if (int e = check_launch("wgrad_stem_kernel")) return e;
+    wgrad_reduce_kernel<<<(unsigned)((nW + 255) / 256), 256, 0, st>>>((const float*)ws, nb, nW, dW, (flags & PCB_CONV_ACCUMULATE) ? 1 : 0);
+    return check_launch("wgrad_reduce_kernel");
+  }
   int tm = pick_tile(Ca), tn = pick_tile(Cb);
   const bool tc_ok = tm && tn && (lda % 4 == 0) && (ldb % 4 == 0) && !(flags & PCB_CONV_FORCE_SIMT);
   if (!tc_ok) { tm = 0; tn = 0; }
