@@ -312,7 +312,7 @@ def run_ours(args):
                 "config": {"workload": wl["desc"], "loss": args.loss, "pairs_per_gpu": wl["batch"], "global_batch": pairs_per_step,
                            "voxels_per_view_per_rank": [n0, n1], "parallelism": f"dp{world}",
                            "l2": "per-step working set (activations + kernel maps, GBs) far exceeds the 126 MB L2; 2 distinct batches cycled",
-                           "final_loss": float(loss)},
+                           "final_loss": float(loss[0] if isinstance(loss, tuple) else loss)},
                 "clocks": clk, "gpu_launches": int(launches),
                 "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
                 "roofline": roof, "cpu_baseline": cb}

@@ -842,7 +842,7 @@ int wgrad_split_splits(int K, int64_t n_out, int Ca, int Cb) {
   int tn = pick_tile(Cb);
   int64_t base = (int64_t)((K + 3) / 4) * ((Ca + 127) / 128) * (Cb / tn);      // CTAs per split: offset groups x channel blocks
   int64_t s = (2ll * num_sms()) / base;       // one CTA per SM: two full waves, never a nearly-empty third one
-  int64_t max_s = (n_out + 511) / 512;
+  int64_t max_s = (n_out + 63) / 64;          // small levels: rather many short CTAs than a few long serial ones
   if (s > max_s) s = max_s;
   if (s < 1) s = 1;
   if (s > 96) s = 96;

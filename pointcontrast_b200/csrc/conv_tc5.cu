@@ -621,8 +621,11 @@ struct Args {
   int ns;               // ring depth (host-chosen to fill shared memory)
 };
 
-__host__ __device__ inline int a_lbo(int mrows) { return (mrows / 8) * 128 + 16; }
-__host__ __device__ inline int b_lbo(int tn) { return (tn / 8) * 128 + 16; }
+// channel-chunk (core-matrix) stride 144 B, not 128: a producer warp writes the 16 chunks of ONE row, and a 128-byte stride
+// would put all 16 stores on the same shared-memory banks (a 16..32-way conflict on every 128-bit store)
+constexpr int SBO = 144;
+__host__ __device__ inline int a_lbo(int mrows) { return (mrows / 8) * SBO + 16; }
+__host__ __device__ inline int b_lbo(int tn) { return (tn / 8) * SBO + 16; }
 __host__ __device__ inline int stage_bytes(int mrows, int tn) { return 4 * b_lbo(tn) + GK * 4 * a_lbo(mrows); }
 
 template <int TN>
@@ -647,8 +650,8 @@ __global__ void __launch_bounds__(NTHR, 1) wgrad_tcgen05_kernel(const Args p) {
   const int64_t r_end = min(p.n_out, r_begin + p.rows_per_split);
   const int nsteps = r_end > r_begin ? (int)((r_end - r_begin + WK - 1) / WK) : 0;
   const uint32_t smem_base = smem_u32(smem);
-  const uint32_t full_bar = smem_base + NS * STAGE + 2048, empty_bar = full_bar + 8 * NS, done_bar = empty_bar + 8 * NS;
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + NS * STAGE + 2048 + (2 * NS + 1) * 8);
+  const uint32_t full_bar = smem_base + NS * STAGE + 4096, empty_bar = full_bar + 8 * NS, done_bar = empty_bar + 8 * NS;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + NS * STAGE + 4096 + (2 * NS + 1) * 8);
   constexpr int ACC_STRIDE = TN <= 32 ? 32 : (TN <= 64 ? 64 : 128);
   constexpr int TMEM_COLS = GK * ACC_STRIDE;
 
@@ -674,8 +677,8 @@ __global__ void __launch_bounds__(NTHR, 1) wgrad_tcgen05_kernel(const Args p) {
     constexpr int PF = 2;
     const int r = tid >> 5, kh = (tid >> 4) & 1, ch = tid & 15;   // row of the step, offset pair (2kh, 2kh+1), 16-byte channel chunk
     const bool a_on = ch < ach, b_on = (ch < BCH) && kh == 0;
-    const uint32_t a_dst = kh * 8 * A_LBO + (r >> 3) * A_LBO + ch * 128 + (r & 7) * 16;   // A block of offset 2kh, hi plane
-    const uint32_t b_dst = (r >> 3) * B_LBO + ch * 128 + (r & 7) * 16;
+    const uint32_t a_dst = kh * 8 * A_LBO + (r >> 3) * A_LBO + ch * SBO + (r & 7) * 16;   // A block of offset 2kh, hi plane
+    const uint32_t b_dst = (r >> 3) * B_LBO + ch * SBO + (r & 7) * 16;
     const int64_t a_col = m0 + ch * 8, b_col = n0 + ch * 8;
     const int32_t* trow = p.tbl + (int64_t)(k0 + 2 * kh) * p.tbl_stride;
     const int32_t* trow_other = p.tbl + (int64_t)(k0 + 2 * (1 - kh)) * p.tbl_stride;
@@ -743,10 +746,10 @@ __global__ void __launch_bounds__(NTHR, 1) wgrad_tcgen05_kernel(const Args p) {
       mbar_wait(full_bar + 8 * s, par);
       tc_fence_after();
       const uint32_t sb = smem_base + s * STAGE;
-      const uint64_t dbh = make_desc(sb, B_LBO, 128), dbl = make_desc(sb + 2 * B_LBO, B_LBO, 128);
+      const uint64_t dbh = make_desc(sb, B_LBO, SBO), dbl = make_desc(sb + 2 * B_LBO, B_LBO, SBO);
       for (int g = 0; g < nk; ++g) {
         const uint32_t ab = sb + 4 * B_LBO + g * 4 * A_LBO;
-        const uint64_t dah = make_desc(ab, A_LBO, 128), dal = make_desc(ab + 2 * A_LBO, A_LBO, 128);
+        const uint64_t dah = make_desc(ab, A_LBO, SBO), dal = make_desc(ab + 2 * A_LBO, A_LBO, SBO);
         const uint32_t acc = tmem_acc + g * ACC_STRIDE;
         tc_mma(acc, dal, dbh, IDESC, i > 0 ? 1u : 0u);
         tc_mma(acc, dah, dbl, IDESC, 1u);
@@ -810,14 +813,14 @@ int launch(Args a, int splits, cudaStream_t st) {
   }
   const int mrows_max = a.Ca < WM ? a.Ca : WM;
   const int stage = stage_bytes(mrows_max, TN);
-  int ns = (MAX_SMEM - 4096) / stage;
+  int ns = (MAX_SMEM - 6144) / stage;
   if (ns > 8) ns = 8;
   if (ns < 2) { set_error("wgrad_tcgen05: stage does not fit"); return PCB_ERR_ARG; }
   a.ns = ns;
   const int groups = (a.K + GK - 1) / GK;
   dim3 grid((unsigned)(groups * ((a.Ca + WM - 1) / WM) * (a.Cb / TN)), splits);
-  // + 2 KB: the M = 128 descriptor of a 96-channel block reads (and ignores) up to 512 B past the last staged chunk
-  wgrad_tcgen05_kernel<TN><<<grid, NTHR, ns * stage + (2 * ns + 1) * 8 + 64 + 2048, st>>>(a);
+  // + 4 KB: the M = 128 descriptor of a 96-channel block reads (and ignores) a few hundred bytes past the last staged chunk
+  wgrad_tcgen05_kernel<TN><<<grid, NTHR, ns * stage + (2 * ns + 1) * 8 + 64 + 4096, st>>>(a);
   return check_launch("wgrad_tcgen05_kernel");
 }
 
