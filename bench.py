@@ -10,7 +10,7 @@ both views, 2x forward, loss, backward, gradient all-reduce (N > 1), fused SGD s
   value    : pairs/s with the batch already resident in HBM, CUDA-event timed, max over ranks.
   e2e      : pairs/s through the public trainer call (`Trainer._train_iter`) with the batch in pinned HOST memory,
              host->device copies and the loss read-back inside the timed region.
-  roofline : the dominant kernel (conv_tcgen05_kernel: sparse-conv forward / data-gradient) -- algorithmic bytes
+  roofline : the dominant kernel (conv_tcgen05_split_kernel: sparse-conv forward / data-gradient) -- algorithmic bytes
               of all its launches in one step / their CUDA-event time, vs the measured HBM peak.
   cpu_baseline : the oracle (ME-0.4.3-algorithm CPU restatement) timed on this box's host cores, bounded sample.
 
@@ -69,7 +69,7 @@ class Clocks:
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
@@ -283,15 +283,21 @@ def run_ours(args):
         for r in prof:
             b, f = conv_alg_bytes(r)
             t = r["ev0"].elapsed_time(r["ev1"])
-            key = (("conv_tcgen05_kernel" if me.CONV_IMPL == "tcgen05" else "conv_mma_kernel") if r["kind"] in ("fwd", "dgrad")
-                   else "wgrad_mma_kernel") if r["tc"] else "simt"
+            tc5 = me.CONV_IMPL == "tcgen05"
+            key = (("conv_tcgen05_split_kernel" if tc5 else "conv_mma_kernel") if r["kind"] in ("fwd", "dgrad")
+                   else ("wgrad_tcgen05_kernel" if tc5 else "wgrad_mma_kernel")) if r["tc"] else "stem_fp32 (conv_simt / wgrad_stem)"
             a = agg.setdefault(key, dict(bytes=0, flops=0, ms=0.0, launches=0))
             a["bytes"] += b; a["flops"] += f; a["ms"] += t; a["launches"] += 1
             r["bytes"], r["flops"], r["ms"] = b, f, t
         dom = max(agg, key=lambda k: agg[k]["ms"])
         a = agg[dom]
+        traffic = None
+        try:        # dram__bytes_read+write per launch of this kernel, from the committed ncu pass (profiles/traffic.json)
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["kernels"][dom]["dram_bytes_per_launch"]
+        except Exception:
+            pass
         roof = {"kernel": dom, "bound": "hbm", "achieved": a["bytes"] / (a["ms"] / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
-                "frac": a["bytes"] / (a["ms"] / 1e3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                "frac": a["bytes"] / (a["ms"] / 1e3) / 1e9 / peak, "traffic": traffic, "peak_source": peak_src,
                 "launches_per_step": a["launches"], "avg_launch_ms": a["ms"] / a["launches"],
                 "alg_bytes_per_launch": a["bytes"] / a["launches"], "tensor_tflops": a["flops"] / (a["ms"] / 1e3) / 1e12,
                 "share_of_step": a["ms"] / (ms_total / args.steps),
