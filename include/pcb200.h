@@ -23,8 +23,7 @@
  *   - every function returns 0 on success, non-zero on failure; pcb_last_error() returns the message
  *     of the last failure on the calling thread.  Nothing throws across this boundary.
  *   - all data pointers are CALLER-OWNED DEVICE memory (16-byte aligned); the library never allocates
- *     device memory for data.  Workspaces are sized by the *_ws_bytes queries.  (The one exception is 256 bytes
- *     of control state per device: the arrival counter of the "last CTA finalises" BatchNorm reductions.)
+ *     device memory.  Workspaces are sized by the *_ws_bytes queries.
  *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous on it unless stated.
  *   - feature matrices are fp32 row-major [rows, channels]; coordinates int32 [rows, 4] = (batch, x, y, z).
  *   - a kernel map is a dense neighbour table  tbl[K][n_out]  (int32): tbl[k][j] = input row feeding output

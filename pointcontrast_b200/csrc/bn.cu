@@ -37,21 +37,10 @@ __global__ void split_rows_kernel(const float* __restrict__ X, int ldx, int64_t 
 // partial[chunk][0][C] = sum(a), partial[chunk][1][C] = sum(a*b)    (b == a for the forward statistics)
 // block: (C/4) channel-vectors x RP row lanes; grid: one CTA per chunk of rows.
 // Strides: lda / ldb / ldm (floats).  Mask (backward only): a is zeroed where mask <= 0 (ReLU folded into the BN backward).
-struct Finalize {            // what the LAST CTA of a column reduction does with the per-chunk partial sums
-  unsigned int* counter;     // zero before the launch; reset by the last CTA
-  int mode;                  // 1: forward statistics, 2: backward sums
-  int64_t n; float eps, momentum;
-  float* mean; float* invstd; float* running_mean; float* running_var;      // mode 1
-  float* dgamma; float* dbeta; int accumulate; float* sums;                  // mode 2
-};
-
-__device__ __forceinline__ void warp_sum2(const float* __restrict__ partial, int chunks, int C, int c, double& s1, double& s2);
-
 template <bool TWO_INPUTS>
 __global__ void colsum_kernel(const float* __restrict__ A, int lda, const float* __restrict__ Bm, int ldb,
                               const float* __restrict__ Mask, int ldm, int64_t n, int C,
-                              const float* __restrict__ mean, const float* __restrict__ invstd, float* __restrict__ partial,
-                              const Finalize fin) {
+                              const float* __restrict__ mean, const float* __restrict__ invstd, float* __restrict__ partial) {
   extern __shared__ float sm[];      // [RP][2][C]
   const int cv = C / 4;
   const int rp = blockDim.x / cv;    // row lanes
@@ -90,49 +79,33 @@ __global__ void colsum_kernel(const float* __restrict__ A, int lda, const float*
     for (int l = 0; l < rp; ++l) s += sm[(int64_t)l * 2 * C + e];
     partial[(int64_t)blockIdx.x * 2 * C + e] = s;
   }
-  // ---- the last CTA to finish reduces the partials (fixed order -> deterministic) and finalises: no second launch
-  __shared__ bool is_last;
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) is_last = atomicAdd(fin.counter, 1u) == gridDim.x - 1;
-  __syncthreads();
-  if (!is_last) return;
-  __threadfence();
-  const int chunks = gridDim.x;
-  const int nwarps = blockDim.x >> 5, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int c = w; c < C; c += nwarps) {
-    double s1, s2;
-    warp_sum2(partial, chunks, C, c, s1, s2);
-    if (lane != 0) continue;
-    if (fin.mode == 1) {
-      double m = s1 / (double)fin.n;
-      double var = s2 / (double)fin.n - m * m;
-      if (var < 0.0) var = 0.0;
-      fin.mean[c] = (float)m;
-      fin.invstd[c] = (float)(1.0 / sqrt(var + (double)fin.eps));
-      if (fin.running_mean) fin.running_mean[c] = (1.f - fin.momentum) * fin.running_mean[c] + fin.momentum * (float)m;
-      if (fin.running_var) {
-        double unb = fin.n > 1 ? var * ((double)fin.n / (double)(fin.n - 1)) : var;
-        fin.running_var[c] = (1.f - fin.momentum) * fin.running_var[c] + fin.momentum * (float)unb;
-      }
-    } else {
-      fin.sums[c] = (float)s1;
-      fin.sums[C + c] = (float)s2;
-      if (fin.accumulate) { fin.dbeta[c] += (float)s1; fin.dgamma[c] += (float)s2; }
-      else { fin.dbeta[c] = (float)s1; fin.dgamma[c] = (float)s2; }
-    }
-  }
-  if (threadIdx.x == 0) *fin.counter = 0u;
 }
 
-// one warp per channel: lanes stride over the row chunks, fp64 shuffle reduction (fixed order: deterministic).
-// The partials were written by other CTAs of the same launch: read them through L2 (volatile), not the read-only path.
+// one warp per channel: lanes stride over the row chunks, fp64 shuffle reduction (fixed order: deterministic)
 __device__ __forceinline__ void warp_sum2(const float* __restrict__ partial, int chunks, int C, int c, double& s1, double& s2) {
   const int lane = threadIdx.x & 31;
   s1 = 0.0; s2 = 0.0;
-  const volatile float* pv = partial;
-  for (int k = lane; k < chunks; k += 32) { s1 += pv[(int64_t)k * 2 * C + c]; s2 += pv[(int64_t)k * 2 * C + C + c]; }
+  for (int k = lane; k < chunks; k += 32) { s1 += partial[(int64_t)k * 2 * C + c]; s2 += partial[(int64_t)k * 2 * C + C + c]; }
   for (int o = 16; o; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+}
+
+__global__ void bn_finalize_kernel(const float* __restrict__ partial, int chunks, int64_t n, int C, float eps, float momentum,
+                                   float* __restrict__ mean, float* __restrict__ invstd, float* running_mean, float* running_var) {
+  int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (c >= C) return;
+  double s1, s2;
+  warp_sum2(partial, chunks, C, c, s1, s2);
+  if ((threadIdx.x & 31) != 0) return;
+  double m = s1 / (double)n;
+  double var = s2 / (double)n - m * m;
+  if (var < 0.0) var = 0.0;
+  mean[c] = (float)m;
+  invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+  if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
+  if (running_var) {
+    double unb = n > 1 ? var * ((double)n / (double)(n - 1)) : var;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
+  }
 }
 
 __global__ void bn_apply_kernel(const float* __restrict__ X, int ldx, int64_t n4, int cv, const float* __restrict__ mean,
@@ -156,6 +129,21 @@ __global__ void bn_apply_kernel(const float* __restrict__ X, int ldx, int64_t n4
   if (relu) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
   *reinterpret_cast<float4*>(Y + row * ldy + c4 * 4) = y;
   if (Yhi) store_split4(y, Yhi + row * lds + c4 * 4, Ylo + row * lds + c4 * 4);
+}
+
+// dgamma = sum(dY*xhat), dbeta = sum(dY); also leaves them in ws for the apply pass
+// sums[0][C] = dbeta, sums[1][C] = dgamma for the apply pass; the parameter gradients are written or accumulated
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int chunks, int C, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta, int accumulate, float* __restrict__ sums) {
+  int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (c >= C) return;
+  double s1, s2;
+  warp_sum2(partial, chunks, C, c, s1, s2);
+  if ((threadIdx.x & 31) != 0) return;
+  sums[c] = (float)s1;
+  sums[C + c] = (float)s2;
+  if (accumulate) { dbeta[c] += (float)s1; dgamma[c] += (float)s2; }
+  else { dbeta[c] = (float)s1; dgamma[c] = (float)s2; }
 }
 
 // gout_mode: 0 none, 1 write, 2 accumulate -- the (ReLU-masked) incoming gradient, i.e. the gradient of the residual input
@@ -193,19 +181,6 @@ __global__ void bn_bwd_apply_kernel(const float* dY, int lddy, const float* __re
   if (dXhi) store_split4(o, dXhi + row * lds + c4 * 4, dXlo + row * lds + c4 * 4);
 }
 
-// 4 bytes of control state per device for the "last CTA finalises" pattern (zeroed once; each launch leaves it at zero).
-// Launches that share it are ordered by the stream; concurrent use from several streams of one device is not supported.
-inline unsigned int* counter_for(cudaStream_t) {
-  static unsigned int* ctr[64] = {};
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-  if (!ctr[dev]) {
-    if (cudaMalloc(&ctr[dev], 256) != cudaSuccess) { set_error("counter allocation failed"); return nullptr; }
-    cudaMemset(ctr[dev], 0, 256);
-  }
-  return ctr[dev];
-}
-
 inline int chunks_for(int64_t n) { return (int)((n + ROWS_PER_CHUNK - 1) / ROWS_PER_CHUNK); }
 
 inline int colsum_threads(int C) {       // (C/4) * row lanes, <= 256, at least one row lane
@@ -229,13 +204,12 @@ extern "C" int pcb_bn_stats2(const float* X, int ldx, int64_t n, int C, float ep
   const int chunks = chunks_for(n);
   const int thr = colsum_threads(C);
   const int rp = thr / (C / 4);
-  Finalize fin{};
-  fin.counter = counter_for(st); fin.mode = 1; fin.n = n; fin.eps = eps; fin.momentum = momentum;
-  fin.mean = mean; fin.invstd = invstd; fin.running_mean = running_mean; fin.running_var = running_var;
-  if (!fin.counter) return PCB_ERR_CUDA;
   colsum_kernel<false><<<chunks, thr, (size_t)rp * 2 * C * sizeof(float), st>>>(X, ldx, nullptr, 0, nullptr, 0, n, C, nullptr, nullptr,
-                                                                                 (float*)ws, fin);
-  return check_launch("colsum_kernel");
+                                                                                 (float*)ws);
+  if (int e = check_launch("colsum_kernel")) return e;
+  bn_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>((const float*)ws, chunks, n, C, eps, momentum, mean, invstd, running_mean,
+                                                      running_var);
+  return check_launch("bn_finalize_kernel");
 }
 
 extern "C" int pcb_bn_stats(const float* X, int64_t n, int C, float eps, float momentum, float* mean, float* invstd,
@@ -288,13 +262,10 @@ extern "C" int pcb_bn_backward2(const float* dY, int lddy, const float* X, int l
   const int rp = thr / (C / 4);
   float* partial = (float*)ws;
   float* sums = partial + (size_t)chunks * 2 * C;        // [2][C]: dbeta, dgamma of THIS call (the apply pass needs them)
-  Finalize fin{};
-  fin.counter = counter_for(st); fin.mode = 2; fin.n = n; fin.dgamma = dgamma; fin.dbeta = dbeta; fin.accumulate = accumulate_param_grads;
-  fin.sums = sums;
-  if (!fin.counter) return PCB_ERR_CUDA;
-  colsum_kernel<true><<<chunks, thr, (size_t)rp * 2 * C * sizeof(float), st>>>(dY, lddy, X, ldx, relu_out, ldm, n, C, mean, invstd, partial,
-                                                                               fin);
+  colsum_kernel<true><<<chunks, thr, (size_t)rp * 2 * C * sizeof(float), st>>>(dY, lddy, X, ldx, relu_out, ldm, n, C, mean, invstd, partial);
   if (int e = check_launch("colsum_kernel<bwd>")) return e;
+  bn_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(partial, chunks, C, dgamma, dbeta, accumulate_param_grads, sums);
+  if (int e = check_launch("bn_bwd_finalize_kernel")) return e;
   int64_t n4 = n * (C / 4);
   bn_bwd_apply_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(dY, lddy, X, ldx, relu_out, ldm, n4, C / 4, 1.0f / (float)n, mean,
                                                                     invstd, gamma, sums + C, sums, dX, lddx, gout, ldg, gout_mode,

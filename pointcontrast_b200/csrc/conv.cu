@@ -570,7 +570,7 @@ int conv_splits(int K, int64_t n_out, int Cin, int Cout) {
   int64_t base = ((n_out + BM - 1) / BM) * (Cout / bn);
   const int64_t one_wave = 2ll * num_sms();
   if (base >= one_wave) return 1;
-  int64_t s = (one_wave + base - 1) / base;          // about one wave of CTAs: per-tile setup dominates on the small levels
+  int64_t s = (2 * one_wave + base - 1) / base;
   int64_t T = (int64_t)K * (Cin / BK);
   if (s > T) s = T;
   if (s > 64) s = 64;
