@@ -401,6 +401,15 @@ def _prof_end(ev0, kind, plan, K, Cin, Cout, tc):
     PROFILE.append(dict(kind=kind, K=K, Cin=Cin, Cout=Cout, n_in=plan.n_in, n_out=plan.n_out, plan=plan, tc=tc, ev0=ev0, ev1=ev1))
 
 
+_WEIGHTS_EPOCH = [0]
+
+
+def bump_weights_epoch():
+    """Parameters were rewritten through raw pointers (the fused SGD kernel, a broadcast into the flat buffer): torch's
+    per-tensor version counters do not see that, so every cached split / tiled copy of a kernel is invalidated here."""
+    _WEIGHTS_EPOCH[0] += 1
+
+
 class _PreparedWeights:
     """bf16 hi/lo split planes of a kernel (+ per-offset transposes), refreshed when the parameter changes."""
 
@@ -412,7 +421,7 @@ class _PreparedWeights:
 
     def tiles(self, kernel):
         """(forward, data-gradient) weights pre-tiled as shared-memory images for the split tcgen05 kernel (TMA bulk loads)."""
-        tag = (kernel.data_ptr(), kernel._version, tuple(kernel.shape))
+        tag = (kernel.data_ptr(), kernel._version, tuple(kernel.shape), _WEIGHTS_EPOCH[0])
         if tag != self.tile_tag:
             K, Cin, Cout = kernel.shape
             f = torch.empty(lib.pcb_weight_tile_bytes(K, Cin, Cout, 0), dtype=torch.uint8, device=kernel.device)
@@ -422,7 +431,7 @@ class _PreparedWeights:
         return self._tiles
 
     def get(self, kernel):
-        tag = (kernel.data_ptr(), kernel._version, tuple(kernel.shape))
+        tag = (kernel.data_ptr(), kernel._version, tuple(kernel.shape), _WEIGHTS_EPOCH[0])
         if tag != self.tag:
             K, Cin, Cout = kernel.shape
             planes = torch.empty(4, K * Cin * Cout, dtype=torch.int16, device=kernel.device)

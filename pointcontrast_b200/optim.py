@@ -8,6 +8,7 @@ Semantics and state_dict layout are those of `torch.optim.SGD(momentum, weight_d
 import torch
 
 from ._lib import check, lib, ptr, stream
+from .me import bump_weights_epoch
 
 
 class FlatSGD(torch.optim.Optimizer):
@@ -38,6 +39,7 @@ class FlatSGD(torch.optim.Optimizer):
                 p.grad = g
         self._first = True
         self.grad_scale = 1.0                            # e.g. 1/world_size after a sum all-reduce
+        bump_weights_epoch()
 
     def _views(self, flat):
         return [flat[off:off + p.numel()].view(p.shape) for p, off in zip(self.param_groups[0]["params"], self._offsets)]
@@ -60,6 +62,7 @@ class FlatSGD(torch.optim.Optimizer):
             check(lib.pcb_sgd_step(ptr(self.flat_param), ptr(self.flat_grad), ptr(self.flat_buf), self.flat_param.numel(),
                                    float(grp["lr"]), float(grp["momentum"]), float(grp["weight_decay"]), float(self.grad_scale),
                                    1 if self._first else 0, stream()))
+        bump_weights_epoch()           # the kernel wrote the parameters behind torch's back: drop cached bf16 copies
         if self._first:
             for p, b in zip(ps, self._views(self.flat_buf)):
                 self.state[p]["momentum_buffer"] = b

@@ -93,6 +93,7 @@ class ContrastiveLossTrainer:
                 logging.info("=> loaded checkpoint '%s' (curr_iter %d)", checkpoint_fn, state["curr_iter"])
         if self.world > 1:                       # DDP construction semantics: every rank starts from rank 0's state
             dist.broadcast(self.optimizer.flat_param, 0)
+            ME.bump_weights_epoch()
             for b in model.buffers():
                 dist.broadcast(b, 0)
             self.optimizer.grad_scale = 1.0 / self.world
