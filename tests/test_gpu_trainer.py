@@ -53,7 +53,7 @@ def test_loss_curve_matches_cpu_oracle():
     if os.environ.get("PCB_REPORT_DIR"):
         json.dump({"gpu": curve, "cpu_oracle_fp32": ocurve, "rel": rel}, open(os.path.join(os.environ["PCB_REPORT_DIR"], "loss_curve.json"), "w"), indent=1)
     assert rel[0] < 1e-3, (curve, ocurve)              # same weights: the 1e-3 loss bar
-    assert max(rel) < 2e-2, (curve, ocurve)            # after 5 updates through an ill-conditioned backward (DESIGN.md "Numerics")
+    assert max(rel) < 1e-2, (curve, ocurve)            # after 5 updates through an ill-conditioned backward (measured: 1.3e-3)
     assert ocurve[-1] < ocurve[0] and curve[-1] < curve[0]
 
 
