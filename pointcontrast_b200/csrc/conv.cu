@@ -11,6 +11,7 @@
 // parity (tests: 1e-3 relative against the fp64 oracle after 63 layers).  An exact fp32 SIMT kernel with the
 // same interface covers channel counts the tensor-core tiling does not (Cin = 3) and is the in-library
 // cross-check (PCB_CONV_FORCE_SIMT).
+#include <stdlib.h>
 #include "common.cuh"
 
 using namespace pcb;
@@ -570,7 +571,9 @@ int conv_splits(int K, int64_t n_out, int Cin, int Cout) {
   int64_t base = ((n_out + BM - 1) / BM) * (Cout / bn);
   const int64_t one_wave = 2ll * num_sms();
   if (base >= one_wave) return 1;
-  int64_t s = (2 * one_wave + base - 1) / base;
+  static double waves = 0.0;        // CTAs to aim for on a small level, in units of one resident wave (measured on C1: 0.25-0.5 best; 2 costs 4 ms/step)
+  if (waves == 0.0) { const char* e = getenv("PCB_CONV_SPLIT_WAVES"); waves = e ? atof(e) : 0.5; if (waves < 0.05) waves = 0.05; }
+  int64_t s = ((int64_t)(waves * one_wave) + base - 1) / base;
   int64_t T = (int64_t)K * (Cin / BK);
   if (s > T) s = T;
   if (s > 64) s = 64;
@@ -841,7 +844,9 @@ namespace {
 int wgrad_split_splits(int K, int64_t n_out, int Ca, int Cb) {
   int tn = pick_tile(Cb);
   int64_t base = (int64_t)((K + 3) / 4) * ((Ca + 127) / 128) * (Cb / tn);      // CTAs per split: offset groups x channel blocks
-  int64_t s = (2ll * num_sms()) / base;       // one CTA per SM: two full waves, never a nearly-empty third one
+  static double wwaves = 0.0;
+  if (wwaves == 0.0) { const char* e = getenv("PCB_WGRAD_SPLIT_WAVES"); wwaves = e ? atof(e) : 1.0; if (wwaves < 0.05) wwaves = 0.05; }      // measured on C1: 1 wave best (0.5 under-fills, 2-3 add reduce traffic)
+  int64_t s = (int64_t)(wwaves * num_sms()) / base;       // one CTA per SM: whole waves, never a nearly-empty extra one
   int64_t max_s = (n_out + 63) / 64;          // small levels: rather many short CTAs than a few long serial ones
   if (s > max_s) s = max_s;
   if (s < 1) s = 1;
