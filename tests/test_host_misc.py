@@ -1,0 +1,75 @@
+"""More CPU-side checks: oracle kernel-map properties under hypothesis, synthetic-data contract, config overrides,
+and the JSON contract of bench.py's reference arm."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+from hypothesis import given, settings, strategies as st
+
+from oracle import me_cpu as OR
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@settings(max_examples=25, deadline=None)
+@given(st.lists(st.tuples(st.integers(0, 2), st.integers(-9, 9), st.integers(-9, 9), st.integers(-9, 9)), min_size=1, max_size=200,
+                unique=True), st.sampled_from([2, 4]))
+def test_oracle_stride_and_maps_properties(cs, ts):
+    c = np.asarray(cs, np.int32)
+    coarse = OR.stride_coords(c, ts)
+    # unique, sorted by (b, x, y, z), every fine voxel has exactly one parent, parents are multiples of ts
+    keys = OR.pack_keys(coarse)
+    assert (np.diff(keys.astype(np.int64)) > 0).all()
+    assert (coarse[:, 1:] % ts == 0).all()
+    parents = np.concatenate([c[:, :1], np.floor_divide(c[:, 1:], ts) * ts], 1)
+    assert set(map(tuple, parents.tolist())) == set(map(tuple, coarse.tolist()))
+    # k2s2-style map: offsets {0..ts-1 step ts/2}... use the 8 child offsets of a stride-2 step on a ts/2 grid
+    half = ts // 2
+    fine = np.unique(np.concatenate([c[:, :1], np.floor_divide(c[:, 1:], half) * half], 1), axis=0).astype(np.int32)
+    coarse2 = OR.stride_coords(fine, ts)
+    offs = OR.hypercube_offsets([2, 2, 2]) * half
+    maps = OR.kernel_map(fine, coarse2, offs)
+    assert sum(len(i) for i, _ in maps) == len(fine)                       # each fine row feeds exactly one coarse row
+    seen = np.concatenate([i for i, _ in maps])
+    assert sorted(seen.tolist()) == list(range(len(fine)))
+    # 3x3x3 map on the fine level: symmetric under offset negation, centre = identity
+    m3 = OR.kernel_map(fine, fine, OR.hypercube_offsets([3, 3, 3]) * half)
+    assert (m3[13][0] == m3[13][1]).all() and len(m3[13][0]) == len(fine)
+    for k in range(27):
+        assert set(zip(m3[k][0].tolist(), m3[k][1].tolist())) == set(zip(m3[26 - k][1].tolist(), m3[26 - k][0].tolist()))
+
+
+def test_synthetic_batch_contract_and_determinism():
+    from pointcontrast_b200 import synth
+    a = synth.synth_batch(3, 2, scale=0.12)
+    b = synth.synth_batch(3, 2, scale=0.12)
+    for k in ("sinput0_C", "sinput1_C", "sinput0_F", "sinput1_F", "correspondences"):
+        assert (a[k] == b[k]).all()
+    C0, P = a["sinput0_C"], a["correspondences"]
+    assert C0.dtype == np.int32 and C0.shape[1] == 4 and a["sinput0_F"].dtype == np.float32 and a["sinput0_F"].shape[1] == 3
+    assert set(C0[:, 0].tolist()) == {0, 1}                                # batch index first (`ddp_data_loaders.py:68-70`)
+    assert len(np.unique(OR.pack_keys(C0))) == len(C0)                     # voxelised: unique per scene
+    assert P.dtype == np.int32 and P[:, 0].max() < len(C0) and P[:, 1].max() < len(a["sinput1_C"])
+    assert (np.diff(P[:, 0]) >= 0).all()                                   # grouped / ascending in column 0
+
+
+def test_config_defaults_and_overrides():
+    from pointcontrast_b200.config import default_config
+    c = default_config(["trainer.batch_size=32", "misc.num_gpus=8", "misc.nceT=0.4", "misc.weight=None", "net.normalize_feature=False"])
+    assert c.trainer.batch_size == 32 and c.misc.num_gpus == 8 and c.misc.nceT == 0.4 and c.misc.weight is None
+    assert c.net.normalize_feature is False and c.opt.momentum == 0.8 and c.opt.bn_momentum == 0.05 and c.misc.npos == 4096
+    assert c.trainer.num_pos_per_batch == 1024 and c.trainer.num_hn_samples_per_batch == 256 and c.data.voxel_size == 0.025
+
+
+def test_reference_arm_json_contract():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "c0", "--steps", "1",
+                        "--warmup", "0"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-500:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "cpu_baseline", "e2e"):
+        assert k in line
+    assert line["impl"] == "reference" and line["unit"] == "pairs/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
