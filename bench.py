@@ -5,7 +5,7 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
 One "step" = one full training iteration on one batch of synthetic scene pairs per rank: coordinate-manager build for
-both views, 2x forward, loss, backward, gradient all-reduce (N > 1), fused SGD step.  Prints ONE JSON line (rank 0).
+both views (stacked in one pass by default; PCB_PAIR=0: two forward calls), loss, backward, gradient all-reduce (N > 1), fused SGD step.  Prints ONE JSON line (rank 0).
 
   value    : pairs/s with the batch already resident in HBM, CUDA-event timed, max over ranks.
   e2e      : pairs/s through the public trainer call (`Trainer._train_iter`) with the batch in pinned HOST memory,
@@ -203,7 +203,7 @@ def conv_alg_bytes(rec):
 
 def run_ours(args):
     import torch.distributed as dist
-    from pointcontrast_b200 import _lib, me
+    from pointcontrast_b200 import _lib, fused, me
     from pointcontrast_b200.config import default_config
     from pointcontrast_b200.data import SyntheticPairLoader
     from pointcontrast_b200.trainer import get_trainer
@@ -297,10 +297,13 @@ def run_ours(args):
         except Exception:
             pass
         roof = {"kernel": dom, "bound": "hbm", "achieved": a["bytes"] / (a["ms"] / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
-                "frac": a["bytes"] / (a["ms"] / 1e3) / 1e9 / peak, "traffic": traffic, "peak_source": peak_src,
+                "frac": a["bytes"] / (a["ms"] / 1e3) / 1e9 / peak, "traffic": None if fused.PAIR else traffic, "peak_source": peak_src,
                 "launches_per_step": a["launches"], "avg_launch_ms": a["ms"] / a["launches"],
                 "alg_bytes_per_launch": a["bytes"] / a["launches"], "tensor_tflops": a["flops"] / (a["ms"] / 1e3) / 1e12,
                 "share_of_step": a["ms"] / (ms_total / args.steps),
+                "traffic_note": "ncu pass of the two-forward schedule (profiles/r1_launch_list.md)" if not fused.PAIR else
+                                f"no ncu pass of the stacked schedule yet (twice the rows per launch); the two-forward schedule "
+                                f"measured {traffic} dram bytes/launch (profiles/r1_launch_list.md)",
                 "other": {k: {"ms": v["ms"], "GB/s": v["bytes"] / (v["ms"] / 1e3) / 1e9, "launches": v["launches"]}
                           for k, v in agg.items() if k != dom}}
         if args.profile_json:
@@ -317,6 +320,8 @@ def run_ours(args):
                 "dtype": "f32 (bf16x3-split tensor-core products, fp32 accumulate)", "data": "synthetic",
                 "config": {"workload": wl["desc"], "loss": args.loss, "pairs_per_gpu": wl["batch"], "global_batch": pairs_per_step,
                            "voxels_per_view_per_rank": [n0, n1], "parallelism": f"dp{world}",
+                           "schedule": "both views stacked in one pass (per-view BatchNorm statistics)" if fused.PAIR
+                           else "two forward calls",
                            "l2": "per-step working set (activations + kernel maps, GBs) far exceeds the 126 MB L2; 2 distinct batches cycled",
                            "final_loss": float(loss[0] if isinstance(loss, tuple) else loss)},
                 "clocks": clk, "gpu_launches": int(launches),

@@ -158,6 +158,19 @@ int pcb_bn_backward2(const float* dY, int lddy, const float* X, int ldx, const f
                      const float* mean, const float* invstd, const float* gamma, float* dX, int lddx, float* dgamma,
                      float* dbeta, int accumulate_param_grads, float* gout, int ldg, int gout_mode, uint16_t* dXhi,
                      uint16_t* dXlo, int lds, void* ws, size_t ws_bytes, void* stream);
+/* Row-segmented variants: rows [0, n0) and [n0, n) are two independent BatchNorm batches -- the two views of a scene pair
+ * stacked in one feature matrix, each normalised with its own statistics exactly as the reference's two forward calls do
+ * (`lib/ddp_trainer.py:290-297,392-398`).  mean / invstd are [2][C]; the running statistics are updated with segment 0 and
+ * then with segment 1; dgamma / dbeta sum over both segments.  n0 == n degenerates to the single-batch functions above. */
+int pcb_bn_stats_seg(const float* X, int ldx, int64_t n, int64_t n0, int C, float eps, float momentum, float* mean, float* invstd,
+                     float* running_mean, float* running_var, void* ws, size_t ws_bytes, void* stream);
+int pcb_bn_apply_seg(const float* X, int ldx, int64_t n, int64_t n0, int C, const float* mean, const float* invstd,
+                     const float* gamma, const float* beta, const float* residual, int ldr, int relu, float* Y, int ldy,
+                     uint16_t* Yhi, uint16_t* Ylo, int lds, void* stream);
+int pcb_bn_backward_seg(const float* dY, int lddy, const float* X, int ldx, const float* relu_out, int ldm, int64_t n, int64_t n0,
+                        int C, const float* mean, const float* invstd, const float* gamma, float* dX, int lddx, float* dgamma,
+                        float* dbeta, int accumulate_param_grads, float* gout, int ldg, int gout_mode, uint16_t* dXhi,
+                        uint16_t* dXlo, int lds, void* ws, size_t ws_bytes, void* stream);
 /* "Split" operand format of the tensor-core conv kernels: an fp32 matrix stored as two bf16 planes, x ~= hi + lo (2^-17);
  * row stride lds in ELEMENTS.  The elementwise producers above can emit it directly (Yhi/Ylo, dXhi/dXlo; NULL = off; dX may
  * then be NULL), so the conv kernels' gather becomes a pure asynchronous copy.  pcb_split_rows converts an fp32 matrix. */

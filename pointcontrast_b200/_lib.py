@@ -53,6 +53,10 @@ _SIGS = {
     "pcb_bn_stats2": (_i, [_p, _i, _l, _i, _f, _f, _p, _p, _p, _p, _p, _sz, _p]),
     "pcb_bn_apply2": (_i, [_p, _i, _l, _i, _p, _p, _p, _p, _p, _i, _i, _p, _i, _p, _p, _i, _p]),
     "pcb_bn_backward2": (_i, [_p, _i, _p, _i, _p, _i, _l, _i, _p, _p, _p, _p, _i, _p, _p, _i, _p, _i, _i, _p, _p, _i, _p, _sz, _p]),
+    "pcb_bn_stats_seg": (_i, [_p, _i, _l, _l, _i, _f, _f, _p, _p, _p, _p, _p, _sz, _p]),
+    "pcb_bn_apply_seg": (_i, [_p, _i, _l, _l, _i, _p, _p, _p, _p, _p, _i, _i, _p, _i, _p, _p, _i, _p]),
+    "pcb_bn_backward_seg": (_i, [_p, _i, _p, _i, _p, _i, _l, _l, _i, _p, _p, _p, _p, _i, _p, _p, _i, _p, _i, _i, _p, _p, _i, _p, _sz,
+                                 _p]),
     "pcb_split_rows": (_i, [_p, _i, _l, _i, _p, _p, _i, _p]),
     "pcb_nce_ws_bytes": (_sz, [_l]),
     "pcb_nce_forward_backward": (_i, [_p, _p, _l, _i, _f, _p, _p, _p, _p, _sz, _p]),

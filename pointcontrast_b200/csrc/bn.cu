@@ -37,20 +37,27 @@ __global__ void split_rows_kernel(const float* __restrict__ X, int ldx, int64_t 
 // partial[chunk][0][C] = sum(a), partial[chunk][1][C] = sum(a*b)    (b == a for the forward statistics)
 // block: (C/4) channel-vectors x RP row lanes; grid: one CTA per chunk of rows.
 // Strides: lda / ldb / ldm (floats).  Mask (backward only): a is zeroed where mask <= 0 (ReLU folded into the BN backward).
+// Row segments: rows [0, n0) and [n0, n) are two independent BatchNorm batches (the two views of a pair stacked in one
+// matrix); chunks never straddle the boundary: CTAs [0, chunks0) cover segment 0, the rest segment 1.  n0 == n: one segment.
+// mean / invstd are [segments][C].
 template <bool TWO_INPUTS>
 __global__ void colsum_kernel(const float* __restrict__ A, int lda, const float* __restrict__ Bm, int ldb,
-                              const float* __restrict__ Mask, int ldm, int64_t n, int C,
+                              const float* __restrict__ Mask, int ldm, int64_t n, int64_t n0, int chunks0, int C,
                               const float* __restrict__ mean, const float* __restrict__ invstd, float* __restrict__ partial) {
   extern __shared__ float sm[];      // [RP][2][C]
   const int cv = C / 4;
   const int rp = blockDim.x / cv;    // row lanes
   const int c4 = threadIdx.x % cv;
   const int rl = threadIdx.x / cv;
-  const int64_t r0 = (int64_t)blockIdx.x * ROWS_PER_CHUNK;
-  const int64_t r1 = min(n, r0 + ROWS_PER_CHUNK);
+  const int seg = (int)blockIdx.x >= chunks0 ? 1 : 0;
+  const int64_t r0 = seg ? n0 + (int64_t)((int)blockIdx.x - chunks0) * ROWS_PER_CHUNK : (int64_t)blockIdx.x * ROWS_PER_CHUNK;
+  const int64_t r1 = min(seg ? n : n0, r0 + ROWS_PER_CHUNK);
   float4 s1 = make_float4(0, 0, 0, 0), s2 = make_float4(0, 0, 0, 0);
   float4 mu = make_float4(0, 0, 0, 0), is = make_float4(1, 1, 1, 1);
-  if (TWO_INPUTS && rl < rp) { mu = reinterpret_cast<const float4*>(mean)[c4]; is = reinterpret_cast<const float4*>(invstd)[c4]; }
+  if (TWO_INPUTS && rl < rp) {
+    mu = reinterpret_cast<const float4*>(mean + seg * C)[c4];
+    is = reinterpret_cast<const float4*>(invstd + seg * C)[c4];
+  }
   if (rl < rp) {
     for (int64_t r = r0 + rl; r < r1; r += rp) {
       float4 a = __ldg(reinterpret_cast<const float4*>(A + r * lda) + c4);
@@ -89,35 +96,46 @@ __device__ __forceinline__ void warp_sum2(const float* __restrict__ partial, int
   for (int o = 16; o; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
 }
 
-__global__ void bn_finalize_kernel(const float* __restrict__ partial, int chunks, int64_t n, int C, float eps, float momentum,
-                                   float* __restrict__ mean, float* __restrict__ invstd, float* running_mean, float* running_var) {
+// Segment s has chunks [s ? chunks0 : 0, ...) and n0 / n - n0 rows.  The running statistics see the segments one after
+// the other, as two forward calls would (`ddp_trainer.py:290-297`: the model runs on view 0, then on view 1).
+__global__ void bn_finalize_kernel(const float* __restrict__ partial, int chunks, int chunks0, int64_t n, int64_t n0, int C, float eps,
+                                   float momentum, float* __restrict__ mean, float* __restrict__ invstd, float* running_mean,
+                                   float* running_var) {
   int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (c >= C) return;
-  double s1, s2;
-  warp_sum2(partial, chunks, C, c, s1, s2);
-  if ((threadIdx.x & 31) != 0) return;
-  double m = s1 / (double)n;
-  double var = s2 / (double)n - m * m;
-  if (var < 0.0) var = 0.0;
-  mean[c] = (float)m;
-  invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
-  if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
-  if (running_var) {
-    double unb = n > 1 ? var * ((double)n / (double)(n - 1)) : var;
-    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
+  const int nseg = n0 < n ? 2 : 1;
+  for (int seg = 0; seg < nseg; ++seg) {
+    const float* p = partial + (seg ? (int64_t)chunks0 * 2 * C : 0);
+    const int ch = seg ? chunks - chunks0 : chunks0;
+    const int64_t rows = seg ? n - n0 : n0;
+    double s1, s2;
+    warp_sum2(p, ch, C, c, s1, s2);
+    if ((threadIdx.x & 31) == 0) {
+      double m = s1 / (double)rows;
+      double var = s2 / (double)rows - m * m;
+      if (var < 0.0) var = 0.0;
+      mean[seg * C + c] = (float)m;
+      invstd[seg * C + c] = (float)(1.0 / sqrt(var + (double)eps));
+      if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
+      if (running_var) {
+        double unb = rows > 1 ? var * ((double)rows / (double)(rows - 1)) : var;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
+      }
+    }
   }
 }
 
 __global__ void bn_apply_kernel(const float* __restrict__ X, int ldx, int64_t n4, int cv, const float* __restrict__ mean,
                                 const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
                                 const float* __restrict__ residual, int ldr, int relu, float* __restrict__ Y, int ldy,
-                                __nv_bfloat16* __restrict__ Yhi, __nv_bfloat16* __restrict__ Ylo, int lds) {
+                                __nv_bfloat16* __restrict__ Yhi, __nv_bfloat16* __restrict__ Ylo, int lds, int64_t n0) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n4) return;
   int c4 = (int)(i % cv);
   const int64_t row = i / cv;
+  const int so = row >= n0 ? cv : 0;          // statistics of this row's segment ([segments][C], in float4 units)
   float4 x = __ldg(reinterpret_cast<const float4*>(X + row * ldx) + c4);
-  float4 mu = reinterpret_cast<const float4*>(mean)[c4], is = reinterpret_cast<const float4*>(invstd)[c4];
+  float4 mu = reinterpret_cast<const float4*>(mean)[so + c4], is = reinterpret_cast<const float4*>(invstd)[so + c4];
   float4 g = reinterpret_cast<const float4*>(gamma)[c4], b = reinterpret_cast<const float4*>(beta)[c4];
   float4 y;
   y.x = (x.x - mu.x) * is.x * g.x + b.x; y.y = (x.y - mu.y) * is.y * g.y + b.y;
@@ -131,28 +149,37 @@ __global__ void bn_apply_kernel(const float* __restrict__ X, int ldx, int64_t n4
   if (Yhi) store_split4(y, Yhi + row * lds + c4 * 4, Ylo + row * lds + c4 * 4);
 }
 
-// dgamma = sum(dY*xhat), dbeta = sum(dY); also leaves them in ws for the apply pass
-// sums[0][C] = dbeta, sums[1][C] = dgamma for the apply pass; the parameter gradients are written or accumulated
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int chunks, int C, float* __restrict__ dgamma,
-                                       float* __restrict__ dbeta, int accumulate, float* __restrict__ sums) {
+// dgamma = sum(dY*xhat), dbeta = sum(dY) over ALL rows (both segments: the parameters are shared);
+// sums[seg][0][C] = that segment's dbeta, sums[seg][1][C] = its dgamma for the apply pass.
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int chunks, int chunks0, int nseg, int C,
+                                       float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate, float* __restrict__ sums) {
   int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (c >= C) return;
-  double s1, s2;
-  warp_sum2(partial, chunks, C, c, s1, s2);
+  float tb = 0.f, tg = 0.f;
+  for (int seg = 0; seg < nseg; ++seg) {
+    const float* p = partial + (seg ? (int64_t)chunks0 * 2 * C : 0);
+    const int ch = seg ? chunks - chunks0 : chunks0;
+    double s1, s2;
+    warp_sum2(p, ch, C, c, s1, s2);
+    if ((threadIdx.x & 31) == 0) {
+      sums[seg * 2 * C + c] = (float)s1;
+      sums[seg * 2 * C + C + c] = (float)s2;
+    }
+    if (seg == 0) { tb = (float)s1; tg = (float)s2; }
+    else { tb = (float)((double)tb + s1); tg = (float)((double)tg + s2); }
+  }
   if ((threadIdx.x & 31) != 0) return;
-  sums[c] = (float)s1;
-  sums[C + c] = (float)s2;
-  if (accumulate) { dbeta[c] += (float)s1; dgamma[c] += (float)s2; }
-  else { dbeta[c] = (float)s1; dgamma[c] = (float)s2; }
+  if (accumulate) { dbeta[c] += tb; dgamma[c] += tg; }
+  else { dbeta[c] = tb; dgamma[c] = tg; }
 }
 
 // gout_mode: 0 none, 1 write, 2 accumulate -- the (ReLU-masked) incoming gradient, i.e. the gradient of the residual input
 __global__ void bn_bwd_apply_kernel(const float* dY, int lddy, const float* __restrict__ X, int ldx,
-                                    const float* __restrict__ Mask, int ldm, int64_t n4, int cv, float inv_n,
-                                    const float* __restrict__ mean, const float* __restrict__ invstd,
-                                    const float* __restrict__ gamma, const float* __restrict__ dgamma,
-                                    const float* __restrict__ dbeta, float* __restrict__ dX, int lddx, float* gout, int ldg,
-                                    int gout_mode, __nv_bfloat16* __restrict__ dXhi, __nv_bfloat16* __restrict__ dXlo, int lds) {
+                                    const float* __restrict__ Mask, int ldm, int64_t n4, int cv, int64_t n0, float inv_n0,
+                                    float inv_n1, const float* __restrict__ mean, const float* __restrict__ invstd,
+                                    const float* __restrict__ gamma, const float* __restrict__ sums, float* __restrict__ dX, int lddx,
+                                    float* gout, int ldg, int gout_mode, __nv_bfloat16* __restrict__ dXhi,
+                                    __nv_bfloat16* __restrict__ dXlo, int lds) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n4) return;
   int c4 = (int)(i % cv);
@@ -169,9 +196,13 @@ __global__ void bn_bwd_apply_kernel(const float* dY, int lddy, const float* __re
     *gp = gv;
   }
   float4 x = __ldg(reinterpret_cast<const float4*>(X + row * ldx) + c4);
-  float4 mu = reinterpret_cast<const float4*>(mean)[c4], is = reinterpret_cast<const float4*>(invstd)[c4];
+  const bool second = row >= n0;
+  const int so = second ? cv : 0;
+  const float inv_n = second ? inv_n1 : inv_n0;
+  float4 mu = reinterpret_cast<const float4*>(mean)[so + c4], is = reinterpret_cast<const float4*>(invstd)[so + c4];
   float4 g = reinterpret_cast<const float4*>(gamma)[c4];
-  float4 dg = reinterpret_cast<const float4*>(dgamma)[c4], db = reinterpret_cast<const float4*>(dbeta)[c4];
+  // sums: [segment][dbeta | dgamma][C]
+  float4 db = reinterpret_cast<const float4*>(sums)[2 * so + c4], dg = reinterpret_cast<const float4*>(sums)[2 * so + cv + c4];
   float4 o;
   o.x = g.x * is.x * (dy.x - db.x * inv_n - (x.x - mu.x) * is.x * dg.x * inv_n);
   o.y = g.y * is.y * (dy.y - db.y * inv_n - (x.y - mu.y) * is.y * dg.y * inv_n);
@@ -193,28 +224,36 @@ inline int colsum_threads(int C) {       // (C/4) * row lanes, <= 256, at least 
 
 extern "C" size_t pcb_bn_ws_bytes(int64_t n, int C) {
   if (n < 1) n = 1;
-  return (size_t)(chunks_for(n) + 1) * 2 * C * sizeof(float) + 256;
+  // partial sums of <= chunks_for(n) + 1 chunks (two segments round up separately) + [2 segments][2][C] sums
+  return (size_t)(chunks_for(n) + 1 + 2) * 2 * C * sizeof(float) + 256;
 }
 
-extern "C" int pcb_bn_stats2(const float* X, int ldx, int64_t n, int C, float eps, float momentum, float* mean, float* invstd,
-                             float* running_mean, float* running_var, void* ws, size_t ws_bytes, void* stream) {
-  PCB_ARG(X && mean && invstd && ws && n >= 1 && C >= 4 && C % 4 == 0 && C <= 1024 && ldx >= C && ldx % 4 == 0);
+// n0: rows [0, n0) and [n0, n) are separate BatchNorm batches (n0 == n: one batch).  mean / invstd: [segments][C].
+extern "C" int pcb_bn_stats_seg(const float* X, int ldx, int64_t n, int64_t n0, int C, float eps, float momentum, float* mean,
+                                float* invstd, float* running_mean, float* running_var, void* ws, size_t ws_bytes, void* stream) {
+  PCB_ARG(X && mean && invstd && ws && n >= 1 && n0 >= 1 && n0 <= n && C >= 4 && C % 4 == 0 && C <= 1024 && ldx >= C && ldx % 4 == 0);
   PCB_ARG(ws_bytes >= pcb_bn_ws_bytes(n, C) - 256);
   cudaStream_t st = (cudaStream_t)stream;
-  const int chunks = chunks_for(n);
+  const int chunks0 = chunks_for(n0);
+  const int chunks = chunks0 + (n0 < n ? chunks_for(n - n0) : 0);
   const int thr = colsum_threads(C);
   const int rp = thr / (C / 4);
-  colsum_kernel<false><<<chunks, thr, (size_t)rp * 2 * C * sizeof(float), st>>>(X, ldx, nullptr, 0, nullptr, 0, n, C, nullptr, nullptr,
-                                                                                 (float*)ws);
+  colsum_kernel<false><<<chunks, thr, (size_t)rp * 2 * C * sizeof(float), st>>>(X, ldx, nullptr, 0, nullptr, 0, n, n0, chunks0, C, nullptr,
+                                                                                 nullptr, (float*)ws);
   if (int e = check_launch("colsum_kernel")) return e;
-  bn_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>((const float*)ws, chunks, n, C, eps, momentum, mean, invstd, running_mean,
+  bn_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>((const float*)ws, chunks, chunks0, n, n0, C, eps, momentum, mean, invstd, running_mean,
                                                       running_var);
   return check_launch("bn_finalize_kernel");
 }
 
+extern "C" int pcb_bn_stats2(const float* X, int ldx, int64_t n, int C, float eps, float momentum, float* mean, float* invstd,
+                             float* running_mean, float* running_var, void* ws, size_t ws_bytes, void* stream) {
+  return pcb_bn_stats_seg(X, ldx, n, n, C, eps, momentum, mean, invstd, running_mean, running_var, ws, ws_bytes, stream);
+}
+
 extern "C" int pcb_bn_stats(const float* X, int64_t n, int C, float eps, float momentum, float* mean, float* invstd,
                             float* running_mean, float* running_var, void* ws, size_t ws_bytes, void* stream) {
-  return pcb_bn_stats2(X, C, n, C, eps, momentum, mean, invstd, running_mean, running_var, ws, ws_bytes, stream);
+  return pcb_bn_stats_seg(X, C, n, n, C, eps, momentum, mean, invstd, running_mean, running_var, ws, ws_bytes, stream);
 }
 
 extern "C" int pcb_split_rows(const float* X, int ldx, int64_t n, int C, uint16_t* hi, uint16_t* lo, int lds, void* stream) {
@@ -227,55 +266,74 @@ extern "C" int pcb_split_rows(const float* X, int ldx, int64_t n, int C, uint16_
   return check_launch("split_rows_kernel");
 }
 
-extern "C" int pcb_bn_apply2(const float* X, int ldx, int64_t n, int C, const float* mean, const float* invstd, const float* gamma,
-                             const float* beta, const float* residual, int ldr, int relu, float* Y, int ldy, uint16_t* Yhi,
-                             uint16_t* Ylo, int lds, void* stream) {
-  PCB_ARG(n >= 0 && C >= 4 && C % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && ldx >= C && ldy >= C);
+extern "C" int pcb_bn_apply_seg(const float* X, int ldx, int64_t n, int64_t n0, int C, const float* mean, const float* invstd,
+                                const float* gamma, const float* beta, const float* residual, int ldr, int relu, float* Y, int ldy,
+                                uint16_t* Yhi, uint16_t* Ylo, int lds, void* stream) {
+  PCB_ARG(n >= 0 && n0 >= 0 && n0 <= n && C >= 4 && C % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && ldx >= C && ldy >= C);
   if (n == 0) return PCB_OK;
   PCB_ARG(X && Y && mean && invstd && gamma && beta && (!residual || (ldr >= C && ldr % 4 == 0)));
   PCB_ARG(!Yhi || (Ylo && lds >= C && lds % 4 == 0));
   int64_t n4 = n * (C / 4);
   bn_apply_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(X, ldx, n4, C / 4, mean, invstd, gamma, beta, residual,
                                                                                  ldr, relu, Y, ldy, (__nv_bfloat16*)Yhi,
-                                                                                 (__nv_bfloat16*)Ylo, lds);
+                                                                                 (__nv_bfloat16*)Ylo, lds, n0);
   return check_launch("bn_apply_kernel");
+}
+
+extern "C" int pcb_bn_apply2(const float* X, int ldx, int64_t n, int C, const float* mean, const float* invstd, const float* gamma,
+                             const float* beta, const float* residual, int ldr, int relu, float* Y, int ldy, uint16_t* Yhi,
+                             uint16_t* Ylo, int lds, void* stream) {
+  return pcb_bn_apply_seg(X, ldx, n, n, C, mean, invstd, gamma, beta, residual, ldr, relu, Y, ldy, Yhi, Ylo, lds, stream);
 }
 
 extern "C" int pcb_bn_apply(const float* X, int64_t n, int C, const float* mean, const float* invstd, const float* gamma,
                             const float* beta, const float* residual, int relu, float* Y, void* stream) {
-  return pcb_bn_apply2(X, C, n, C, mean, invstd, gamma, beta, residual, C, relu, Y, C, nullptr, nullptr, 0, stream);
+  return pcb_bn_apply_seg(X, C, n, n, C, mean, invstd, gamma, beta, residual, C, relu, Y, C, nullptr, nullptr, 0, stream);
 }
 
-extern "C" int pcb_bn_backward2(const float* dY, int lddy, const float* X, int ldx, const float* relu_out, int ldm, int64_t n, int C,
-                                const float* mean, const float* invstd, const float* gamma, float* dX, int lddx, float* dgamma,
-                                float* dbeta, int accumulate_param_grads, float* gout, int ldg, int gout_mode, uint16_t* dXhi,
-                                uint16_t* dXlo, int lds, void* ws, size_t ws_bytes, void* stream) {
+extern "C" int pcb_bn_backward_seg(const float* dY, int lddy, const float* X, int ldx, const float* relu_out, int ldm, int64_t n,
+                                   int64_t n0, int C, const float* mean, const float* invstd, const float* gamma, float* dX, int lddx,
+                                   float* dgamma, float* dbeta, int accumulate_param_grads, float* gout, int ldg, int gout_mode,
+                                   uint16_t* dXhi, uint16_t* dXlo, int lds, void* ws, size_t ws_bytes, void* stream) {
   PCB_ARG(dY && X && mean && invstd && gamma && (dX || dXhi) && dgamma && dbeta && ws && n >= 1 && C >= 4 && C % 4 == 0 && C <= 1024);
+  PCB_ARG(n0 >= 1 && n0 <= n);
   PCB_ARG(lddy >= C && ldx >= C && lddy % 4 == 0 && ldx % 4 == 0 && (!dX || (lddx >= C && lddx % 4 == 0)));
   PCB_ARG(!dXhi || (dXlo && lds >= C && lds % 4 == 0));
   PCB_ARG(!relu_out || (ldm >= C && ldm % 4 == 0));
   PCB_ARG(gout_mode == 0 || (gout && ldg >= C && ldg % 4 == 0));
   PCB_ARG(ws_bytes >= pcb_bn_ws_bytes(n, C) - 256);
   cudaStream_t st = (cudaStream_t)stream;
-  const int chunks = chunks_for(n);
+  const int nseg = n0 < n ? 2 : 1;
+  const int chunks0 = chunks_for(n0);
+  const int chunks = chunks0 + (nseg == 2 ? chunks_for(n - n0) : 0);
   const int thr = colsum_threads(C);
   const int rp = thr / (C / 4);
   float* partial = (float*)ws;
-  float* sums = partial + (size_t)chunks * 2 * C;        // [2][C]: dbeta, dgamma of THIS call (the apply pass needs them)
-  colsum_kernel<true><<<chunks, thr, (size_t)rp * 2 * C * sizeof(float), st>>>(dY, lddy, X, ldx, relu_out, ldm, n, C, mean, invstd, partial);
+  float* sums = partial + (size_t)chunks * 2 * C;        // [segments][2][C]: dbeta, dgamma of THIS call (the apply pass needs them)
+  colsum_kernel<true><<<chunks, thr, (size_t)rp * 2 * C * sizeof(float), st>>>(dY, lddy, X, ldx, relu_out, ldm, n, n0, chunks0, C, mean,
+                                                                                invstd, partial);
   if (int e = check_launch("colsum_kernel<bwd>")) return e;
-  bn_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(partial, chunks, C, dgamma, dbeta, accumulate_param_grads, sums);
+  bn_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(partial, chunks, chunks0, nseg, C, dgamma, dbeta, accumulate_param_grads, sums);
   if (int e = check_launch("bn_bwd_finalize_kernel")) return e;
   int64_t n4 = n * (C / 4);
-  bn_bwd_apply_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(dY, lddy, X, ldx, relu_out, ldm, n4, C / 4, 1.0f / (float)n, mean,
-                                                                    invstd, gamma, sums + C, sums, dX, lddx, gout, ldg, gout_mode,
-                                                                    (__nv_bfloat16*)dXhi, (__nv_bfloat16*)dXlo, lds);
+  bn_bwd_apply_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(dY, lddy, X, ldx, relu_out, ldm, n4, C / 4, n0, 1.0f / (float)n0,
+                                                                    nseg == 2 ? 1.0f / (float)(n - n0) : 0.f, mean, invstd, gamma, sums,
+                                                                    dX, lddx, gout, ldg, gout_mode, (__nv_bfloat16*)dXhi,
+                                                                    (__nv_bfloat16*)dXlo, lds);
   return check_launch("bn_bwd_apply_kernel");
+}
+
+extern "C" int pcb_bn_backward2(const float* dY, int lddy, const float* X, int ldx, const float* relu_out, int ldm, int64_t n, int C,
+                                const float* mean, const float* invstd, const float* gamma, float* dX, int lddx, float* dgamma,
+                                float* dbeta, int accumulate_param_grads, float* gout, int ldg, int gout_mode, uint16_t* dXhi,
+                                uint16_t* dXlo, int lds, void* ws, size_t ws_bytes, void* stream) {
+  return pcb_bn_backward_seg(dY, lddy, X, ldx, relu_out, ldm, n, n, C, mean, invstd, gamma, dX, lddx, dgamma, dbeta,
+                             accumulate_param_grads, gout, ldg, gout_mode, dXhi, dXlo, lds, ws, ws_bytes, stream);
 }
 
 extern "C" int pcb_bn_backward(const float* dY, const float* X, int64_t n, int C, const float* mean, const float* invstd,
                                const float* gamma, float* dX, float* dgamma, float* dbeta, void* ws, size_t ws_bytes,
                                void* stream) {
-  return pcb_bn_backward2(dY, C, X, C, nullptr, 0, n, C, mean, invstd, gamma, dX, C, dgamma, dbeta, 0, nullptr, 0, 0, nullptr, nullptr,
-                          0, ws, ws_bytes, stream);
+  return pcb_bn_backward_seg(dY, C, X, C, nullptr, 0, n, n, C, mean, invstd, gamma, dX, C, dgamma, dbeta, 0, nullptr, 0, 0, nullptr,
+                             nullptr, 0, ws, ws_bytes, stream);
 }

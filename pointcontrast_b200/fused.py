@@ -14,6 +14,7 @@ This module runs the SAME graph (`pretrain/pointcontrast/model/res16unet.py:206-
 Numerics are those of the modular path (same kernels, same order of operations per element).
 """
 import ctypes
+import os
 
 import torch
 
@@ -21,6 +22,24 @@ from . import _lib, me
 from ._lib import check, lib, ptr, stream
 
 ENABLED = True
+# Both views of a pair batch in ONE pass (see `stack_views`): half the launches, twice the rows per launch on the deep,
+# latency-bound levels.  BatchNorm keeps the reference's per-view statistics through the row-segmented kernels.
+PAIR = os.environ.get("PCB_PAIR", "1") == "1"
+VIEW1_BATCH_OFFSET = 1 << 14      # batch indices of view 1 in a stacked tensor (packed keys hold batch < 65535)
+
+
+def stack_views(feats0, coords0, feats1, coords1, device):
+    """One SparseTensor holding view 0's rows followed by view 1's, view 1's batch indices shifted by VIEW1_BATCH_OFFSET.
+    Scenes never interact in the network (the batch index is part of the coordinate key), so every convolution of the
+    stacked tensor equals the two separate forwards row for row; on every strided level (rows in packed-key order,
+    batch most significant) view 0's rows still come first.  Returns (SparseTensor on `device`, rows of view 0)."""
+    if not coords0.is_cuda and coords0.shape[0] and int(coords0[:, 0].max()) >= VIEW1_BATCH_OFFSET:
+        raise _lib.PcbError(f"batch index >= {VIEW1_BATCH_OFFSET} cannot be stacked")
+    n0 = coords0.shape[0]
+    C = torch.cat([coords0.to(device, non_blocking=True).to(torch.int32), coords1.to(device, non_blocking=True).to(torch.int32)])
+    C[n0:, 0] += VIEW1_BATCH_OFFSET
+    F = torch.cat([feats0.to(device, non_blocking=True), feats1.to(device, non_blocking=True)])
+    return me.SparseTensor(F, coords=C), n0
 
 
 class Buf:
@@ -127,22 +146,24 @@ class Runner:
         bn = bnm.bn
         K, Cin, Cout = conv.kernel.shape
         n = plan.n_out
+        n0 = self.seg_of[id(plan)]                       # rows of view 0 at the output level (== n: a single view)
+        nseg = 2 if n0 < n else 1
         z = Buf.new(n, Cout, self.device)
         self._conv(a_in, plan.fwd_tbl, _kmap(plan.fwd_kmap), conv, False, n, z, False, plan=plan)
         if out is None:
             out = Buf.new(n, Cout, self.device, split=True)
-        mean = self._stat(Cout)
-        invstd = self._stat(Cout)
+        mean = self._stat(nseg * Cout)
+        invstd = self._stat(nseg * Cout)
         wsb = lib.pcb_bn_ws_bytes(n, Cout)
         ws = me.workspace(wsb, self.device)
         st = stream()
-        check(lib.pcb_bn_stats2(z.p, z.ld, n, Cout, bn.eps, bn.momentum, mean, invstd, bn.running_mean.data_ptr(),
-                                bn.running_var.data_ptr(), ptr(ws), wsb, st))
-        check(lib.pcb_bn_apply2(z.p, z.ld, n, Cout, mean, invstd, bn.weight.data_ptr(), bn.bias.data_ptr(),
-                                residual.p if residual is not None else None, residual.ld if residual is not None else 0,
-                                1 if relu else 0, out.p, out.ld, out.hi or None, out.lo or None, out.ld, st))
+        check(lib.pcb_bn_stats_seg(z.p, z.ld, n, n0, Cout, bn.eps, bn.momentum, mean, invstd, bn.running_mean.data_ptr(),
+                                   bn.running_var.data_ptr(), ptr(ws), wsb, st))
+        check(lib.pcb_bn_apply_seg(z.p, z.ld, n, n0, Cout, mean, invstd, bn.weight.data_ptr(), bn.bias.data_ptr(),
+                                   residual.p if residual is not None else None, residual.ld if residual is not None else 0,
+                                   1 if relu else 0, out.p, out.ld, out.hi or None, out.lo or None, out.ld, st))
         self.bns.append(bn)
-        self.tape.append((conv, bn, a_in, z, out, mean, invstd, plan, relu, residual))
+        self.tape.append((conv, bn, a_in, z, out, mean, invstd, plan, relu, residual, n0))
         return out
 
     def _stat(self, C):
@@ -161,14 +182,15 @@ class Runner:
             x = self._block(blk, x, plan3, plan1, out if i == len(blocks) - 1 else None)
         return x
 
-    def forward(self, sinput):
+    def forward(self, sinput, view0_rows=None):
+        """`view0_rows`: the input is a `stack_views` tensor whose first `view0_rows` rows are view 0."""
         m = self.model
         feats = sinput.F
         _lib.require_cuda(feats)
         self.device = feats.device
         cm = sinput.coords_man
         self.tape, self.bns = [], []
-        self.stats = torch.empty(2 * sum(mod.bn.num_features for mod in m.modules() if isinstance(mod, me.MinkowskiBatchNorm)),
+        self.stats = torch.empty(4 * sum(mod.bn.num_features for mod in m.modules() if isinstance(mod, me.MinkowskiBatchNorm)),
                                  dtype=torch.float32, device=self.device)
         self.stat_off = 0
         with torch.cuda.device(self.device):
@@ -184,6 +206,22 @@ class Runner:
             down = [cm.conv_plan(keys[i], keys[i + 1], kg2, False) for i in range(4)]
             up = [cm.conv_plan(keys[i + 1], keys[i], kg2, True) for i in range(4)]
             p0 = cm.conv_plan(keys[0], keys[0], m.conv0p1s1.kernel_generator, False)
+            if view0_rows is None or view0_rows >= n[0]:
+                seg = list(n)
+            else:                                # rows of view 0 per level: strided levels are sorted by key, batch most significant
+                if view0_rows < 1:
+                    raise _lib.PcbError("view 0 of a stacked pair is empty")
+                thr = VIEW1_BATCH_OFFSET << 48
+                cnt = torch.stack([(cm.levels[k.ts].keys < thr).sum() for k in keys[1:]]).tolist()
+                seg = [int(view0_rows)] + [int(c) for c in cnt]
+            self.seg_of = {id(p0): seg[0]}
+            for l in range(5):
+                self.seg_of[id(p3[l])] = seg[l]
+                self.seg_of[id(p1[l])] = seg[l]
+            for i in range(4):
+                self.seg_of[id(down[i])] = seg[i + 1]
+                self.seg_of[id(up[i])] = seg[i]
+            calls = 2 if seg[0] < n[0] else 1
             P = m.PLANES
             x_in = feats.detach().contiguous().float()
             a0 = Buf([x_in], x_in.data_ptr(), n[0], x_in.shape[1], x_in.shape[1], self.device)
@@ -217,7 +255,7 @@ class Runner:
             self._conv(x, p1[0].fwd_tbl, None, fin, False, n[0], out, False,
                        bias=fin.bias.detach().reshape(-1) if fin.bias is not None else None, plan=p1[0])
             for bn in self.bns:
-                bn.num_batches_tracked += 1
+                bn.num_batches_tracked += calls
         ctx = (self.tape, x, p1[0], self.stats)
         self.tape = None
         return out_t, ctx
@@ -242,7 +280,7 @@ class Runner:
             self._conv(dfin, p_final.dg_tbl, _kmap(p_final.dg_kmap), fin, True, p_final.n_in, gx, False, plan=p_final)
             x_last.slot[0] = True
             st = stream()
-            for (conv, bn, a_in, z, out, mean, invstd, plan, relu, residual) in reversed(tape):
+            for (conv, bn, a_in, z, out, mean, invstd, plan, relu, residual, n0) in reversed(tape):
                 K, Cin, Cout = conv.kernel.shape
                 n = plan.n_out
                 g = out.grad()
@@ -260,9 +298,10 @@ class Runner:
                         prm.grad = torch.zeros_like(prm)
                 wsb = lib.pcb_bn_ws_bytes(n, Cout)
                 ws = me.workspace(wsb, dev)
-                check(lib.pcb_bn_backward2(g.p, g.ld, z.p, z.ld, out.p if relu else None, out.ld, n, Cout, mean, invstd,
-                                           bn.weight.data_ptr(), dz.p or None, dz.ld, bn.weight.grad.data_ptr(), bn.bias.grad.data_ptr(), 1,
-                                           gout_p, gout_ld, gout_mode, dz.hi or None, dz.lo or None, dz.ld, ptr(ws), wsb, st))
+                check(lib.pcb_bn_backward_seg(g.p, g.ld, z.p, z.ld, out.p if relu else None, out.ld, n, n0, Cout, mean, invstd,
+                                              bn.weight.data_ptr(), dz.p or None, dz.ld, bn.weight.grad.data_ptr(),
+                                              bn.bias.grad.data_ptr(), 1, gout_p, gout_ld, gout_mode, dz.hi or None, dz.lo or None,
+                                              dz.ld, ptr(ws), wsb, st))
                 self._wgrad(conv, plan, a_in, dz)
                 if a_in.slot[0] is not None:
                     ga = a_in.grad()
@@ -272,8 +311,8 @@ class Runner:
 
 class _FusedFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, anchor, runner, sinput):
-        out, fctx = runner.forward(sinput)
+    def forward(ctx, anchor, runner, sinput, view0_rows):
+        out, fctx = runner.forward(sinput, view0_rows)
         ctx.runner, ctx.fctx = runner, fctx
         return out
 
@@ -281,18 +320,22 @@ class _FusedFunction(torch.autograd.Function):
     def backward(ctx, d_out):
         ctx.runner.backward(ctx.fctx, d_out)
         ctx.fctx = None
-        return None, None, None
+        return None, None, None, None
+
+
+def applicable_on(model, device):
+    return (ENABLED and model.training and torch.is_grad_enabled() and torch.device(device).type == "cuda"
+            and me.CONV_IMPL == "tcgen05" and not me.FORCE_SIMT)
 
 
 def applicable(model, sinput):
-    return (ENABLED and model.training and torch.is_grad_enabled() and sinput.F.is_cuda and me.CONV_IMPL == "tcgen05"
-            and not me.FORCE_SIMT)
+    return applicable_on(model, sinput.F.device)
 
 
-def run(model, sinput):
+def run(model, sinput, view0_rows=None):
     """Final-layer features [N, out_channels] (before the optional L2 normalisation) as ONE autograd node."""
     runner = model.__dict__.get("_fused_runner")
     if runner is None:
         runner = Runner(model)
         model.__dict__["_fused_runner"] = runner
-    return _FusedFunction.apply(runner.anchor, runner, sinput)
+    return _FusedFunction.apply(runner.anchor, runner, sinput, view0_rows)

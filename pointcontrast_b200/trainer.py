@@ -117,6 +117,9 @@ class ContrastiveLossTrainer:
     # -- shared step pieces
     def _forward_views(self, input_dict):
         dev = self.device
+        if hasattr(self.model, "forward_pair"):
+            return self.model.forward_pair(input_dict["sinput0_F"], input_dict["sinput0_C"], input_dict["sinput1_F"],
+                                           input_dict["sinput1_C"], dev)
         s0 = ME.SparseTensor(input_dict["sinput0_F"], coords=input_dict["sinput0_C"]).to(dev)
         F0 = self.model(s0).F
         s1 = ME.SparseTensor(input_dict["sinput1_F"], coords=input_dict["sinput1_C"]).to(dev)

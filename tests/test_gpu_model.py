@@ -176,3 +176,50 @@ def test_fused_executor_matches_modular_path():
             assert rel_err(a[4][n], b[4][n]) < 1e-5, n
         else:
             assert (a[4][n] == b[4][n]).all(), n
+
+
+def test_stacked_pair_pass_matches_two_forwards():
+    """`forward_pair` with fused.PAIR: both views in one stacked pass (view 1's batch indices shifted, BatchNorm statistics
+    per view through the row-segmented kernels) vs the reference's two forward calls: features, loss, every parameter
+    gradient and the running statistics.  The passes differ only in fp32 summation order (split points of the small
+    levels, one weight-gradient reduction instead of two); the network amplifies that to ~2e-4 on the features (each pass
+    is ~3e-4 from the fp64 oracle, `__graft_entry__.smoke`) and the ill-conditioned backward further (see _grad_tol)."""
+    from pointcontrast_b200 import fused, losses, synth
+    batch = synth.collate_pairs([synth.synth_pair(5, scale=0.15), synth.synth_pair(6, scale=0.12)])
+    rng = np.random.default_rng(1)
+    pairs = batch["correspondences"]
+    nq = len(np.unique(pairs[:, 0]))
+    q, k = loss_cpu.select_positives(pairs, rng.random(nq).astype(np.float32), 4096,
+                                     rng.choice(nq, 4096, replace=False) if nq > 4096 else None)
+    out = {}
+    saved = fused.PAIR
+    for mode in (True, False):
+        fused.PAIR = mode
+        try:
+            net = _gpu_net(4)
+            F0, F1 = net.forward_pair(torch.from_numpy(batch["sinput0_F"]), torch.from_numpy(batch["sinput0_C"]),
+                                      torch.from_numpy(batch["sinput1_F"]), torch.from_numpy(batch["sinput1_C"]), torch.device("cuda"))
+            assert F0.shape[0] == len(batch["sinput0_C"]) and F1.shape[0] == len(batch["sinput1_C"])
+            loss = losses.point_nce_loss(F0, F1, q.cuda(), k.cuda(), 0.4)
+            loss.backward()
+            out[mode] = (F0.detach(), F1.detach(), float(loss.detach()), {n: p.grad.clone() for n, p in net.named_parameters()},
+                         {n: b.clone() for n, b in net.named_buffers()})
+        finally:
+            fused.PAIR = saved
+    a, b = out[True], out[False]
+    errs = sorted((rel_err(a[3][n], b[3][n]), n) for n in b[3])
+    stats = max((rel_err(a[4][n], b[4][n]), n) for n in b[4] if b[4][n].dtype.is_floating_point)
+    report = {"F0": max_rel_err(a[0], b[0]), "F1": max_rel_err(a[1], b[1]), "loss": abs(a[2] - b[2]) / abs(b[2]),
+              "grad_worst": errs[-1], "grad_median": errs[len(errs) // 2], "running_stats_worst": stats}
+    if os.environ.get("PCB_REPORT_DIR"):
+        import json
+        json.dump(report, open(os.path.join(os.environ["PCB_REPORT_DIR"], "stacked_vs_two_forwards.json"), "w"), indent=1)
+    assert report["F0"] < 1e-3 and report["F1"] < 1e-3 and report["loss"] < 1e-5, report
+    # measured (gpurun_out r44): features 1.9e-4 / 2.1e-4, loss 6e-8, gradients median 1.2e-2 / worst 1.6e-2, running
+    # statistics 1.2e-5.  The gradient spread is the tensor-core path's own distance from fp64 on these tiny scenes
+    # (median 2.3e-2, worst 3.5e-2 against a plain-fp32 floor of 3e-3 / 6e-3: test_small_scene_against_live_oracle...).
+    assert errs[-1][0] < 5e-2 and errs[len(errs) // 2][0] < 3e-2, report
+    assert stats[0] < 1e-3, report
+    for n in b[4]:
+        if not b[4][n].dtype.is_floating_point:
+            assert (a[4][n] == b[4][n]).all(), n

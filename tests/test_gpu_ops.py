@@ -321,3 +321,57 @@ def test_split_operand_conv_forward_matches_fp32_input_kernel(cin, cout):
                                      me._c_int_array(opp), 27, n, cout, cin, ptr(dt), None, ptr(got_dx), cin, ptr(ws), wsb, 0, stream()))
     torch.cuda.synchronize()
     assert max_rel_err(got_dx, ref_dx) < 1e-5
+
+
+@pytest.mark.parametrize("n0,n1,C", [(5000, 3777, 32), (130, 1, 96), (128, 128, 64), (1, 300, 256)])
+def test_segmented_batchnorm_equals_two_batches(n0, n1, C):
+    """pcb_bn_*_seg: rows [0,n0) and [n0,n0+n1) normalised as two batches (the two views of a pair stacked in one matrix)
+    == torch BatchNorm1d applied to view 0 and then to view 1 (fp64), including the sequential running-stat updates and
+    the summed parameter gradients; residual + ReLU folded in as in the fused executor."""
+    from pointcontrast_b200 import _lib
+    from pointcontrast_b200._lib import check, lib, ptr, stream
+    n = n0 + n1
+    g = torch.Generator().manual_seed(n + C)
+    x = torch.randn(n, C, generator=g, dtype=torch.float64) * 1.5 + 0.3
+    res = torch.randn(n, C, generator=g, dtype=torch.float64)
+    dy = torch.randn(n, C, generator=g, dtype=torch.float64)
+    w = torch.rand(C, generator=g, dtype=torch.float64) + 0.5
+    b = torch.randn(C, generator=g, dtype=torch.float64)
+    ref = torch.nn.BatchNorm1d(C, momentum=0.1).double()
+    with torch.no_grad():
+        ref.weight.copy_(w); ref.bias.copy_(b)
+    xo = x.clone().requires_grad_(True)
+    ro = res.clone().requires_grad_(True)
+    if n0 > 1 and n1 > 1:
+        yo = torch.relu(torch.cat([ref(xo[:n0]), ref(xo[n0:])]) + ro)
+        yo.backward(dy)
+    dev = torch.device("cuda")
+    X, R, DY = x.float().to(dev), res.float().to(dev), dy.float().to(dev)
+    W, B = w.float().to(dev), b.float().to(dev)
+    mean = torch.empty(2, C, device=dev); invstd = torch.empty(2, C, device=dev)
+    rm = torch.zeros(C, device=dev); rv = torch.ones(C, device=dev)
+    wsb = lib.pcb_bn_ws_bytes(n, C)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    Y = torch.empty(n, C, device=dev)
+    hi = torch.empty(n, C, dtype=torch.bfloat16, device=dev); lo = torch.empty(n, C, dtype=torch.bfloat16, device=dev)
+    st = stream()
+    check(lib.pcb_bn_stats_seg(ptr(X), C, n, n0, C, 1e-5, 0.1, ptr(mean), ptr(invstd), ptr(rm), ptr(rv), ptr(ws), wsb, st))
+    check(lib.pcb_bn_apply_seg(ptr(X), C, n, n0, C, ptr(mean), ptr(invstd), ptr(W), ptr(B), ptr(R), C, 1, ptr(Y), C, ptr(hi), ptr(lo), C, st))
+    for s, (a, e) in enumerate(((0, n0), (n0, n))):
+        m = x[a:e].mean(0); v = x[a:e].var(0, unbiased=False)
+        assert rel_err(mean[s], m) < 1e-5
+        if e - a > 1:       # one row: x - mean == 0 whatever invstd is (E[x^2] - mean^2 cancels to ~1e-7 x^2 next to eps = 1e-5)
+            assert rel_err(invstd[s], 1 / torch.sqrt(v + 1e-5)) < 1e-5
+        else:
+            assert rel_err(invstd[s], 1 / torch.sqrt(v + 1e-5)) < 5e-2
+    assert max_rel_err(hi.float() + lo.float(), Y) < 1e-4
+    if not (n0 > 1 and n1 > 1):
+        return
+    assert max_rel_err(Y, yo) < 1e-4
+    assert rel_err(rm, ref.running_mean) < 1e-5 and rel_err(rv, ref.running_var) < 1e-5
+    dX = torch.empty(n, C, device=dev); dW = torch.zeros(C, device=dev); dB = torch.zeros(C, device=dev)
+    gout = torch.empty(n, C, device=dev)
+    check(lib.pcb_bn_backward_seg(ptr(DY), C, ptr(X), C, ptr(Y), C, n, n0, C, ptr(mean), ptr(invstd), ptr(W), ptr(dX), C, ptr(dW), ptr(dB), 1,
+                                  ptr(gout), C, 1, None, None, 0, ptr(ws), wsb, st))
+    assert max_rel_err(dX, xo.grad) < 1e-4 and max_rel_err(gout, ro.grad) < 1e-5
+    assert rel_err(dW, ref.weight.grad) < 1e-4 and rel_err(dB, ref.bias.grad) < 1e-4
