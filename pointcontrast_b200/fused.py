@@ -26,6 +26,9 @@ ENABLED = True
 # latency-bound levels.  BatchNorm keeps the reference's per-view statistics through the row-segmented kernels.
 PAIR = os.environ.get("PCB_PAIR", "1") == "1"
 VIEW1_BATCH_OFFSET = 1 << 14      # batch indices of view 1 in a stacked tensor (packed keys hold batch < 65535)
+# EXPERIMENTAL, off by default, not yet measured on a GPU: weight gradients on a second CUDA stream, concurrent with the
+# data-gradient chain of the reverse sweep (they only share the read-only dz / activation planes).
+WGRAD_STREAM = os.environ.get("PCB_WGRAD_STREAM", "0") == "1"
 
 
 def stack_views(feats0, coords0, feats1, coords1, device):
@@ -118,7 +121,21 @@ class Runner:
             check(lib.pcb_conv_forward(x.p, x.ld, ptr(tbl), tbl.shape[1], kmap, K, n_out, Cin, Cout, None, None, None, None,
                                        ptr(kern.detach()), ptr(bias), out.p, out.ld, None, 0, 0, st))
 
-    def _wgrad(self, conv, plan, a_in, dz):
+    def _wgrad_side(self, conv, plan, a_in, dz):
+        """`_wgrad` on the side stream: ordered after everything issued so far on the current stream (dz is ready), own
+        workspace slot; the caller joins the streams at the end of the sweep."""
+        side = self.__dict__.get("_side_stream")
+        if side is None:
+            side = self._side_stream = torch.cuda.Stream(device=self.device)
+        ev = torch.cuda.Event()
+        ev.record()
+        with torch.cuda.stream(side):
+            side.wait_event(ev)
+            self._wgrad(conv, plan, a_in, dz, slot=3)
+        for t in dz.owner:                         # dz is released by the main-stream loop while the side stream reads it
+            t.record_stream(side)
+
+    def _wgrad(self, conv, plan, a_in, dz, slot=0):
         kern = conv.kernel
         K, Cin, Cout = kern.shape
         if kern.grad is None:
@@ -130,12 +147,12 @@ class Runner:
         ev = me._prof_begin()
         if Ca % 32 == 0 and Cb % 32 == 0:
             wsb = lib.pcb_conv_wgrad_split_ws_bytes(K, rows, Ca, Cb)
-            ws = me.workspace(wsb, self.device)
+            ws = me.workspace(wsb, self.device, slot=slot)
             check(lib.pcb_conv_wgrad_split(A.hi, A.lo, A.ld, B.hi, B.lo, B.ld, ptr(plan.wg_tbl), plan.wg_tbl.shape[1], K, rows, Ca, Cb,
                                            kern.grad.data_ptr(), tr, ptr(ws), wsb, 4, stream()))
         else:
             wsb = lib.pcb_conv_wgrad_ws_bytes(K, rows, Ca, Cb)
-            ws = me.workspace(wsb, self.device)
+            ws = me.workspace(wsb, self.device, slot=slot)
             check(lib.pcb_conv_wgrad(A.p, A.ld, B.p, B.ld, ptr(plan.wg_tbl), plan.wg_tbl.shape[1], K, rows, Ca, Cb, kern.grad.data_ptr(),
                                      tr, ptr(ws), wsb, 4, stream()))
         me._prof_end(ev, "wgrad", plan, K, Cin, Cout, Ca % 32 == 0 and Cb % 32 == 0)
@@ -302,11 +319,16 @@ class Runner:
                                               bn.weight.data_ptr(), dz.p or None, dz.ld, bn.weight.grad.data_ptr(),
                                               bn.bias.grad.data_ptr(), 1, gout_p, gout_ld, gout_mode, dz.hi or None, dz.lo or None,
                                               dz.ld, ptr(ws), wsb, st))
-                self._wgrad(conv, plan, a_in, dz)
+                if WGRAD_STREAM:
+                    self._wgrad_side(conv, plan, a_in, dz)
+                else:
+                    self._wgrad(conv, plan, a_in, dz)
                 if a_in.slot[0] is not None:
                     ga = a_in.grad()
                     self._conv(dz, plan.dg_tbl, _kmap(plan.dg_kmap), conv, True, plan.n_in, ga, bool(a_in.slot[0]), plan=plan)
                     a_in.slot[0] = True
+            if WGRAD_STREAM and self.__dict__.get("_side_stream") is not None:
+                torch.cuda.current_stream().wait_stream(self._side_stream)
 
 
 class _FusedFunction(torch.autograd.Function):
