@@ -73,3 +73,39 @@ def test_reference_arm_json_contract():
     assert line["impl"] == "reference" and line["unit"] == "pairs/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+
+
+def test_stacked_views_are_block_diagonal_on_the_oracle():
+    """The invariant behind `fused.stack_views`: with view 1's batch indices shifted by 2^14, every strided level keeps view
+    0's rows first, and every kernel map of the stacked coordinates is the union of the two per-view maps with view 1's row
+    indices shifted -- scenes never interact."""
+    from pointcontrast_b200 import synth
+    from pointcontrast_b200.fused import VIEW1_BATCH_OFFSET
+    b = synth.synth_batch(5, 2, scale=0.15)
+    c0, c1 = b["sinput0_C"], b["sinput1_C"].copy()
+    c1s = c1.copy(); c1s[:, 0] += VIEW1_BATCH_OFFSET
+    lv0, lv1, lvs = [c0], [c1], [np.concatenate([c0, c1s])]
+    for ts in (2, 4, 8, 16):
+        lv0.append(OR.stride_coords(lv0[-1], ts)); lv1.append(OR.stride_coords(lv1[-1], ts)); lvs.append(OR.stride_coords(lvs[-1], ts))
+    for l in range(5):
+        n0 = len(lv0[l])
+        assert len(lvs[l]) == n0 + len(lv1[l])
+        assert (lvs[l][:n0] == lv0[l]).all()
+        back = lvs[l][n0:].copy(); back[:, 0] -= VIEW1_BATCH_OFFSET
+        assert (back == lv1[l]).all()
+    ts = 1
+    for l in range(5):
+        n0 = len(lv0[l])
+        offs = OR.hypercube_offsets([3, 3, 3]) * ts
+        ms, m0, m1 = (OR.kernel_map(c, c, offs) for c in (lvs[l], lv0[l], lv1[l]))
+        for k in range(27):
+            want = set(zip(m0[k][0].tolist(), m0[k][1].tolist())) | set(zip((m1[k][0] + n0).tolist(), (m1[k][1] + n0).tolist()))
+            assert set(zip(ms[k][0].tolist(), ms[k][1].tolist())) == want
+        if l < 4:
+            n0c = len(lv0[l + 1])
+            offs2 = OR.hypercube_offsets([2, 2, 2]) * ts
+            ms, m0, m1 = (OR.kernel_map(f, c, offs2) for f, c in ((lvs[l], lvs[l + 1]), (lv0[l], lv0[l + 1]), (lv1[l], lv1[l + 1])))
+            for k in range(8):
+                want = set(zip(m0[k][0].tolist(), m0[k][1].tolist())) | set(zip((m1[k][0] + n0).tolist(), (m1[k][1] + n0c).tolist()))
+                assert set(zip(ms[k][0].tolist(), ms[k][1].tolist())) == want
+        ts *= 2
