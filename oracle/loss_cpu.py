@@ -3,10 +3,12 @@
 The reference draws its random subsets from process-global RNGs (`lib/ddp_trainer.py:199-200,203,404,413`).
 For parity the draws are *injected*: every function here takes the already-chosen indices.
 
-PINNED: `hardest_contrastive_loss` is checked against the reference's own unmodified function
-(`HardestContrastiveLossTrainer.contrastive_hardest_negative_loss`, `lib/ddp_trainer.py:186-238`) in
-tests/test_oracle_loss.py (runs where /root/reference exists).  `point_nce_loss` restates
-`lib/ddp_trainer.py:400-426` + `lib/criterion.py:15-19` (those lines hard-code `.cuda()`, so cannot run here).
+PINNED against the reference's own unmodified code (tests/test_oracle_reference.py, runs where /root/reference exists):
+  * `hardest_contrastive_loss` == `HardestContrastiveLossTrainer.contrastive_hardest_negative_loss`
+    (`lib/ddp_trainer.py:186-238`), same numpy RNG draws, rtol 1e-12;
+  * `select_positives` + `point_nce_loss` == the loss and gradients of `PointNCELossTrainer._train_iter`
+    (`lib/ddp_trainer.py:380-440` + `lib/criterion.py:10-19`) executed on the CPU with its hard-coded `.cuda()` calls
+    patched to identity and a stand-in model, same torch / numpy RNG draws, rtol 1e-12.
 """
 import numpy as np
 import torch
