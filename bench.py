@@ -42,7 +42,7 @@ WORKLOADS = {   # per-rank batch, synthetic scale -> ~voxels/view
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--loss", default="nce", choices=["nce", "hardest"])
