@@ -117,9 +117,12 @@ class Runner:
             check(lib.pcb_conv_forward_split(x.hi, x.lo, x.ld, ptr(tbl), tbl.shape[1], kmap, K, n_out, Cin, Cout, ptr(wt),
                                              ptr(bias), out.p, out.ld, ptr(ws), wsb, flags, st))
         else:
-            assert not accumulate and not transposed_roles
+            # exact fp32 SIMT kernel: the 3-channel stem and output widths the tensor-core tiling does not cover (13 / 20
+            # semantic classes); as a data gradient it runs on the per-offset transposed weights
+            assert not accumulate and x.p, "the fp32 SIMT conv writes (never accumulates) and reads the fp32 plane"
+            w = kern.detach().transpose(1, 2).contiguous() if transposed_roles else kern.detach()
             check(lib.pcb_conv_forward(x.p, x.ld, ptr(tbl), tbl.shape[1], kmap, K, n_out, Cin, Cout, None, None, None, None,
-                                       ptr(kern.detach()), ptr(bias), out.p, out.ld, None, 0, 0, st))
+                                       ptr(w), ptr(bias), out.p, out.ld, None, 0, 0, st))
 
     def _wgrad_side(self, conv, plan, a_in, dz):
         """`_wgrad` on the side stream: ordered after everything issued so far on the current stream (dz is ready), own
@@ -286,8 +289,11 @@ class Runner:
         self.device = dev
         with torch.cuda.device(dev):
             fin = m.final
-            dfin = Buf.new(d_out.shape[0], d_out.shape[1], dev, fp32=False, split=True)
-            check(lib.pcb_split_rows(d_out.data_ptr(), d_out.shape[1], d_out.shape[0], d_out.shape[1], dfin.hi, dfin.lo, dfin.ld, stream()))
+            if fin.out_channels % 32 == 0:
+                dfin = Buf.new(d_out.shape[0], d_out.shape[1], dev, fp32=False, split=True)
+                check(lib.pcb_split_rows(d_out.data_ptr(), d_out.shape[1], d_out.shape[0], d_out.shape[1], dfin.hi, dfin.lo, dfin.ld, stream()))
+            else:                                # e.g. 13 / 20 classes: the final layer's backward runs on the exact fp32 kernels
+                dfin = Buf([d_out], d_out.data_ptr(), d_out.shape[0], d_out.shape[1], d_out.shape[1], dev)
             if fin.bias is not None:
                 if fin.bias.grad is None:
                     fin.bias.grad = torch.zeros_like(fin.bias)
@@ -345,13 +351,68 @@ class _FusedFunction(torch.autograd.Function):
         return None, None, None, None
 
 
+_STAGES = ("block1", "block2", "block3", "block4", "block5", "block6", "block7", "block8")
+_UNITS = (("conv0p1s1", "bn0"), ("conv1p1s2", "bn1"), ("conv2p2s2", "bn2"), ("conv3p4s2", "bn3"), ("conv4p8s2", "bn4"),
+          ("convtr4p16s2", "bntr4"), ("convtr5p8s2", "bntr5"), ("convtr6p4s2", "bntr6"), ("convtr7p2s2", "bntr7"))
+
+
+def matches(model):
+    """Is `model` wired like `pretrain/pointcontrast/model/res16unet.py:36-268` (Res16UNet with BasicBlock stages)?  The
+    executor reads the graph from the attribute names, so ANY class with this wiring -- this package's model file or the
+    reference's own, unmodified -- runs fused.  Also checks what the tensor-core tiling needs (all hidden widths % 32)."""
+    ok = model.__dict__.get("_fused_ok")
+    if ok is None:
+        ok = _matches(model)
+        model.__dict__["_fused_ok"] = ok
+    return ok
+
+
+def _matches(m):
+    try:
+        for c, b in _UNITS:
+            if not isinstance(getattr(m, c), me._ConvolutionBase) or not isinstance(getattr(m, b), me.MinkowskiBatchNorm):
+                return False
+        if not isinstance(m.final, me.MinkowskiConvolution) or m.final.kernel_volume != 1:
+            return False
+        widths = [m.INIT_DIM] + list(m.PLANES)
+        for name in _STAGES:
+            for blk in getattr(m, name):
+                if not all(isinstance(getattr(blk, a), t) for a, t in (("conv1", me.MinkowskiConvolution), ("conv2", me.MinkowskiConvolution),
+                                                                       ("norm1", me.MinkowskiBatchNorm), ("norm2", me.MinkowskiBatchNorm))):
+                    return False
+                if hasattr(blk, "conv3") or (blk.downsample is not None and len(blk.downsample) != 2):
+                    return False
+                widths += [blk.conv1.in_channels, blk.conv1.out_channels, blk.conv2.out_channels]
+        if m.conv0p1s1.out_channels != m.INIT_DIM or m.final.in_channels != m.PLANES[7]:
+            return False
+        return all(w % 32 == 0 for w in widths) and m.conv0p1s1.in_channels % 32 != 0      # exact fp32 stem (3 input channels)
+    except (AttributeError, TypeError):
+        return False
+
+
 def applicable_on(model, device):
     return (ENABLED and model.training and torch.is_grad_enabled() and torch.device(device).type == "cuda"
-            and me.CONV_IMPL == "tcgen05" and not me.FORCE_SIMT)
+            and me.CONV_IMPL == "tcgen05" and not me.FORCE_SIMT and matches(model))
 
 
 def applicable(model, sinput):
     return applicable_on(model, sinput.F.device)
+
+
+def forward_pair(model, feats0, coords0, feats1, coords1, device):
+    """Features (F0, F1) of the two views of a pair batch -- what `lib/ddp_trainer.py:290-297,392-398` gets from two
+    calls of the model.  With the fused executor both views go through ONE stacked pass (`stack_views`), each BatchNorm
+    still normalising every view with its own statistics; otherwise this is the two calls.  Works for any model class
+    that `matches` (this package's or the reference's own `model/res16unet.py`)."""
+    if PAIR and isinstance(model, me.MinkowskiNetwork) and applicable_on(model, device) and len(coords0) and len(coords1):
+        s, n0 = stack_views(feats0, coords0, feats1, coords1, device)
+        F = run(model, s, n0)
+        if getattr(model, "normalize_feature", False):
+            F = F / torch.norm(F, p=2, dim=1, keepdim=True)
+        return F[:n0], F[n0:]
+    F0 = model(me.SparseTensor(feats0, coords=coords0).to(device)).F
+    F1 = model(me.SparseTensor(feats1, coords=coords1).to(device)).F
+    return F0, F1
 
 
 def run(model, sinput, view0_rows=None):

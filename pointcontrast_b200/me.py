@@ -381,6 +381,7 @@ class SparseTensor:
 import os as _os
 
 FORCE_SIMT = False      # tests flip this to run the exact fp32 kernels
+SIMT_OPS = set()        # diagnostics (profiles/grad_precision_ab.py): subset of {"fwd", "dgrad", "wgrad"} forced onto the exact fp32 kernels (modular path)
 CONV_IMPL = _os.environ.get("PCB_CONV_IMPL", "tcgen05")     # "mma" (mma.sync) | "tcgen05" (TMEM accumulators)
 PROFILE = None          # bench.py sets this to a list: every conv launch is then bracketed by CUDA events
 
@@ -441,14 +442,18 @@ class _PreparedWeights:
         return self.planes
 
 
-def _use_tc(Cin, Cout):
-    return (not FORCE_SIMT) and Cin % 32 == 0 and Cout % 32 == 0
+def _simt(op):
+    return FORCE_SIMT or op in SIMT_OPS
 
 
-def _conv_forward_raw(x, tbl, kmap, K, n_out, Cin, Cout, planes_hi, planes_lo, w_f32, bias, kmajor_hi=None, kmajor_lo=None):
+def _use_tc(Cin, Cout, op="fwd"):
+    return (not _simt(op)) and Cin % 32 == 0 and Cout % 32 == 0
+
+
+def _conv_forward_raw(x, tbl, kmap, K, n_out, Cin, Cout, planes_hi, planes_lo, w_f32, bias, kmajor_hi=None, kmajor_lo=None, op="fwd"):
     y = torch.empty(n_out, Cout, dtype=torch.float32, device=x.device)
     km = _c_int_array(kmap) if kmap is not None else None
-    flags = (1 if FORCE_SIMT else 0) | (2 if CONV_IMPL == "tcgen05" else 0)
+    flags = (1 if _simt(op) else 0) | (2 if CONV_IMPL == "tcgen05" else 0)
     wsb = lib.pcb_conv_forward_ws_bytes(K, n_out, Cin, Cout)
     ws = workspace(wsb, x.device, slot=2)
     check(lib.pcb_conv_forward(ptr(x), x.stride(0), ptr(tbl), tbl.shape[1], km, K, n_out, Cin, Cout, ptr(planes_hi),
@@ -488,17 +493,17 @@ class _SparseConvFunction(torch.autograd.Function):
         with torch.cuda.device(dy.device):
             if ctx.needs_input_grad[0]:
                 hi = lo = khi = klo = wt = None
-                if _use_tc(Cout, Cin):
+                if _use_tc(Cout, Cin, "dgrad"):
                     pl = ctx.prepared.get(kernel)
                     hi, lo, khi, klo = pl[2], pl[3], pl[0], pl[1]
                 else:
                     wt = kernel.detach().transpose(1, 2).contiguous()
                 ev = _prof_begin()
-                dx = _conv_forward_raw(dy, plan.dg_tbl, plan.dg_kmap, K, plan.n_in, Cout, Cin, hi, lo, wt, None, khi, klo)
+                dx = _conv_forward_raw(dy, plan.dg_tbl, plan.dg_kmap, K, plan.n_in, Cout, Cin, hi, lo, wt, None, khi, klo, op="dgrad")
                 _prof_end(ev, "dgrad", plan, K, Cin, Cout, hi is not None)
             if ctx.needs_input_grad[1]:
                 dw = torch.empty_like(kernel)
-                flags = 1 if FORCE_SIMT else 0
+                flags = 1 if _simt("wgrad") else 0
                 if plan.wg_gather_x:
                     A, B, Ca, Cb, tr, rows = x, dy, Cin, Cout, 0, plan.n_out
                 else:
@@ -508,7 +513,7 @@ class _SparseConvFunction(torch.autograd.Function):
                 ev = _prof_begin()
                 check(lib.pcb_conv_wgrad(ptr(A), A.stride(0), ptr(B), B.stride(0), ptr(plan.wg_tbl), plan.wg_tbl.shape[1], K,
                                          rows, Ca, Cb, ptr(dw), tr, ptr(ws), wsb, flags, stream()))
-                _prof_end(ev, "wgrad", plan, K, Cin, Cout, Ca % 32 == 0 and Cb % 32 == 0 and not FORCE_SIMT)
+                _prof_end(ev, "wgrad", plan, K, Cin, Cout, Ca % 32 == 0 and Cb % 32 == 0 and not _simt("wgrad"))
             if ctx.has_bias and ctx.needs_input_grad[2]:
                 db = dy.sum(0, keepdim=True)
         return dx, dw, db, None, None
@@ -518,6 +523,20 @@ class MinkowskiNetwork(nn.Module):
     def __init__(self, D):
         super().__init__()
         self.D = D
+
+    def __call__(self, *args, **kwargs):
+        """Training-mode calls of a network wired like Res16UNet (`model/res16unet.py:36-268`) run as ONE fused autograd
+        node (`fused.py`) -- whichever file defines the class, so the reference's own `model/res16unet.py` gets the same
+        kernels and schedule as this package's model.  Everything else goes through `forward` module by module."""
+        if len(args) == 1 and not kwargs and isinstance(args[0], SparseTensor) and args[0].F.is_cuda:
+            from . import fused
+            if fused.applicable(self, args[0]):
+                x = args[0]
+                F = fused.run(self, x)
+                if getattr(self, "normalize_feature", False):        # `model/res16unet.py:262-266` (no epsilon)
+                    F = F / torch.norm(F, p=2, dim=1, keepdim=True)
+                return SparseTensor(F, coords_key=x.coords_key, coords_manager=x.coords_man)
+        return super().__call__(*args, **kwargs)
 
 
 class _ConvolutionBase(nn.Module):

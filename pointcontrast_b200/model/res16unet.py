@@ -99,28 +99,16 @@ class Res16UNetBase(ME.MinkowskiNetwork):
         return nn.Sequential(*layers)
 
     def forward(self, x):
-        if ME is fused.me and fused.applicable(self, x):      # training on CUDA: the whole graph as one fused autograd node
-            out = ME.SparseTensor(fused.run(self, x), coords_key=x.coords_key, coords_manager=x.coords_man)
-        else:
-            out = self._forward_modular(x)
+        # training on CUDA never gets here: `me.MinkowskiNetwork.__call__` runs the whole graph as one fused autograd node
+        out = self._forward_modular(x)
         if self.normalize_feature:               # `model/res16unet.py:262-266` (no epsilon)
             return ME.SparseTensor(out.F / torch.norm(out.F, p=2, dim=1, keepdim=True), coords_key=out.coords_key,
                                    coords_manager=out.coords_man)
         return out
 
     def forward_pair(self, feats0, coords0, feats1, coords1, device):
-        """Features (F0, F1) of the two views of a pair batch -- what `lib/ddp_trainer.py:290-297,392-398` gets from two
-        calls of the model.  With the fused executor both views go through ONE stacked pass (`fused.stack_views`), each
-        BatchNorm still normalising every view with its own statistics; otherwise this is the two calls."""
-        if ME is fused.me and fused.PAIR and fused.applicable_on(self, device) and len(coords0) and len(coords1):
-            s, n0 = fused.stack_views(feats0, coords0, feats1, coords1, device)
-            F = fused.run(self, s, n0)
-            if self.normalize_feature:
-                F = F / torch.norm(F, p=2, dim=1, keepdim=True)
-            return F[:n0], F[n0:]
-        F0 = self(ME.SparseTensor(feats0, coords=coords0).to(device)).F
-        F1 = self(ME.SparseTensor(feats1, coords=coords1).to(device)).F
-        return F0, F1
+        """Features (F0, F1) of the two views of a pair batch: see `fused.forward_pair`."""
+        return fused.forward_pair(self, feats0, coords0, feats1, coords1, device)
 
     def _forward_modular(self, x):
         out_p1 = self.relu(self.bn0(self.conv0p1s1(x)))

@@ -16,7 +16,7 @@ import os.path as osp
 import torch
 import torch.distributed as dist
 
-from . import losses, me as ME
+from . import fused, losses, me as ME
 from .model import load_model
 from .optim import FlatSGD
 
@@ -117,14 +117,8 @@ class ContrastiveLossTrainer:
     # -- shared step pieces
     def _forward_views(self, input_dict):
         dev = self.device
-        if hasattr(self.model, "forward_pair"):
-            return self.model.forward_pair(input_dict["sinput0_F"], input_dict["sinput0_C"], input_dict["sinput1_F"],
-                                           input_dict["sinput1_C"], dev)
-        s0 = ME.SparseTensor(input_dict["sinput0_F"], coords=input_dict["sinput0_C"]).to(dev)
-        F0 = self.model(s0).F
-        s1 = ME.SparseTensor(input_dict["sinput1_F"], coords=input_dict["sinput1_C"]).to(dev)
-        F1 = self.model(s1).F
-        return F0, F1
+        return fused.forward_pair(self.model, input_dict["sinput0_F"], input_dict["sinput0_C"], input_dict["sinput1_F"],
+                                  input_dict["sinput1_C"], dev)
 
     def _all_reduce_grads(self):
         if self.world > 1:

@@ -1,15 +1,20 @@
 """Import pieces of the read-only reference tree (/root/reference) on top of a chosen MinkowskiEngine-compatible
-module.  Only usable where the reference exists (this container); GPU-box tests never call it."""
+module.  In the build container that is the reference itself; on the GPU box only the model package staged by
+`oracle/stage_ref.py` is available (the trainer module is not)."""
 import importlib
 import os
 import sys
 import types
 
 REF_PC = "/root/reference/pretrain/pointcontrast"
+if not os.path.isdir(REF_PC):       # GPU box: the model package staged by oracle/stage_ref.py (git-ignored, travels with gpurun)
+    _staged = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "pointcontrast")
+    if os.path.isdir(os.path.join(_staged, "model")):
+        REF_PC = _staged
 
 
 def available():
-    return os.path.isdir(REF_PC)
+    return os.path.isdir(os.path.join(REF_PC, "model"))
 
 
 def _purge():
