@@ -54,6 +54,12 @@ const char* pcb_version(void);
 uint64_t pcb_launch_count(void);
 /* The library links its own (static) CUDA runtime: select the device the caller's pointers/streams live on. */
 int pcb_set_device(int device);
+/* Measurement aid (bench.py's roofline): while enabled, every convolution / weight-gradient entry point (including the ones
+ * issued inside pcb_unit_*) is bracketed by CUDA events on its stream.  pcb_profile_read synchronises with them, returns the
+ * elapsed ms and kind (0 = convolution forward / data gradient, 1 = weight gradient) of up to max_records records in issue
+ * order, *count = records taken since the last read, and clears the list.  Not thread-safe; off by default. */
+int pcb_profile_enable(int on);
+int pcb_profile_read(float* ms, int32_t* kinds, int max_records, int* count);
 
 /* ----------------------------------------------------------------------------------------------- coordinates */
 /* (b,x,y,z) -> 64-bit keys whose unsigned order is lexicographic (b,x,y,z).  b in [0,65535), |x|,|y|,|z| < 32768.
@@ -175,6 +181,52 @@ int pcb_bn_backward_seg(const float* dY, int lddy, const float* X, int ldx, cons
  * row stride lds in ELEMENTS.  The elementwise producers above can emit it directly (Yhi/Ylo, dXhi/dXlo; NULL = off; dX may
  * then be NULL), so the conv kernels' gather becomes a pure asynchronous copy.  pcb_split_rows converts an fp32 matrix. */
 int pcb_split_rows(const float* X, int ldx, int64_t n, int C, uint16_t* hi, uint16_t* lo, int lds, void* stream);
+
+/* ----------------------------------------------------------------------------------------------- fused units */
+/* One "unit" of the Res16UNet graph = convolution -> BatchNorm (training statistics) -> [+ residual] -> [ReLU]
+ * (`model/res16unet.py:206-268`, `model/modules/resnet_block.py:44-60`: a BasicBlock is two units).  pcb_unit_forward issues the whole
+ * unit from ONE call -- the BatchNorm column sums come out of the convolution's epilogue (TMEM -> registers -> per-tile partial
+ * sums) or out of the offset-split reduction pass, so the pre-normalisation tensor z is written once and read once --
+ * and pcb_unit_backward issues its reverse: ReLU mask + BatchNorm backward + residual-gradient fan-out in one elementwise
+ * pass, then the weight gradient (accumulated into dW) and the data gradient (written or accumulated into gin).
+ * The caller (pointcontrast_b200/fused.py; a C++ host would do the same) owns every buffer; the struct is plain data.
+ *
+ * Matrices: fp32 pointer `*_p` (row stride `*_ld` floats) and/or bf16 split planes `*_hi`/`*_lo` (row stride `*_lds` elements).
+ *   x    : unit input  [n_in, Cin]   (split planes when Cin % 32 == 0, else fp32: the 3-channel stem)
+ *   z    : convolution output [n_out, Cout], fp32 (kept for the backward pass)
+ *   out  : unit output [n_out, Cout]: split planes (always) and fp32 (only if out_p != NULL: it feeds a residual add)
+ *   res  : residual input, fp32 (or NULL);  rows [0, n0) / [n0, n_out) are the two views of a stacked pair (n0 == n_out: one)
+ *   g    : gradient of `out` (fp32, complete when pcb_unit_backward is called)
+ *   dz   : scratch for the gradient of z: split planes [n_out, Cout] (+ fp32 `dz_p` when Cout or Cin is not a multiple of 32)
+ *   gin  : gradient of x (fp32) -- written (gin_mode 1) or accumulated (2); 0: not wanted (network input)
+ *   gres : gradient of the residual input -- written (1) / accumulated (2) / none (0)
+ * Tables (device int32 [K][stride]) and kmaps (HOST int32 [K] or NULL) as for pcb_conv_forward / pcb_conv_wgrad.
+ * ws: pcb_unit_ws_bytes(K, n_in, n_out, Cin, Cout) bytes of scratch. */
+typedef struct pcb_unit {
+  int64_t n_in, n_out, n0;
+  int32_t K, Cin, Cout, relu;
+  const int32_t* fwd_tbl; int64_t fwd_stride; const int32_t* fwd_kmap;
+  const int32_t* dg_tbl; int64_t dg_stride; const int32_t* dg_kmap;
+  const int32_t* wg_tbl; int64_t wg_stride; int32_t wg_gather_x;
+  const float* W; const void* wt_fwd; const void* wt_dg; float* dW;
+  const float* gamma; const float* beta; float* running_mean; float* running_var; float* dgamma; float* dbeta;
+  float eps, momentum;
+  float* mean; float* invstd;                       /* [segments][Cout], written by forward, read by backward */
+  const float* x_p; int32_t x_ld; const uint16_t* x_hi; const uint16_t* x_lo; int32_t x_lds;
+  float* z_p; int32_t z_ld;
+  float* out_p; int32_t out_ld; uint16_t* out_hi; uint16_t* out_lo; int32_t out_lds;
+  const float* res_p; int32_t res_ld;
+  const float* g_p; int32_t g_ld;
+  float* dz_p; uint16_t* dz_hi; uint16_t* dz_lo; int32_t dz_ld;
+  float* gin_p; int32_t gin_ld; int32_t gin_mode;
+  float* gres_p; int32_t gres_ld; int32_t gres_mode;
+  void* ws; size_t ws_bytes;
+  int32_t flags;                                    /* PCB_UNIT_* */
+} pcb_unit;
+#define PCB_UNIT_SEPARATE_STATS 1   /* forward: BatchNorm statistics by a separate pass over z (cross-check of the fused epilogue) */
+size_t pcb_unit_ws_bytes(int K, int64_t n_in, int64_t n_out, int Cin, int Cout);
+int pcb_unit_forward(const pcb_unit* u, void* stream);
+int pcb_unit_backward(const pcb_unit* u, void* stream);
 
 /* ----------------------------------------------------------------------------------------------- losses */
 /* PointInfoNCE on gathered rows q,k [n, D] (D % 4 == 0, D <= 128): loss = mean_i(logsumexp_j(q_i.k_j/T) - q_i.k_i/T).

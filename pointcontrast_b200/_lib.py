@@ -62,7 +62,37 @@ _SIGS = {
     "pcb_nce_forward_backward": (_i, [_p, _p, _l, _i, _f, _p, _p, _p, _p, _sz, _p]),
     "pcb_pdist_rowmin": (_i, [_p, _l, _p, _l, _i, _p, _p, _p, _p]),
     "pcb_sgd_step": (_i, [_p, _p, _p, _l, _f, _f, _f, _f, _i, _p]),
+    "pcb_profile_enable": (_i, [_i]),
+    "pcb_profile_read": (_i, [_p, _p, _i, C.POINTER(C.c_int)]),
+    "pcb_unit_ws_bytes": (_sz, [_i, _l, _l, _i, _i]),
+    "pcb_unit_forward": (_i, [_p, _p]),
+    "pcb_unit_backward": (_i, [_p, _p]),
 }
+
+
+class PcbUnit(C.Structure):
+    """`struct pcb_unit` of include/pcb200.h (field for field)."""
+    _fields_ = [
+        ("n_in", _l), ("n_out", _l), ("n0", _l),
+        ("K", C.c_int32), ("Cin", C.c_int32), ("Cout", C.c_int32), ("relu", C.c_int32),
+        ("fwd_tbl", _p), ("fwd_stride", _l), ("fwd_kmap", _p),
+        ("dg_tbl", _p), ("dg_stride", _l), ("dg_kmap", _p),
+        ("wg_tbl", _p), ("wg_stride", _l), ("wg_gather_x", C.c_int32),
+        ("W", _p), ("wt_fwd", _p), ("wt_dg", _p), ("dW", _p),
+        ("gamma", _p), ("beta", _p), ("running_mean", _p), ("running_var", _p), ("dgamma", _p), ("dbeta", _p),
+        ("eps", _f), ("momentum", _f),
+        ("mean", _p), ("invstd", _p),
+        ("x_p", _p), ("x_ld", C.c_int32), ("x_hi", _p), ("x_lo", _p), ("x_lds", C.c_int32),
+        ("z_p", _p), ("z_ld", C.c_int32),
+        ("out_p", _p), ("out_ld", C.c_int32), ("out_hi", _p), ("out_lo", _p), ("out_lds", C.c_int32),
+        ("res_p", _p), ("res_ld", C.c_int32),
+        ("g_p", _p), ("g_ld", C.c_int32),
+        ("dz_p", _p), ("dz_hi", _p), ("dz_lo", _p), ("dz_ld", C.c_int32),
+        ("gin_p", _p), ("gin_ld", C.c_int32), ("gin_mode", C.c_int32),
+        ("gres_p", _p), ("gres_ld", C.c_int32), ("gres_mode", C.c_int32),
+        ("ws", _p), ("ws_bytes", _sz),
+        ("flags", C.c_int32),
+    ]
 EXPORTS = sorted(_SIGS)
 for _name, (_res, _args) in _SIGS.items():
     _fn = getattr(lib, _name)          # AttributeError here == the library does not export a declared symbol

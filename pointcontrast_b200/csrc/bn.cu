@@ -40,9 +40,19 @@ __global__ void split_rows_kernel(const float* __restrict__ X, int ldx, int64_t 
 // Row segments: rows [0, n0) and [n0, n) are two independent BatchNorm batches (the two views of a pair stacked in one
 // matrix); chunks never straddle the boundary: CTAs [0, chunks0) cover segment 0, the rest segment 1.  n0 == n: one segment.
 // mean / invstd are [segments][C].
+// ReLU mask from the bf16 hi plane of the unit's output: out > 0  <=>  hi > 0 (bf16 keeps fp32's exponent range; the only
+// difference is an fp32 denormal below 2^-134 rounding to 0).  4 channels = 8 bytes.
+__device__ __forceinline__ void mask4_bf16(const __nv_bfloat16* m, float4& a) {
+  const uint2 b = __ldg(reinterpret_cast<const uint2*>(m));
+  auto pos = [](uint32_t h) { return (h & 0x7FFFu) != 0u && !(h & 0x8000u); };
+  a.x = pos(b.x & 0xFFFFu) ? a.x : 0.f; a.y = pos(b.x >> 16) ? a.y : 0.f;
+  a.z = pos(b.y & 0xFFFFu) ? a.z : 0.f; a.w = pos(b.y >> 16) ? a.w : 0.f;
+}
+
 template <bool TWO_INPUTS>
 __global__ void colsum_kernel(const float* __restrict__ A, int lda, const float* __restrict__ Bm, int ldb,
-                              const float* __restrict__ Mask, int ldm, int64_t n, int64_t n0, int chunks0, int C,
+                              const float* __restrict__ Mask, int ldm, const __nv_bfloat16* __restrict__ MaskH, int ldmh,
+                              int64_t n, int64_t n0, int chunks0, int C,
                               const float* __restrict__ mean, const float* __restrict__ invstd, float* __restrict__ partial) {
   extern __shared__ float sm[];      // [RP][2][C]
   const int cv = C / 4;
@@ -65,6 +75,8 @@ __global__ void colsum_kernel(const float* __restrict__ A, int lda, const float*
         if (Mask) {
           float4 m = __ldg(reinterpret_cast<const float4*>(Mask + r * ldm) + c4);
           a.x = m.x > 0.f ? a.x : 0.f; a.y = m.y > 0.f ? a.y : 0.f; a.z = m.z > 0.f ? a.z : 0.f; a.w = m.w > 0.f ? a.w : 0.f;
+        } else if (MaskH) {
+          mask4_bf16(MaskH + r * ldmh + c4 * 4, a);
         }
         float4 x = __ldg(reinterpret_cast<const float4*>(Bm + r * ldb) + c4);
         // a = dY, second sum = dY * xhat
@@ -75,6 +87,43 @@ __global__ void colsum_kernel(const float* __restrict__ A, int lda, const float*
         s1.x += a.x; s1.y += a.y; s1.z += a.z; s1.w += a.w;
         s2.x += a.x * a.x; s2.y += a.y * a.y; s2.z += a.z * a.z; s2.w += a.w * a.w;
       }
+    }
+    float* d = sm + (int64_t)rl * 2 * C;
+    reinterpret_cast<float4*>(d)[c4] = s1;
+    reinterpret_cast<float4*>(d + C)[c4] = s2;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 2 * C; e += blockDim.x) {
+    float s = 0.f;
+    for (int l = 0; l < rp; ++l) s += sm[(int64_t)l * 2 * C + e];
+    partial[(int64_t)blockIdx.x * 2 * C + e] = s;
+  }
+}
+
+// Offset-split convolutions (small levels): Y[row] = sum_z partial_conv[z][row]  AND the BatchNorm column sums of Y in the same
+// pass (same chunking / segment layout as colsum_kernel<false>), so the statistics cost no extra read of Y.
+__global__ void reduce_stats_kernel(const float* __restrict__ P, int nsplit, float* __restrict__ Y, int ldy, int64_t n, int64_t n0,
+                                    int chunks0, int C, float* __restrict__ partial) {
+  extern __shared__ float sm[];      // [RP][2][C]
+  const int cv = C / 4;
+  const int rp = blockDim.x / cv;
+  const int c4 = threadIdx.x % cv;
+  const int rl = threadIdx.x / cv;
+  const int seg = (int)blockIdx.x >= chunks0 ? 1 : 0;
+  const int64_t r0 = seg ? n0 + (int64_t)((int)blockIdx.x - chunks0) * ROWS_PER_CHUNK : (int64_t)blockIdx.x * ROWS_PER_CHUNK;
+  const int64_t r1 = min(seg ? n : n0, r0 + ROWS_PER_CHUNK);
+  float4 s1 = make_float4(0, 0, 0, 0), s2 = make_float4(0, 0, 0, 0);
+  if (rl < rp) {
+    const int64_t plane = n * cv;
+    for (int64_t r = r0 + rl; r < r1; r += rp) {
+      float4 a = make_float4(0, 0, 0, 0);
+      for (int z = 0; z < nsplit; ++z) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(P) + z * plane + r * cv + c4);
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+      }
+      *reinterpret_cast<float4*>(Y + r * ldy + c4 * 4) = a;
+      s1.x += a.x; s1.y += a.y; s1.z += a.z; s1.w += a.w;
+      s2.x += a.x * a.x; s2.y += a.y * a.y; s2.z += a.z * a.z; s2.w += a.w * a.w;
     }
     float* d = sm + (int64_t)rl * 2 * C;
     reinterpret_cast<float4*>(d)[c4] = s1;
@@ -145,7 +194,7 @@ __global__ void bn_apply_kernel(const float* __restrict__ X, int ldx, int64_t n4
     y.x += r.x; y.y += r.y; y.z += r.z; y.w += r.w;
   }
   if (relu) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
-  *reinterpret_cast<float4*>(Y + row * ldy + c4 * 4) = y;
+  if (Y) *reinterpret_cast<float4*>(Y + row * ldy + c4 * 4) = y;
   if (Yhi) store_split4(y, Yhi + row * lds + c4 * 4, Ylo + row * lds + c4 * 4);
 }
 
@@ -175,7 +224,8 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int ch
 
 // gout_mode: 0 none, 1 write, 2 accumulate -- the (ReLU-masked) incoming gradient, i.e. the gradient of the residual input
 __global__ void bn_bwd_apply_kernel(const float* dY, int lddy, const float* __restrict__ X, int ldx,
-                                    const float* __restrict__ Mask, int ldm, int64_t n4, int cv, int64_t n0, float inv_n0,
+                                    const float* __restrict__ Mask, int ldm, const __nv_bfloat16* __restrict__ MaskH, int ldmh,
+                                    int64_t n4, int cv, int64_t n0, float inv_n0,
                                     float inv_n1, const float* __restrict__ mean, const float* __restrict__ invstd,
                                     const float* __restrict__ gamma, const float* __restrict__ sums, float* __restrict__ dX, int lddx,
                                     float* gout, int ldg, int gout_mode, __nv_bfloat16* __restrict__ dXhi,
@@ -188,6 +238,8 @@ __global__ void bn_bwd_apply_kernel(const float* dY, int lddy, const float* __re
   if (Mask) {
     float4 m = __ldg(reinterpret_cast<const float4*>(Mask + row * ldm) + c4);
     dy.x = m.x > 0.f ? dy.x : 0.f; dy.y = m.y > 0.f ? dy.y : 0.f; dy.z = m.z > 0.f ? dy.z : 0.f; dy.w = m.w > 0.f ? dy.w : 0.f;
+  } else if (MaskH) {
+    mask4_bf16(MaskH + row * ldmh + c4 * 4, dy);
   }
   if (gout_mode) {
     float4* gp = reinterpret_cast<float4*>(gout + row * ldg) + c4;
@@ -238,8 +290,8 @@ extern "C" int pcb_bn_stats_seg(const float* X, int ldx, int64_t n, int64_t n0, 
   const int chunks = chunks0 + (n0 < n ? chunks_for(n - n0) : 0);
   const int thr = colsum_threads(C);
   const int rp = thr / (C / 4);
-  colsum_kernel<false><<<chunks, thr, (size_t)rp * 2 * C * sizeof(float), st>>>(X, ldx, nullptr, 0, nullptr, 0, n, n0, chunks0, C, nullptr,
-                                                                                 nullptr, (float*)ws);
+  colsum_kernel<false><<<chunks, thr, (size_t)rp * 2 * C * sizeof(float), st>>>(X, ldx, nullptr, 0, nullptr, 0, nullptr, 0, n, n0, chunks0, C,
+                                                                                 nullptr, nullptr, (float*)ws);
   if (int e = check_launch("colsum_kernel")) return e;
   bn_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>((const float*)ws, chunks, chunks0, n, n0, C, eps, momentum, mean, invstd, running_mean,
                                                       running_var);
@@ -269,9 +321,9 @@ extern "C" int pcb_split_rows(const float* X, int ldx, int64_t n, int C, uint16_
 extern "C" int pcb_bn_apply_seg(const float* X, int ldx, int64_t n, int64_t n0, int C, const float* mean, const float* invstd,
                                 const float* gamma, const float* beta, const float* residual, int ldr, int relu, float* Y, int ldy,
                                 uint16_t* Yhi, uint16_t* Ylo, int lds, void* stream) {
-  PCB_ARG(n >= 0 && n0 >= 0 && n0 <= n && C >= 4 && C % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && ldx >= C && ldy >= C);
+  PCB_ARG(n >= 0 && n0 >= 0 && n0 <= n && C >= 4 && C % 4 == 0 && ldx % 4 == 0 && ldx >= C && (!Y || (ldy % 4 == 0 && ldy >= C)));
   if (n == 0) return PCB_OK;
-  PCB_ARG(X && Y && mean && invstd && gamma && beta && (!residual || (ldr >= C && ldr % 4 == 0)));
+  PCB_ARG(X && (Y || Yhi) && mean && invstd && gamma && beta && (!residual || (ldr >= C && ldr % 4 == 0)));
   PCB_ARG(!Yhi || (Ylo && lds >= C && lds % 4 == 0));
   int64_t n4 = n * (C / 4);
   bn_apply_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(X, ldx, n4, C / 4, mean, invstd, gamma, beta, residual,
@@ -291,18 +343,20 @@ extern "C" int pcb_bn_apply(const float* X, int64_t n, int C, const float* mean,
   return pcb_bn_apply_seg(X, C, n, n, C, mean, invstd, gamma, beta, residual, C, relu, Y, C, nullptr, nullptr, 0, stream);
 }
 
-extern "C" int pcb_bn_backward_seg(const float* dY, int lddy, const float* X, int ldx, const float* relu_out, int ldm, int64_t n,
-                                   int64_t n0, int C, const float* mean, const float* invstd, const float* gamma, float* dX, int lddx,
-                                   float* dgamma, float* dbeta, int accumulate_param_grads, float* gout, int ldg, int gout_mode,
-                                   uint16_t* dXhi, uint16_t* dXlo, int lds, void* ws, size_t ws_bytes, void* stream) {
+namespace pcb {
+// mask: the unit's ReLU output as fp32 (relu_out) or as its bf16 hi plane (relu_hi); neither: no ReLU
+int bn_backward_impl(const float* dY, int lddy, const float* X, int ldx, const float* relu_out, int ldm, const uint16_t* relu_hi, int ldmh,
+                     int64_t n, int64_t n0, int C, const float* mean, const float* invstd, const float* gamma, float* dX, int lddx,
+                     float* dgamma, float* dbeta, int accumulate_param_grads, float* gout, int ldg, int gout_mode, uint16_t* dXhi,
+                     uint16_t* dXlo, int lds, void* ws, size_t ws_bytes, cudaStream_t st) {
   PCB_ARG(dY && X && mean && invstd && gamma && (dX || dXhi) && dgamma && dbeta && ws && n >= 1 && C >= 4 && C % 4 == 0 && C <= 1024);
   PCB_ARG(n0 >= 1 && n0 <= n);
   PCB_ARG(lddy >= C && ldx >= C && lddy % 4 == 0 && ldx % 4 == 0 && (!dX || (lddx >= C && lddx % 4 == 0)));
   PCB_ARG(!dXhi || (dXlo && lds >= C && lds % 4 == 0));
   PCB_ARG(!relu_out || (ldm >= C && ldm % 4 == 0));
+  PCB_ARG(!relu_hi || (!relu_out && ldmh >= C && ldmh % 4 == 0));
   PCB_ARG(gout_mode == 0 || (gout && ldg >= C && ldg % 4 == 0));
   PCB_ARG(ws_bytes >= pcb_bn_ws_bytes(n, C) - 256);
-  cudaStream_t st = (cudaStream_t)stream;
   const int nseg = n0 < n ? 2 : 1;
   const int chunks0 = chunks_for(n0);
   const int chunks = chunks0 + (nseg == 2 ? chunks_for(n - n0) : 0);
@@ -310,17 +364,52 @@ extern "C" int pcb_bn_backward_seg(const float* dY, int lddy, const float* X, in
   const int rp = thr / (C / 4);
   float* partial = (float*)ws;
   float* sums = partial + (size_t)chunks * 2 * C;        // [segments][2][C]: dbeta, dgamma of THIS call (the apply pass needs them)
-  colsum_kernel<true><<<chunks, thr, (size_t)rp * 2 * C * sizeof(float), st>>>(dY, lddy, X, ldx, relu_out, ldm, n, n0, chunks0, C, mean,
-                                                                                invstd, partial);
+  colsum_kernel<true><<<chunks, thr, (size_t)rp * 2 * C * sizeof(float), st>>>(dY, lddy, X, ldx, relu_out, ldm, (const __nv_bfloat16*)relu_hi,
+                                                                                ldmh, n, n0, chunks0, C, mean, invstd, partial);
   if (int e = check_launch("colsum_kernel<bwd>")) return e;
   bn_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(partial, chunks, chunks0, nseg, C, dgamma, dbeta, accumulate_param_grads, sums);
   if (int e = check_launch("bn_bwd_finalize_kernel")) return e;
   int64_t n4 = n * (C / 4);
-  bn_bwd_apply_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(dY, lddy, X, ldx, relu_out, ldm, n4, C / 4, n0, 1.0f / (float)n0,
-                                                                    nseg == 2 ? 1.0f / (float)(n - n0) : 0.f, mean, invstd, gamma, sums,
-                                                                    dX, lddx, gout, ldg, gout_mode, (__nv_bfloat16*)dXhi,
-                                                                    (__nv_bfloat16*)dXlo, lds);
+  bn_bwd_apply_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(dY, lddy, X, ldx, relu_out, ldm, (const __nv_bfloat16*)relu_hi, ldmh, n4,
+                                                                    C / 4, n0, 1.0f / (float)n0, nseg == 2 ? 1.0f / (float)(n - n0) : 0.f, mean,
+                                                                    invstd, gamma, sums, dX, lddx, gout, ldg, gout_mode,
+                                                                    (__nv_bfloat16*)dXhi, (__nv_bfloat16*)dXlo, lds);
   return check_launch("bn_bwd_apply_kernel");
+}
+
+// Layout of the per-128-row-tile column sums written by a producer (conv epilogue / reduce_stats_kernel) for rows [0, n) with
+// segments [0, n0) and [n0, n): TILES ARE ALIGNED TO ROW 0 for the conv epilogue (conv_tile_aligned) -- the tile containing
+// row n0 contributes a row to both segments -- and aligned to each segment's first row for reduce_stats_kernel.
+void bn_partial_layout(int64_t n, int64_t n0, bool conv_tile_aligned, int* chunks, int* chunks0) {
+  if (n0 >= n) { *chunks0 = chunks_for(n); *chunks = *chunks0; return; }
+  *chunks0 = chunks_for(n0);
+  *chunks = *chunks0 + (conv_tile_aligned ? chunks_for(n) - (int)(n0 / ROWS_PER_CHUNK) : chunks_for(n - n0));
+}
+
+int bn_finalize_launch(const float* partial, int chunks, int chunks0, int64_t n, int64_t n0, int C, float eps, float momentum, float* mean,
+                       float* invstd, float* running_mean, float* running_var, cudaStream_t st) {
+  bn_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(partial, chunks, chunks0, n, n0, C, eps, momentum, mean, invstd, running_mean, running_var);
+  return check_launch("bn_finalize_kernel");
+}
+
+// Y = sum of the nsplit partial planes P[z][n][C] (offset-split convolution), column sums of Y -> partial (segment-aligned chunks)
+int bn_reduce_stats_launch(const float* P, int nsplit, float* Y, int ldy, int64_t n, int64_t n0, int C, float* partial, cudaStream_t st) {
+  PCB_ARG(P && Y && partial && nsplit >= 1 && n >= 1 && n0 >= 1 && n0 <= n && C % 4 == 0 && C <= 1024 && ldy >= C && ldy % 4 == 0);
+  int chunks, chunks0;
+  bn_partial_layout(n, n0, false, &chunks, &chunks0);
+  const int thr = colsum_threads(C);
+  const int rp = thr / (C / 4);
+  reduce_stats_kernel<<<chunks, thr, (size_t)rp * 2 * C * sizeof(float), st>>>(P, nsplit, Y, ldy, n, n0, chunks0, C, partial);
+  return check_launch("reduce_stats_kernel");
+}
+}  // namespace pcb
+
+extern "C" int pcb_bn_backward_seg(const float* dY, int lddy, const float* X, int ldx, const float* relu_out, int ldm, int64_t n,
+                                   int64_t n0, int C, const float* mean, const float* invstd, const float* gamma, float* dX, int lddx,
+                                   float* dgamma, float* dbeta, int accumulate_param_grads, float* gout, int ldg, int gout_mode,
+                                   uint16_t* dXhi, uint16_t* dXlo, int lds, void* ws, size_t ws_bytes, void* stream) {
+  return pcb::bn_backward_impl(dY, lddy, X, ldx, relu_out, ldm, nullptr, 0, n, n0, C, mean, invstd, gamma, dX, lddx, dgamma, dbeta,
+                               accumulate_param_grads, gout, ldg, gout_mode, dXhi, dXlo, lds, ws, ws_bytes, (cudaStream_t)stream);
 }
 
 extern "C" int pcb_bn_backward2(const float* dY, int lddy, const float* X, int ldx, const float* relu_out, int ldm, int64_t n, int C,

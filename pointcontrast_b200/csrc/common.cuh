@@ -39,6 +39,15 @@ __device__ __forceinline__ int hash_lookup(const uint64_t* __restrict__ tk, cons
   }
 }
 
+// Optional per-launch timing (pcb_profile_*, unit.cu): CUDA events around every convolution / weight-gradient entry point.
+void prof_begin(cudaStream_t st);
+void prof_end(cudaStream_t st, int kind);      // kind: 0 conv forward / data gradient, 1 weight gradient
+struct ProfScope {
+  cudaStream_t st; int kind;
+  ProfScope(cudaStream_t s, int k) : st(s), kind(k) { prof_begin(st); }
+  ~ProfScope() { prof_end(st, kind); }
+};
+
 inline int num_sms() {
   static int n = 0;
   if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }

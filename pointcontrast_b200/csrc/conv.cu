@@ -518,13 +518,17 @@ __global__ void __launch_bounds__(256) wgrad_stem_kernel(const float* __restrict
       }
     }
   }
+  for (int w = 0; w < 8; ++w) {          // warp after warp, in a fixed order: deterministic (no shared-memory atomics)
+    if (warp == w) {
 #pragma unroll
-  for (int k = 0; k < PCB_MAX_KERNEL_VOLUME; ++k)
-    if (k < K) {
+      for (int k = 0; k < PCB_MAX_KERNEL_VOLUME; ++k)
+        if (k < K) {
 #pragma unroll
-      for (int c = 0; c < CA; ++c) atomicAdd(&s_acc[(k * CA + c) * 32 + lane], acc[k][c]);
+          for (int c = 0; c < CA; ++c) s_acc[(k * CA + c) * 32 + lane] += acc[k][c];
+        }
     }
-  __syncthreads();
+    __syncthreads();
+  }
   float* out = partial + (int64_t)blockIdx.x * K * CA * 32;
   for (int e = threadIdx.x; e < K * CA * 32; e += 256) out[e] = s_acc[e];
 }
@@ -642,7 +646,7 @@ int launch_wgrad_tcgen05(const uint16_t* Ahi, const uint16_t* Alo, int lda, cons
 int launch_conv_tcgen05(const float* X, int ldx, const uint16_t* Xhi, const uint16_t* Xlo, int lds, const void* wt, const int32_t* tbl,
                         int64_t tbl_stride, const int* kmap, int K, int64_t n_out,
                         int Cin, int Cout, const uint16_t* wk_hi, const uint16_t* wk_lo, const float* bias, float* Y, int ldy,
-                        float* partial, int nsplit, int bn, int accumulate, cudaStream_t st);
+                        float* partial, int nsplit, int bn, int accumulate, cudaStream_t st, float* stats = nullptr, int64_t seg_n0 = 0);
 }
 
 extern "C" size_t pcb_conv_forward_ws_bytes(int K, int64_t n_out, int Cin, int Cout) {
@@ -659,6 +663,7 @@ extern "C" int pcb_conv_forward(const float* X, int ldx, const int32_t* tbl, int
   if (n_out == 0) return PCB_OK;
   PCB_ARG(X && tbl && Y && tbl_stride >= n_out);
   cudaStream_t st = (cudaStream_t)stream;
+  ProfScope prof(st, 0);
   KMap km;
   for (int k = 0; k < K; ++k) { km.v[k] = kmap ? kmap[k] : k; PCB_ARG(km.v[k] >= 0 && km.v[k] < PCB_MAX_KERNEL_VOLUME); }
   const bool tc_ok = (Cin % 32 == 0) && (Cout % 32 == 0) && (ldx % 4 == 0) && (ldy % 2 == 0) && w_hi && w_lo &&
@@ -722,6 +727,7 @@ extern "C" int pcb_conv_wgrad(const float* A, int lda, const float* B, int ldb, 
     return PCB_OK;
   }
   PCB_ARG(A && B && tbl && ws && tbl_stride >= n_out);
+  ProfScope prof(st, 1);
   if (Ca == 3 && Cb == 32 && !transpose_out && !(flags & PCB_CONV_FORCE_SIMT)) {      // the stem layer: dedicated exact-fp32 kernel
     const int blocks = (int)((size_t)ws_bytes / ((size_t)nW * sizeof(float)));
     PCB_ARG(blocks >= 1);
@@ -816,28 +822,46 @@ extern "C" int pcb_weight_tile(const float* W, int K, int Cin, int Cout, void* f
   return check_launch("weight_tile_kernel");
 }
 
-extern "C" int pcb_conv_forward_split(const uint16_t* Xhi, const uint16_t* Xlo, int lds, const int32_t* tbl, int64_t tbl_stride,
-                                      const int32_t* kmap, int K, int64_t n_out, int Cin, int Cout, const void* w_tiles,
-                                      const float* bias, float* Y, int ldy, void* ws, size_t ws_bytes,
-                                      int flags, void* stream) {
+namespace pcb {
+int bn_reduce_stats_launch(const float* P, int nsplit, float* Y, int ldy, int64_t n, int64_t n0, int C, float* partial, cudaStream_t st);
+void bn_partial_layout(int64_t n, int64_t n0, bool conv_tile_aligned, int* chunks, int* chunks0);
+
+// stats != NULL: also produce the BatchNorm column sums of Y (rows [0, seg_n0) and [seg_n0, n_out) separately) as per-128-row
+// partials [chunks][2][Cout] -- from the TMEM epilogue in direct mode, from the reduce pass in offset-split mode; *chunks / *chunks0
+// describe the layout for bn_finalize_launch.  Requires no bias and no accumulate (a BatchNorm follows the convolution).
+int conv_forward_split_impl(const uint16_t* Xhi, const uint16_t* Xlo, int lds, const int32_t* tbl, int64_t tbl_stride, const int32_t* kmap,
+                            int K, int64_t n_out, int Cin, int Cout, const void* w_tiles, const float* bias, float* Y, int ldy, void* ws,
+                            size_t ws_bytes, int flags, cudaStream_t st, float* stats, int64_t seg_n0, int* chunks, int* chunks0) {
   PCB_ARG(K >= 1 && K <= PCB_MAX_KERNEL_VOLUME && n_out >= 0 && Cin % 32 == 0 && Cout % 32 == 0 && Cin >= 32 && Cout >= 32);
   PCB_ARG(lds >= Cin && lds % 8 == 0 && ldy >= Cout && ldy % 4 == 0);
   if (n_out == 0) return PCB_OK;
   PCB_ARG(Xhi && Xlo && tbl && Y && w_tiles && tbl_stride >= n_out);
-  cudaStream_t st = (cudaStream_t)stream;
+  ProfScope prof(st, 0);
   int km[PCB_MAX_KERNEL_VOLUME];
   for (int k = 0; k < K; ++k) { km[k] = kmap ? kmap[k] : k; PCB_ARG(km[k] >= 0 && km[k] < PCB_MAX_KERNEL_VOLUME); }
   const int accumulate = (flags & PCB_CONV_ACCUMULATE) ? 1 : 0;
   const int nsplit = conv_splits(K, n_out, Cin, Cout);
   if (nsplit > 1) PCB_ARG(ws && ws_bytes >= (size_t)nsplit * n_out * Cout * sizeof(float));
+  if (stats) PCB_ARG(!bias && !accumulate && seg_n0 >= 1 && seg_n0 <= n_out && chunks && chunks0);
   if (int e = launch_conv_tcgen05(nullptr, 0, Xhi, Xlo, lds, w_tiles, tbl, tbl_stride, km, K, n_out, Cin, Cout, nullptr, nullptr, bias, Y, ldy,
-                                  nsplit > 1 ? (float*)ws : nullptr, nsplit, pick_tile(Cout), accumulate, st)) return e;
+                                  nsplit > 1 ? (float*)ws : nullptr, nsplit, pick_tile(Cout), accumulate, st, stats, seg_n0)) return e;
+  if (stats) bn_partial_layout(n_out, seg_n0, nsplit == 1, chunks, chunks0);
   if (nsplit > 1) {
+    if (stats) return bn_reduce_stats_launch((const float*)ws, nsplit, Y, ldy, n_out, seg_n0, Cout, stats, st);
     int64_t n4 = n_out * (Cout / 4);
     conv_split_reduce_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>((const float*)ws, nsplit, n_out, Cout, bias, Y, ldy, accumulate);
     return check_launch("conv_split_reduce_kernel");
   }
   return PCB_OK;
+}
+}  // namespace pcb
+
+extern "C" int pcb_conv_forward_split(const uint16_t* Xhi, const uint16_t* Xlo, int lds, const int32_t* tbl, int64_t tbl_stride,
+                                      const int32_t* kmap, int K, int64_t n_out, int Cin, int Cout, const void* w_tiles,
+                                      const float* bias, float* Y, int ldy, void* ws, size_t ws_bytes,
+                                      int flags, void* stream) {
+  return pcb::conv_forward_split_impl(Xhi, Xlo, lds, tbl, tbl_stride, kmap, K, n_out, Cin, Cout, w_tiles, bias, Y, ldy, ws, ws_bytes, flags,
+                                      (cudaStream_t)stream, nullptr, 0, nullptr, nullptr);
 }
 
 namespace {
@@ -872,6 +896,7 @@ extern "C" int pcb_conv_wgrad_split(const uint16_t* Ahi, const uint16_t* Alo, in
     return PCB_OK;
   }
   PCB_ARG(Ahi && Alo && Bhi && Blo && tbl && ws && tbl_stride >= n_out);
+  ProfScope prof(st, 1);
   const int splits = wgrad_split_splits(K, n_out, Ca, Cb);
   PCB_ARG(ws_bytes >= (size_t)splits * nW * sizeof(float));
   int64_t rps = (n_out + splits - 1) / splits;

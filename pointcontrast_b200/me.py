@@ -117,8 +117,8 @@ _WS = {}
 
 
 def workspace(nbytes, device, slot=0):
-    """Stream-ordered scratch owned by torch's allocator; grows, never shrinks."""
-    key = (device.index, slot)
+    """Stream-ordered scratch owned by torch's allocator, one per (device, slot, stream); grows, never shrinks."""
+    key = (device.index, slot, torch.cuda.current_stream(device).cuda_stream)
     t = _WS.get(key)
     if t is None or t.numel() < nbytes:
         t = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
@@ -141,7 +141,7 @@ class ConvPlan:
     fwd:   Y[j]  = sum_k X[fwd_tbl[fwd_kmap[k]][j]] W[k]
     dgrad: dX[i] = sum_k dY[dg_tbl[dg_kmap[k]][i]] W[k]^T
     wgrad: dW[k] = sum_r A[wg_tbl[k][r]]^T B[r], (A,B) = (X,dY) if wg_gather_x else (dY,X) with transposed output."""
-    __slots__ = ("K", "n_in", "n_out", "fwd_tbl", "fwd_kmap", "dg_tbl", "dg_kmap", "wg_tbl", "wg_gather_x", "_counts")
+    __slots__ = ("K", "n_in", "n_out", "fwd_tbl", "fwd_kmap", "dg_tbl", "dg_kmap", "wg_tbl", "wg_gather_x", "_counts", "_c_kmaps")
 
     def pair_counts(self):
         """|M_k| per kernel offset (host list) -- the ME per-offset map sizes."""
@@ -248,7 +248,7 @@ class CoordsManager:
             with torch.cuda.device(self.device):
                 out_keys = torch.empty(src.n, dtype=torch.int64, device=self.device)
                 wsb = lib.pcb_coords_stride_ws_bytes(src.n)
-                ws = workspace(wsb, self.device)
+                ws = workspace(wsb, self.device, slot=4)
                 n_out = ctypes.c_int64(0)
                 check(lib.pcb_coords_stride(ptr(src.keys), src.n, new_ts[0], ptr(out_keys), None, ctypes.byref(n_out),
                                             ptr(ws), wsb, stream()))
@@ -288,6 +288,7 @@ class CoordsManager:
                 self.plans[ck] = ent
         p = ConvPlan()
         p._counts = None
+        p._c_kmaps = {}
         p.K = kgen.kernel_volume
         p.n_in, p.n_out = self.levels[in_key.ts].n, self.levels[out_key.ts].n
         if "same" in ent:
@@ -383,23 +384,18 @@ import os as _os
 FORCE_SIMT = False      # tests flip this to run the exact fp32 kernels
 SIMT_OPS = set()        # diagnostics (profiles/grad_precision_ab.py): subset of {"fwd", "dgrad", "wgrad"} forced onto the exact fp32 kernels (modular path)
 CONV_IMPL = _os.environ.get("PCB_CONV_IMPL", "tcgen05")     # "mma" (mma.sync) | "tcgen05" (TMEM accumulators)
-PROFILE = None          # bench.py sets this to a list: every conv launch is then bracketed by CUDA events
+# bench.py sets this to a list: every convolution / weight-gradient entry-point call then appends its description here, in
+# issue order -- the same order in which the library (pcb_profile_enable) brackets those calls with CUDA events.
+PROFILE = None
 
 
 def _prof_begin():
-    if PROFILE is None:
-        return None
-    ev = torch.cuda.Event(enable_timing=True)
-    ev.record()
-    return ev
+    return PROFILE is not None
 
 
-def _prof_end(ev0, kind, plan, K, Cin, Cout, tc):
-    if ev0 is None:
-        return
-    ev1 = torch.cuda.Event(enable_timing=True)
-    ev1.record()
-    PROFILE.append(dict(kind=kind, K=K, Cin=Cin, Cout=Cout, n_in=plan.n_in, n_out=plan.n_out, plan=plan, tc=tc, ev0=ev0, ev1=ev1))
+def _prof_end(on, kind, plan, K, Cin, Cout, tc):
+    if on:
+        PROFILE.append(dict(kind=kind, K=K, Cin=Cin, Cout=Cout, n_in=plan.n_in, n_out=plan.n_out, plan=plan, tc=tc))
 
 
 _WEIGHTS_EPOCH = [0]

@@ -97,6 +97,8 @@ class ContrastiveLossTrainer:
             for b in model.buffers():
                 dist.broadcast(b, 0)
             self.optimizer.grad_scale = 1.0 / self.world
+        self.timing = None                       # bench.py: dict -> CUDA events of one step (per-rank breakdown)
+        self._setup_gradient_chunks()
 
     # -- checkpoint (`ddp_trainer.py:151-169`)
     def _save_checkpoint(self, curr_iter, filename="checkpoint"):
@@ -115,14 +117,106 @@ class ContrastiveLossTrainer:
         os.symlink(f"{filename}.pth", link)
 
     # -- shared step pieces
+    def prepare(self, input_dict):
+        """Stage a batch: host->device copies, view stacking and the whole coordinate-manager build on a side stream
+        (`fused.prepare_pair`).  Returns the dict with the staged batch attached; `train_step` consumes it.  Calling this
+        for batch i+1 before the loss of batch i is read back takes the coordinate build off the critical path."""
+        if "_prepared" not in input_dict and fused.can_stack(self.model, self.device) and len(input_dict["sinput0_C"]) \
+                and len(input_dict["sinput1_C"]):
+            input_dict = dict(input_dict)
+            input_dict["_prepared"] = fused.prepare_pair(self.model, input_dict["sinput0_F"], input_dict["sinput0_C"],
+                                                         input_dict["sinput1_F"], input_dict["sinput1_C"], self.device)
+        return input_dict
+
     def _forward_views(self, input_dict):
-        dev = self.device
+        prep = input_dict.get("_prepared")
+        if prep is not None:
+            return fused.run_prepared(self.model, prep)
         return fused.forward_pair(self.model, input_dict["sinput0_F"], input_dict["sinput0_C"], input_dict["sinput1_F"],
-                                  input_dict["sinput1_C"], dev)
+                                  input_dict["sinput1_C"], self.device)
+
+    def _next_batch(self, data_loader_iter):
+        """The batch for this iteration (staged during the previous one if there was one) -- `ddp_trainer.py:287,389`."""
+        nxt = self.__dict__.pop("_staged", None)
+        if nxt is not None and nxt[0] is data_loader_iter:
+            return nxt[1]
+        return self.prepare(next(data_loader_iter))
+
+    def _stage_next(self, data_loader_iter):
+        """Fetch and stage the following batch while this iteration's kernels are still running (before the loss read-back)."""
+        try:
+            self._staged = (data_loader_iter, self.prepare(next(data_loader_iter)))
+        except StopIteration:
+            self._staged = None
+
+    # -- gradient all-reduce, overlapped with the backward pass (`ddp_trainer.py:96-102`: DistributedDataParallel's buckets)
+    def _setup_gradient_chunks(self):
+        """Parameters are registered in forward order, so the backward sweep completes the flat gradient buffer from its END:
+        [decoder: convtr4p16s2 .. final] is complete once convtr4p16s2's unit has run backward (~85 % of the bytes together
+        with the next chunk, while the costly stride-1/2 encoder layers are still to come), [conv4p8s2 .. block4] after
+        conv4p8s2's unit, the rest at the end.  Each chunk's NCCL all-reduce (sum; 1/world is folded into the SGD kernel) is
+        launched on a side stream as soon as its last weight gradient is enqueued."""
+        self._chunk_after = {}
+        self._comm = None
+        m = self.model
+        if self.world <= 1 or not fused.matches(m):
+            return
+        off = {id(p): o for p, o in zip(self.optimizer.param_groups[0]["params"], self.optimizer._offsets)}
+        b1, b2 = off[id(m.convtr4p16s2.kernel)], off[id(m.conv4p8s2.kernel)]
+        late = {id(p) for mod in (m.convtr4p16s2, m.bntr4, m.block5, m.convtr5p8s2, m.bntr5, m.block6, m.convtr6p4s2, m.bntr6, m.block7,
+                                  m.convtr7p2s2, m.bntr7, m.block8, m.final) for p in mod.parameters()}
+        mid = {id(p) for mod in (m.conv4p8s2, m.bn4, m.block4) for p in mod.parameters()}
+        ok = all((o >= b1) == (pid in late) and (b2 <= o < b1) == (pid in mid) for pid, o in off.items())
+        if ok:                                   # else (unexpected registration order): one all-reduce after the backward pass
+            self._chunk_after = {id(m.convtr4p16s2): b1, id(m.conv4p8s2): b2}
+            m.__dict__["_fused_after_unit"] = self._on_unit_backward_done
+        self._comm = torch.cuda.Stream(device=self.device)
+        self._pending_hi = self.optimizer.flat_grad.numel()
+
+    def _on_unit_backward_done(self, conv):
+        lo = self._chunk_after.get(id(conv))
+        if lo is not None:
+            self._reduce_range(lo, self._pending_hi)
+
+    def _reduce_range(self, lo, hi):
+        if hi <= lo:
+            return
+        ev = torch.cuda.Event()
+        ev.record()                              # everything that wrote flat_grad[lo:hi] is enqueued before this point
+        comm = self._comm if self._comm is not None else torch.cuda.current_stream()
+        comm.wait_event(ev)
+        with torch.cuda.stream(comm):
+            if self.timing is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            dist.all_reduce(self.optimizer.flat_grad[lo:hi])
+            if self.timing is not None:
+                e1.record()
+                self.timing.setdefault("allreduce", []).append((e0, e1))
+        self._pending_hi = lo
 
     def _all_reduce_grads(self):
+        """The part of the flat gradient not yet reduced during the backward pass, then the compute stream waits for all chunks."""
         if self.world > 1:
-            dist.all_reduce(self.optimizer.flat_grad)          # sum; the 1/world is folded into the SGD kernel
+            if self.timing is not None:
+                t0 = torch.cuda.Event(enable_timing=True); t0.record()
+                self.timing["tail"] = [t0, None]
+            self._reduce_range(0, self._pending_hi)
+            self._pending_hi = self.optimizer.flat_grad.numel()
+            if self._comm is not None:
+                torch.cuda.current_stream().wait_stream(self._comm)
+
+    def _step_timing(self, begin):
+        if self.timing is None:
+            return
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        if begin:
+            self.timing["total"] = [e, None]
+        else:
+            self.timing["total"][1] = e
+            if "tail" in self.timing:
+                self.timing["tail"][1] = e
 
     def train(self):
         curr_iter = self.curr_iter
@@ -157,6 +251,7 @@ class HardestContrastiveLossTrainer(ContrastiveLossTrainer):
     def train_step(self, input_dict):
         """One iteration on a batch dict; returns device scalars (loss, pos_loss, neg_loss) without synchronising."""
         self.model.train()
+        self._step_timing(True)
         self.optimizer.zero_grad()
         F0, F1 = self._forward_views(input_dict)
         pos_pairs = input_dict["correspondences"].to(self.device, non_blocking=True)
@@ -167,11 +262,13 @@ class HardestContrastiveLossTrainer(ContrastiveLossTrainer):
         loss.backward()
         self._all_reduce_grads()
         self.optimizer.step()
+        self._step_timing(False)
         return loss.detach(), pos_loss.detach(), neg_loss.detach()
 
     def _train_iter(self, data_loader_iter, timers):
-        input_dict = next(data_loader_iter)
+        input_dict = self._next_batch(data_loader_iter)
         loss, pos_loss, neg_loss = self.train_step(input_dict)
+        self._stage_next(data_loader_iter)
         result = scaled_all_reduce_dict({"loss": loss, "pos_loss": pos_loss, "neg_loss": neg_loss}, self.world)
         return result["loss"].item(), result["pos_loss"].item(), result["neg_loss"].item()
 
@@ -185,6 +282,8 @@ class PointNCELossTrainer(ContrastiveLossTrainer):
         self.npos = config.misc.npos
 
     def train_step(self, input_dict):
+        self.model.train()
+        self._step_timing(True)
         self.optimizer.zero_grad()
         F0, F1 = self._forward_views(input_dict)
         pos_pairs = input_dict["correspondences"].to(self.device, non_blocking=True)
@@ -193,11 +292,13 @@ class PointNCELossTrainer(ContrastiveLossTrainer):
         loss.backward()
         self._all_reduce_grads()
         self.optimizer.step()
+        self._step_timing(False)
         return loss.detach()
 
     def _train_iter(self, data_loader_iter, timers):
-        input_dict = next(data_loader_iter)
+        input_dict = self._next_batch(data_loader_iter)
         loss = self.train_step(input_dict)
+        self._stage_next(data_loader_iter)
         result = scaled_all_reduce_dict({"loss": loss}, self.world)
         return result["loss"].item()
 

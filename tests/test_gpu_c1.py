@@ -11,7 +11,7 @@ holds that mode, and the whole network at full C1 size, to the fp64 oracle:
     loss, every parameter gradient, per-offset kernel-map sizes of every level (`lib/ddp_trainer.py:392-426`);
   * the same features through the hardest-contrastive loss (`lib/ddp_trainer.py:186-238,290-308`);
   * the REFERENCE's own `model/res16unet.py` (staged copy, `oracle/stage_ref.py`) executed on CUDA through
-    `pointcontrast_b200.me.install()`: it must take the fused executor and reproduce this package's model bit for bit.
+    `pointcontrast_b200.me.install()`: it must take the fused executor and reproduce this package's model (features bit for bit).
 
 Tolerances: 1e-3 relative on features and losses (north star); parameter gradients max(1e-3, 10 x the fp32-CPU floor of
 the same graph), as in test_gpu_model.py.
@@ -246,7 +246,7 @@ def test_reference_model_file_runs_on_cuda_fused():
     assert max_rel_err(ref[0], torch.from_numpy(g["F0"])) < TOL and max_rel_err(ref[1], torch.from_numpy(g["F1"])) < TOL
     assert abs(ref[2] - float(g["loss"])) / float(g["loss"]) < TOL
     assert torch.equal(ref[0], own[0]) and torch.equal(ref[1], own[1]) and ref[2] == own[2]
-    for n in own[3]:
-        assert torch.equal(ref[3][n], own[3][n]), n
+    for n in own[3]:          # same kernels in the same order; the loss's gather backward (ATen index_put, atomics) is not bit-reproducible
+        assert rel_err(ref[3][n], own[3][n]) < 1e-5, n
     for n in own[4]:
         assert torch.equal(ref[4][n], own[4][n]), n
