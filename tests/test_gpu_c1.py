@@ -250,3 +250,28 @@ def test_reference_model_file_runs_on_cuda_fused():
         assert rel_err(ref[3][n], own[3][n]) < 1e-5, n
     for n in own[4]:
         assert torch.equal(ref[4][n], own[4][n]), n
+
+
+def test_fused_epilogue_statistics_match_separate_pass(c1):
+    """BatchNorm statistics from the convolution's TMEM epilogue / offset-split reduction pass (default) vs a separate column-sum
+    pass over z (PCB_UNIT_SEPARATE_STATS): same numbers up to the fp32 order of the per-tile partial sums -- on the full-size
+    pair, which has direct-mode levels (tile straddling the view boundary included) and offset-split levels."""
+    from pointcontrast_b200 import fused
+    from pointcontrast_b200.model import load_model
+    b = c1["batch"]
+    outs = {}
+    for sep in (False, True):
+        fused.SEPARATE_STATS = sep
+        try:
+            net = load_model("Res16UNet34C")(3, 32, refload.default_config(), D=3)
+            det_init(net, 5)
+            net = net.cuda().train()
+            F0, F1 = net.forward_pair(torch.from_numpy(b["sinput0_F"]), torch.from_numpy(b["sinput0_C"]), torch.from_numpy(b["sinput1_F"]),
+                                      torch.from_numpy(b["sinput1_C"]), torch.device("cuda"))
+            outs[sep] = (F0.detach(), F1.detach(), {n: v.clone() for n, v in net.named_buffers() if v.dtype.is_floating_point})
+        finally:
+            fused.SEPARATE_STATS = False
+    assert max_rel_err(outs[False][0], outs[True][0]) < 2e-5 and max_rel_err(outs[False][1], outs[True][1]) < 2e-5
+    for n in outs[True][2]:
+        assert rel_err(outs[False][2][n], outs[True][2][n]) < 1e-5, n
+    assert torch.equal(outs[False][0], c1["F"][0])            # the default path is the one the other tests of this file checked
