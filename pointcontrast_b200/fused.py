@@ -360,6 +360,9 @@ class Runner:
         """Scratch for the largest unit of this geometry (the units run back to back on one stream and share it)."""
         m = self.model
         n, best = g.n, 0
+        cached = self.__dict__.setdefault("_ws_cache", {})
+        if tuple(n) in cached:
+            return cached[tuple(n)]
         shapes = {(27, n[0], n[0], m.conv0p1s1.in_channels, m.INIT_DIM)}
         for name, lvl in (("block1", 1), ("block2", 2), ("block3", 3), ("block4", 4), ("block5", 3), ("block6", 2), ("block7", 1), ("block8", 0)):
             for blk in getattr(m, name):
@@ -374,6 +377,9 @@ class Runner:
             shapes.add((8, n[i + 1], n[i], u.in_channels, u.out_channels))
         for (K, n_in, n_out, ci, co) in shapes:
             best = max(best, lib.pcb_unit_ws_bytes(K, n_in, n_out, ci, co))
+        if len(cached) > 64:
+            cached.clear()
+        cached[tuple(n)] = best
         return best
 
     def forward(self, sinput, view0_rows=None, geom=None):
