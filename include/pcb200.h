@@ -105,6 +105,9 @@ int pcb_weight_prep(const float* W, int K, int Cin, int Cout, uint16_t* w_hi, ui
 #define PCB_CONV_FORCE_SIMT 1
 #define PCB_CONV_TCGEN05 2     /* use the tcgen05/TMEM kernel (needs wk_hi/wk_lo = the K-major planes [K][Cout][Cin]) */
 #define PCB_CONV_ACCUMULATE 4  /* Y += result (pcb_conv_forward, tcgen05 path) / dW += result (pcb_conv_wgrad) */
+#define PCB_PLANES_A_FP16 8    /* split-operand calls: the GATHERED operand's planes are fp16 hi/lo (default: bf16 hi/lo) */
+#define PCB_PLANES_B_FP16 16   /* pcb_conv_forward_split: the weight tiles are fp16 x 2^10 (pcb_weight_tile with this flag);
+                                  pcb_conv_wgrad_split: the ROW-ALIGNED operand's planes are fp16 */
 /* Small levels split the (offset, channel-chunk) loop over extra CTAs and reduce through `ws` (deterministic). */
 size_t pcb_conv_forward_ws_bytes(int K, int64_t n_out, int Cin, int Cout);
 int pcb_conv_forward(const float* X, int ldx, const int32_t* tbl, int64_t tbl_stride, const int32_t* kmap, int K,
@@ -124,9 +127,10 @@ int pcb_conv_wgrad(const float* A, int lda, const float* B, int ldb, const int32
  * operand staging is then a pure asynchronous copy (cp.async, zero-filled where a neighbour is missing). */
 /* pcb_weight_tile: fp32 W[K][Cin][Cout] -> split weights pre-tiled as the shared-memory images of the split conv kernel (one
  * contiguous blob per (offset, 32-channel chunk, column block), fetched by ONE TMA bulk copy per pipeline stage):
- * `fwd_tiles` for the forward roles, `dgrad_tiles` for the data-gradient roles (Cin/Cout swapped). */
+ * `fwd_tiles` for the forward roles, `dgrad_tiles` for the data-gradient roles (Cin/Cout swapped).  flags & PCB_PLANES_B_FP16:
+ * the FORWARD tiles hold fp16 hi/lo of W * 2^10 (|W| < 60; the kernel rescales its output), the data-gradient tiles stay bf16. */
 size_t pcb_weight_tile_bytes(int K, int Cin, int Cout, int dgrad_roles);
-int pcb_weight_tile(const float* W, int K, int Cin, int Cout, void* fwd_tiles, void* dgrad_tiles, void* stream);
+int pcb_weight_tile(const float* W, int K, int Cin, int Cout, void* fwd_tiles, void* dgrad_tiles, int flags, void* stream);
 int pcb_conv_forward_split(const uint16_t* Xhi, const uint16_t* Xlo, int lds, const int32_t* tbl, int64_t tbl_stride,
                            const int32_t* kmap, int K, int64_t n_out, int Cin, int Cout, const void* w_tiles,
                            const float* bias, float* Y, int ldy, void* ws, size_t ws_bytes, int flags, void* stream);
@@ -149,21 +153,14 @@ int pcb_bn_backward(const float* dY, const float* X, int64_t n, int C, const flo
                     const float* gamma, float* dX, float* dgamma, float* dbeta, void* ws, size_t ws_bytes,
                     void* stream);
 
-/* Strided / fused variants used by the fused network executor (pointcontrast_b200/fused.py).  All ld* are row strides
+/* Strided / row-segmented variants used by the fused network executor (pointcontrast_b200/fused.py).  All ld* are row strides
  * in floats (>= C, multiples of 4), so inputs/outputs may be column slices of wider (concatenated) buffers.
- *   pcb_bn_apply2   : Y = [relu]( (X-mean)*invstd*gamma+beta [+ residual] )
- *   pcb_bn_backward2: g = dY * (relu_out > 0) if relu_out else dY;   dgamma/dbeta (+)= sum(g*xhat) / sum(g);
- *                     dX = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat));   gout (=|+=) g  (gout_mode 0 none, 1 write, 2 add)
- *                     -- gout is the gradient of the residual input of the forward unit; it may alias dY. */
-int pcb_bn_stats2(const float* X, int ldx, int64_t n, int C, float eps, float momentum, float* mean, float* invstd,
-                  float* running_mean, float* running_var, void* ws, size_t ws_bytes, void* stream);
-int pcb_bn_apply2(const float* X, int ldx, int64_t n, int C, const float* mean, const float* invstd, const float* gamma,
-                  const float* beta, const float* residual, int ldr, int relu, float* Y, int ldy, uint16_t* Yhi,
-                  uint16_t* Ylo, int lds, void* stream);
-int pcb_bn_backward2(const float* dY, int lddy, const float* X, int ldx, const float* relu_out, int ldm, int64_t n, int C,
-                     const float* mean, const float* invstd, const float* gamma, float* dX, int lddx, float* dgamma,
-                     float* dbeta, int accumulate_param_grads, float* gout, int ldg, int gout_mode, uint16_t* dXhi,
-                     uint16_t* dXlo, int lds, void* ws, size_t ws_bytes, void* stream);
+ *   apply   : Y = [relu]( (X-mean)*invstd*gamma+beta [+ residual] ), as fp32 (Y, may be NULL) and/or split planes (Yhi/Ylo);
+ *             flags: PCB_BN_RELU, PCB_PLANES_A_FP16 (the planes are fp16 hi/lo instead of bf16 hi/lo)
+ *   backward: g = dY * (relu_out > 0) if relu_out else dY;   dgamma/dbeta (+)= sum(g*xhat) / sum(g);
+ *             dX = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat));   gout (=|+=) g  (gout_mode 0 none, 1 write, 2 add)
+ *             -- gout is the gradient of the residual input of the forward unit; it may alias dY. */
+#define PCB_BN_RELU 1
 /* Row-segmented variants: rows [0, n0) and [n0, n) are two independent BatchNorm batches -- the two views of a scene pair
  * stacked in one feature matrix, each normalised with its own statistics exactly as the reference's two forward calls do
  * (`lib/ddp_trainer.py:290-297,392-398`).  mean / invstd are [2][C]; the running statistics are updated with segment 0 and
@@ -171,16 +168,18 @@ int pcb_bn_backward2(const float* dY, int lddy, const float* X, int ldx, const f
 int pcb_bn_stats_seg(const float* X, int ldx, int64_t n, int64_t n0, int C, float eps, float momentum, float* mean, float* invstd,
                      float* running_mean, float* running_var, void* ws, size_t ws_bytes, void* stream);
 int pcb_bn_apply_seg(const float* X, int ldx, int64_t n, int64_t n0, int C, const float* mean, const float* invstd,
-                     const float* gamma, const float* beta, const float* residual, int ldr, int relu, float* Y, int ldy,
+                     const float* gamma, const float* beta, const float* residual, int ldr, int flags, float* Y, int ldy,
                      uint16_t* Yhi, uint16_t* Ylo, int lds, void* stream);
 int pcb_bn_backward_seg(const float* dY, int lddy, const float* X, int ldx, const float* relu_out, int ldm, int64_t n, int64_t n0,
                         int C, const float* mean, const float* invstd, const float* gamma, float* dX, int lddx, float* dgamma,
                         float* dbeta, int accumulate_param_grads, float* gout, int ldg, int gout_mode, uint16_t* dXhi,
                         uint16_t* dXlo, int lds, void* ws, size_t ws_bytes, void* stream);
-/* "Split" operand format of the tensor-core conv kernels: an fp32 matrix stored as two bf16 planes, x ~= hi + lo (2^-17);
+/* "Split" operand format of the tensor-core conv kernels: an fp32 matrix stored as two 16-bit planes, x ~= hi + lo: bf16 planes
+ * (2^-17 relative, fp32's exponent range: gradients) or, with PCB_PLANES_A_FP16, fp16 planes (2^-22 relative, |x| < 65504: the
+ * activations gathered by the FORWARD convolutions -- the forward pass sets the whole-network gradient error, profiles/r2_results.md);
  * row stride lds in ELEMENTS.  The elementwise producers above can emit it directly (Yhi/Ylo, dXhi/dXlo; NULL = off; dX may
  * then be NULL), so the conv kernels' gather becomes a pure asynchronous copy.  pcb_split_rows converts an fp32 matrix. */
-int pcb_split_rows(const float* X, int ldx, int64_t n, int C, uint16_t* hi, uint16_t* lo, int lds, void* stream);
+int pcb_split_rows(const float* X, int ldx, int64_t n, int C, uint16_t* hi, uint16_t* lo, int lds, int flags, void* stream);
 
 /* ----------------------------------------------------------------------------------------------- fused units */
 /* One "unit" of the Res16UNet graph = convolution -> BatchNorm (training statistics) -> [+ residual] -> [ReLU]
@@ -224,6 +223,9 @@ typedef struct pcb_unit {
   int32_t flags;                                    /* PCB_UNIT_* */
 } pcb_unit;
 #define PCB_UNIT_SEPARATE_STATS 1   /* forward: BatchNorm statistics by a separate pass over z (cross-check of the fused epilogue) */
+#define PCB_UNIT_FP16_FORWARD 2     /* activations travel as fp16 hi/lo planes (x_hi/x_lo, out_hi/out_lo) and wt_fwd holds fp16 tiles
+                                       (pcb_weight_tile with PCB_PLANES_B_FP16): 2^-22 products in the forward pass; gradients
+                                       (dz) and the data-gradient tiles stay bf16 hi/lo (fp32's exponent range) */
 size_t pcb_unit_ws_bytes(int K, int64_t n_in, int64_t n_out, int Cin, int Cout);
 int pcb_unit_forward(const pcb_unit* u, void* stream);
 int pcb_unit_backward(const pcb_unit* u, void* stream);

@@ -42,7 +42,7 @@ _SIGS = {
     "pcb_conv_wgrad_ws_bytes": (_sz, [_i, _l, _i, _i]),
     "pcb_conv_wgrad": (_i, [_p, _i, _p, _i, _p, _l, _i, _l, _i, _i, _p, _i, _p, _sz, _i, _p]),
     "pcb_weight_tile_bytes": (_sz, [_i, _i, _i, _i]),
-    "pcb_weight_tile": (_i, [_p, _i, _i, _i, _p, _p, _p]),
+    "pcb_weight_tile": (_i, [_p, _i, _i, _i, _p, _p, _i, _p]),
     "pcb_conv_forward_split": (_i, [_p, _p, _i, _p, _l, _p, _i, _l, _i, _i, _p, _p, _p, _i, _p, _sz, _i, _p]),
     "pcb_conv_wgrad_split_ws_bytes": (_sz, [_i, _l, _i, _i]),
     "pcb_conv_wgrad_split": (_i, [_p, _p, _i, _p, _p, _i, _p, _l, _i, _l, _i, _i, _p, _i, _p, _sz, _i, _p]),
@@ -50,14 +50,11 @@ _SIGS = {
     "pcb_bn_stats": (_i, [_p, _l, _i, _f, _f, _p, _p, _p, _p, _p, _sz, _p]),
     "pcb_bn_apply": (_i, [_p, _l, _i, _p, _p, _p, _p, _p, _i, _p, _p]),
     "pcb_bn_backward": (_i, [_p, _p, _l, _i, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
-    "pcb_bn_stats2": (_i, [_p, _i, _l, _i, _f, _f, _p, _p, _p, _p, _p, _sz, _p]),
-    "pcb_bn_apply2": (_i, [_p, _i, _l, _i, _p, _p, _p, _p, _p, _i, _i, _p, _i, _p, _p, _i, _p]),
-    "pcb_bn_backward2": (_i, [_p, _i, _p, _i, _p, _i, _l, _i, _p, _p, _p, _p, _i, _p, _p, _i, _p, _i, _i, _p, _p, _i, _p, _sz, _p]),
     "pcb_bn_stats_seg": (_i, [_p, _i, _l, _l, _i, _f, _f, _p, _p, _p, _p, _p, _sz, _p]),
     "pcb_bn_apply_seg": (_i, [_p, _i, _l, _l, _i, _p, _p, _p, _p, _p, _i, _i, _p, _i, _p, _p, _i, _p]),
     "pcb_bn_backward_seg": (_i, [_p, _i, _p, _i, _p, _i, _l, _l, _i, _p, _p, _p, _p, _i, _p, _p, _i, _p, _i, _i, _p, _p, _i, _p, _sz,
                                  _p]),
-    "pcb_split_rows": (_i, [_p, _i, _l, _i, _p, _p, _i, _p]),
+    "pcb_split_rows": (_i, [_p, _i, _l, _i, _p, _p, _i, _i, _p]),
     "pcb_nce_ws_bytes": (_sz, [_l]),
     "pcb_nce_forward_backward": (_i, [_p, _p, _l, _i, _f, _p, _p, _p, _p, _sz, _p]),
     "pcb_pdist_rowmin": (_i, [_p, _l, _p, _l, _i, _p, _p, _p, _p]),

@@ -2,6 +2,7 @@
 // affine-normalise (+ residual, + ReLU) fused into one elementwise pass.  HBM-bound: every kernel moves
 // 16-byte vectors with consecutive threads on consecutive channels.
 // Replaces MinkowskiBatchNorm == torch.nn.BatchNorm1d on .F (reference call sites in include/pcb200.h).
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 using namespace pcb;
@@ -9,6 +10,21 @@ using namespace pcb;
 namespace {
 
 constexpr int ROWS_PER_CHUNK = 128;
+
+// fp32 x4 -> fp16 hi x4 + fp16 lo x4 (x ~= hi + lo to 2^-22 |x|, absolute floor 2^-25: fp16 subnormals): the operand format of the
+// FORWARD convolutions.  Activations are O(1) after BatchNorm; |x| is clamped to the fp16 range (65504) so that hi stays finite.
+__device__ __forceinline__ void store_split4_f16(const float4& v, void* hi, void* lo) {
+  const float M = 65000.f;
+  const float x = fminf(fmaxf(v.x, -M), M), y = fminf(fmaxf(v.y, -M), M), z = fminf(fmaxf(v.z, -M), M), w = fminf(fmaxf(v.w, -M), M);
+  __half2 h0 = __floats2half2_rn(x, y), h1 = __floats2half2_rn(z, w);
+  float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+  __half2 l0 = __floats2half2_rn(x - f0.x, y - f0.y), l1 = __floats2half2_rn(z - f1.x, w - f1.y);
+  uint2 H, L;
+  H.x = *reinterpret_cast<uint32_t*>(&h0); H.y = *reinterpret_cast<uint32_t*>(&h1);
+  L.x = *reinterpret_cast<uint32_t*>(&l0); L.y = *reinterpret_cast<uint32_t*>(&l1);
+  *reinterpret_cast<uint2*>(hi) = H;
+  *reinterpret_cast<uint2*>(lo) = L;
+}
 
 // fp32 x4 -> bf16 hi x4 + bf16 lo x4 (x ~= hi + lo to 2^-17): the operand format of the tensor-core conv kernels
 __device__ __forceinline__ void store_split4(const float4& v, __nv_bfloat16* hi, __nv_bfloat16* lo) {
@@ -25,13 +41,15 @@ __device__ __forceinline__ void store_split4(const float4& v, __nv_bfloat16* hi,
 }
 
 __global__ void split_rows_kernel(const float* __restrict__ X, int ldx, int64_t n4, int cv, __nv_bfloat16* __restrict__ hi,
-                                  __nv_bfloat16* __restrict__ lo, int lds) {
+                                  __nv_bfloat16* __restrict__ lo, int lds, int fp16) {
+  pdl_wait(); pdl_trigger();
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n4) return;
   int c4 = (int)(i % cv);
   const int64_t row = i / cv;
   float4 x = __ldg(reinterpret_cast<const float4*>(X + row * ldx) + c4);
-  store_split4(x, hi + row * lds + c4 * 4, lo + row * lds + c4 * 4);
+  if (fp16) store_split4_f16(x, hi + row * lds + c4 * 4, lo + row * lds + c4 * 4);
+  else store_split4(x, hi + row * lds + c4 * 4, lo + row * lds + c4 * 4);
 }
 
 // partial[chunk][0][C] = sum(a), partial[chunk][1][C] = sum(a*b)    (b == a for the forward statistics)
@@ -54,6 +72,7 @@ __global__ void colsum_kernel(const float* __restrict__ A, int lda, const float*
                               const float* __restrict__ Mask, int ldm, const __nv_bfloat16* __restrict__ MaskH, int ldmh,
                               int64_t n, int64_t n0, int chunks0, int C,
                               const float* __restrict__ mean, const float* __restrict__ invstd, float* __restrict__ partial) {
+  pdl_wait(); pdl_trigger();
   extern __shared__ float sm[];      // [RP][2][C]
   const int cv = C / 4;
   const int rp = blockDim.x / cv;    // row lanes
@@ -104,6 +123,7 @@ __global__ void colsum_kernel(const float* __restrict__ A, int lda, const float*
 // pass (same chunking / segment layout as colsum_kernel<false>), so the statistics cost no extra read of Y.
 __global__ void reduce_stats_kernel(const float* __restrict__ P, int nsplit, float* __restrict__ Y, int ldy, int64_t n, int64_t n0,
                                     int chunks0, int C, float* __restrict__ partial) {
+  pdl_wait(); pdl_trigger();
   extern __shared__ float sm[];      // [RP][2][C]
   const int cv = C / 4;
   const int rp = blockDim.x / cv;
@@ -150,6 +170,7 @@ __device__ __forceinline__ void warp_sum2(const float* __restrict__ partial, int
 __global__ void bn_finalize_kernel(const float* __restrict__ partial, int chunks, int chunks0, int64_t n, int64_t n0, int C, float eps,
                                    float momentum, float* __restrict__ mean, float* __restrict__ invstd, float* running_mean,
                                    float* running_var) {
+  pdl_wait(); pdl_trigger();
   int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (c >= C) return;
   const int nseg = n0 < n ? 2 : 1;
@@ -177,7 +198,8 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, int chunks
 __global__ void bn_apply_kernel(const float* __restrict__ X, int ldx, int64_t n4, int cv, const float* __restrict__ mean,
                                 const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
                                 const float* __restrict__ residual, int ldr, int relu, float* __restrict__ Y, int ldy,
-                                __nv_bfloat16* __restrict__ Yhi, __nv_bfloat16* __restrict__ Ylo, int lds, int64_t n0) {
+                                __nv_bfloat16* __restrict__ Yhi, __nv_bfloat16* __restrict__ Ylo, int lds, int64_t n0, int fp16) {
+  pdl_wait(); pdl_trigger();
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n4) return;
   int c4 = (int)(i % cv);
@@ -195,13 +217,17 @@ __global__ void bn_apply_kernel(const float* __restrict__ X, int ldx, int64_t n4
   }
   if (relu) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
   if (Y) *reinterpret_cast<float4*>(Y + row * ldy + c4 * 4) = y;
-  if (Yhi) store_split4(y, Yhi + row * lds + c4 * 4, Ylo + row * lds + c4 * 4);
+  if (Yhi) {
+    if (fp16) store_split4_f16(y, Yhi + row * lds + c4 * 4, Ylo + row * lds + c4 * 4);
+    else store_split4(y, Yhi + row * lds + c4 * 4, Ylo + row * lds + c4 * 4);
+  }
 }
 
 // dgamma = sum(dY*xhat), dbeta = sum(dY) over ALL rows (both segments: the parameters are shared);
 // sums[seg][0][C] = that segment's dbeta, sums[seg][1][C] = its dgamma for the apply pass.
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int chunks, int chunks0, int nseg, int C,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate, float* __restrict__ sums) {
+  pdl_wait(); pdl_trigger();
   int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (c >= C) return;
   float tb = 0.f, tg = 0.f;
@@ -230,6 +256,7 @@ __global__ void bn_bwd_apply_kernel(const float* dY, int lddy, const float* __re
                                     const float* __restrict__ gamma, const float* __restrict__ sums, float* __restrict__ dX, int lddx,
                                     float* gout, int ldg, int gout_mode, __nv_bfloat16* __restrict__ dXhi,
                                     __nv_bfloat16* __restrict__ dXlo, int lds) {
+  pdl_wait(); pdl_trigger();
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n4) return;
   int c4 = (int)(i % cv);
@@ -290,17 +317,12 @@ extern "C" int pcb_bn_stats_seg(const float* X, int ldx, int64_t n, int64_t n0, 
   const int chunks = chunks0 + (n0 < n ? chunks_for(n - n0) : 0);
   const int thr = colsum_threads(C);
   const int rp = thr / (C / 4);
-  colsum_kernel<false><<<chunks, thr, (size_t)rp * 2 * C * sizeof(float), st>>>(X, ldx, nullptr, 0, nullptr, 0, nullptr, 0, n, n0, chunks0, C,
+  launch_kernel(colsum_kernel<false>, chunks, thr, (size_t)rp * 2 * C * sizeof(float), st, X, ldx, nullptr, 0, nullptr, 0, nullptr, 0, n, n0, chunks0, C,
                                                                                  nullptr, nullptr, (float*)ws);
   if (int e = check_launch("colsum_kernel")) return e;
-  bn_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>((const float*)ws, chunks, chunks0, n, n0, C, eps, momentum, mean, invstd, running_mean,
+  launch_kernel(bn_finalize_kernel, (C + 7) / 8, 256, 0, st, (const float*)ws, chunks, chunks0, n, n0, C, eps, momentum, mean, invstd, running_mean,
                                                       running_var);
   return check_launch("bn_finalize_kernel");
-}
-
-extern "C" int pcb_bn_stats2(const float* X, int ldx, int64_t n, int C, float eps, float momentum, float* mean, float* invstd,
-                             float* running_mean, float* running_var, void* ws, size_t ws_bytes, void* stream) {
-  return pcb_bn_stats_seg(X, ldx, n, n, C, eps, momentum, mean, invstd, running_mean, running_var, ws, ws_bytes, stream);
 }
 
 extern "C" int pcb_bn_stats(const float* X, int64_t n, int C, float eps, float momentum, float* mean, float* invstd,
@@ -308,34 +330,28 @@ extern "C" int pcb_bn_stats(const float* X, int64_t n, int C, float eps, float m
   return pcb_bn_stats_seg(X, C, n, n, C, eps, momentum, mean, invstd, running_mean, running_var, ws, ws_bytes, stream);
 }
 
-extern "C" int pcb_split_rows(const float* X, int ldx, int64_t n, int C, uint16_t* hi, uint16_t* lo, int lds, void* stream) {
+extern "C" int pcb_split_rows(const float* X, int ldx, int64_t n, int C, uint16_t* hi, uint16_t* lo, int lds, int flags, void* stream) {
   PCB_ARG(n >= 0 && C >= 4 && C % 4 == 0 && ldx >= C && ldx % 4 == 0 && lds >= C && lds % 4 == 0);
   if (n == 0) return PCB_OK;
   PCB_ARG(X && hi && lo);
   int64_t n4 = n * (C / 4);
-  split_rows_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(X, ldx, n4, C / 4, (__nv_bfloat16*)hi,
-                                                                                   (__nv_bfloat16*)lo, lds);
+  launch_kernel(split_rows_kernel, (unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream, X, ldx, n4, C / 4, (__nv_bfloat16*)hi,
+                (__nv_bfloat16*)lo, lds, (flags & PCB_PLANES_A_FP16) ? 1 : 0);
   return check_launch("split_rows_kernel");
 }
 
 extern "C" int pcb_bn_apply_seg(const float* X, int ldx, int64_t n, int64_t n0, int C, const float* mean, const float* invstd,
-                                const float* gamma, const float* beta, const float* residual, int ldr, int relu, float* Y, int ldy,
+                                const float* gamma, const float* beta, const float* residual, int ldr, int flags, float* Y, int ldy,
                                 uint16_t* Yhi, uint16_t* Ylo, int lds, void* stream) {
+  const int relu = flags & PCB_BN_RELU;
   PCB_ARG(n >= 0 && n0 >= 0 && n0 <= n && C >= 4 && C % 4 == 0 && ldx % 4 == 0 && ldx >= C && (!Y || (ldy % 4 == 0 && ldy >= C)));
   if (n == 0) return PCB_OK;
   PCB_ARG(X && (Y || Yhi) && mean && invstd && gamma && beta && (!residual || (ldr >= C && ldr % 4 == 0)));
   PCB_ARG(!Yhi || (Ylo && lds >= C && lds % 4 == 0));
   int64_t n4 = n * (C / 4);
-  bn_apply_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(X, ldx, n4, C / 4, mean, invstd, gamma, beta, residual,
-                                                                                 ldr, relu, Y, ldy, (__nv_bfloat16*)Yhi,
-                                                                                 (__nv_bfloat16*)Ylo, lds, n0);
+  launch_kernel(bn_apply_kernel, (unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream, X, ldx, n4, C / 4, mean, invstd, gamma, beta, residual,
+                ldr, relu, Y, ldy, (__nv_bfloat16*)Yhi, (__nv_bfloat16*)Ylo, lds, n0, (flags & PCB_PLANES_A_FP16) ? 1 : 0);
   return check_launch("bn_apply_kernel");
-}
-
-extern "C" int pcb_bn_apply2(const float* X, int ldx, int64_t n, int C, const float* mean, const float* invstd, const float* gamma,
-                             const float* beta, const float* residual, int ldr, int relu, float* Y, int ldy, uint16_t* Yhi,
-                             uint16_t* Ylo, int lds, void* stream) {
-  return pcb_bn_apply_seg(X, ldx, n, n, C, mean, invstd, gamma, beta, residual, ldr, relu, Y, ldy, Yhi, Ylo, lds, stream);
 }
 
 extern "C" int pcb_bn_apply(const float* X, int64_t n, int C, const float* mean, const float* invstd, const float* gamma,
@@ -364,13 +380,13 @@ int bn_backward_impl(const float* dY, int lddy, const float* X, int ldx, const f
   const int rp = thr / (C / 4);
   float* partial = (float*)ws;
   float* sums = partial + (size_t)chunks * 2 * C;        // [segments][2][C]: dbeta, dgamma of THIS call (the apply pass needs them)
-  colsum_kernel<true><<<chunks, thr, (size_t)rp * 2 * C * sizeof(float), st>>>(dY, lddy, X, ldx, relu_out, ldm, (const __nv_bfloat16*)relu_hi,
+  launch_kernel(colsum_kernel<true>, chunks, thr, (size_t)rp * 2 * C * sizeof(float), st, dY, lddy, X, ldx, relu_out, ldm, (const __nv_bfloat16*)relu_hi,
                                                                                 ldmh, n, n0, chunks0, C, mean, invstd, partial);
   if (int e = check_launch("colsum_kernel<bwd>")) return e;
-  bn_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(partial, chunks, chunks0, nseg, C, dgamma, dbeta, accumulate_param_grads, sums);
+  launch_kernel(bn_bwd_finalize_kernel, (C + 7) / 8, 256, 0, st, partial, chunks, chunks0, nseg, C, dgamma, dbeta, accumulate_param_grads, sums);
   if (int e = check_launch("bn_bwd_finalize_kernel")) return e;
   int64_t n4 = n * (C / 4);
-  bn_bwd_apply_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(dY, lddy, X, ldx, relu_out, ldm, (const __nv_bfloat16*)relu_hi, ldmh, n4,
+  launch_kernel(bn_bwd_apply_kernel, (unsigned)((n4 + 255) / 256), 256, 0, st, dY, lddy, X, ldx, relu_out, ldm, (const __nv_bfloat16*)relu_hi, ldmh, n4,
                                                                     C / 4, n0, 1.0f / (float)n0, nseg == 2 ? 1.0f / (float)(n - n0) : 0.f, mean,
                                                                     invstd, gamma, sums, dX, lddx, gout, ldg, gout_mode,
                                                                     (__nv_bfloat16*)dXhi, (__nv_bfloat16*)dXlo, lds);
@@ -388,7 +404,7 @@ void bn_partial_layout(int64_t n, int64_t n0, bool conv_tile_aligned, int* chunk
 
 int bn_finalize_launch(const float* partial, int chunks, int chunks0, int64_t n, int64_t n0, int C, float eps, float momentum, float* mean,
                        float* invstd, float* running_mean, float* running_var, cudaStream_t st) {
-  bn_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(partial, chunks, chunks0, n, n0, C, eps, momentum, mean, invstd, running_mean, running_var);
+  launch_kernel(bn_finalize_kernel, (C + 7) / 8, 256, 0, st, partial, chunks, chunks0, n, n0, C, eps, momentum, mean, invstd, running_mean, running_var);
   return check_launch("bn_finalize_kernel");
 }
 
@@ -399,7 +415,7 @@ int bn_reduce_stats_launch(const float* P, int nsplit, float* Y, int ldy, int64_
   bn_partial_layout(n, n0, false, &chunks, &chunks0);
   const int thr = colsum_threads(C);
   const int rp = thr / (C / 4);
-  reduce_stats_kernel<<<chunks, thr, (size_t)rp * 2 * C * sizeof(float), st>>>(P, nsplit, Y, ldy, n, n0, chunks0, C, partial);
+  launch_kernel(reduce_stats_kernel, chunks, thr, (size_t)rp * 2 * C * sizeof(float), st, P, nsplit, Y, ldy, n, n0, chunks0, C, partial);
   return check_launch("reduce_stats_kernel");
 }
 }  // namespace pcb
@@ -410,14 +426,6 @@ extern "C" int pcb_bn_backward_seg(const float* dY, int lddy, const float* X, in
                                    uint16_t* dXhi, uint16_t* dXlo, int lds, void* ws, size_t ws_bytes, void* stream) {
   return pcb::bn_backward_impl(dY, lddy, X, ldx, relu_out, ldm, nullptr, 0, n, n0, C, mean, invstd, gamma, dX, lddx, dgamma, dbeta,
                                accumulate_param_grads, gout, ldg, gout_mode, dXhi, dXlo, lds, ws, ws_bytes, (cudaStream_t)stream);
-}
-
-extern "C" int pcb_bn_backward2(const float* dY, int lddy, const float* X, int ldx, const float* relu_out, int ldm, int64_t n, int C,
-                                const float* mean, const float* invstd, const float* gamma, float* dX, int lddx, float* dgamma,
-                                float* dbeta, int accumulate_param_grads, float* gout, int ldg, int gout_mode, uint16_t* dXhi,
-                                uint16_t* dXlo, int lds, void* ws, size_t ws_bytes, void* stream) {
-  return pcb_bn_backward_seg(dY, lddy, X, ldx, relu_out, ldm, n, n, C, mean, invstd, gamma, dX, lddx, dgamma, dbeta,
-                             accumulate_param_grads, gout, ldg, gout_mode, dXhi, dXlo, lds, ws, ws_bytes, stream);
 }
 
 extern "C" int pcb_bn_backward(const float* dY, const float* X, int64_t n, int C, const float* mean, const float* invstd,

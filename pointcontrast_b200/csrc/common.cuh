@@ -48,6 +48,25 @@ struct ProfScope {
   ~ProfScope() { prof_end(st, kind); }
 };
 
+// Programmatic dependent launch (PCB_PDL=1): every kernel below starts with pdl_wait() -- it blocks until the preceding kernel of
+// the stream has completed and its writes are visible -- followed by pdl_trigger(), which lets the NEXT kernel's CTAs be scheduled
+// as soon as all of this kernel's CTAs are running.  The launch latency and CTA ramp-up of a kernel then overlap the tail of its
+// predecessor; ordering is unchanged (nothing precedes the wait).  Launched without the attribute, both are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();
+
+template <typename... Exp, typename... Act>
+inline void launch_kernel(void (*kernel)(Exp...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Act&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<Act&&>(args)...);       // errors surface through check_launch (cudaGetLastError)
+}
+
 inline int num_sms() {
   static int n = 0;
   if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }

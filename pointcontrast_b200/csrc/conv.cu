@@ -12,6 +12,7 @@
 // same interface covers channel counts the tensor-core tiling does not (Cin = 3) and is the in-library
 // cross-check (PCB_CONV_FORCE_SIMT).
 #include <stdlib.h>
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 using namespace pcb;
@@ -254,6 +255,7 @@ __global__ void __launch_bounds__(NTHR, 2) conv_mma_kernel(const ConvArgs p) {
 // Y[row, c] = bias[c] + sum_z partial[z][row][c]   (fixed order: deterministic)
 __global__ void conv_split_reduce_kernel(const float* __restrict__ partial, int nsplit, int64_t n_out, int Cout,
                                          const float* __restrict__ bias, float* __restrict__ Y, int ldy, int accumulate) {
+  pdl_wait(); pdl_trigger();
   const int cv = Cout / 4;
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n_out * cv) return;
@@ -274,6 +276,7 @@ __global__ void conv_split_reduce_kernel(const float* __restrict__ partial, int 
 __global__ void conv_simt_kernel(const float* __restrict__ X, int ldx, const int32_t* __restrict__ tbl, int64_t tbl_stride,
                                  KMap kmap, int K, int64_t n_out, int Cin, int Cout, const float* __restrict__ W,
                                  const float* __restrict__ bias, float* __restrict__ Y, int ldy) {
+  pdl_wait(); pdl_trigger();
   // one thread per (row, cout); consecutive threads -> consecutive cout (W reads coalesced, X reads broadcast)
   int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (e >= n_out * Cout) return;
@@ -494,6 +497,7 @@ template <int CA>
 __global__ void __launch_bounds__(256) wgrad_stem_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
                                                          const int32_t* __restrict__ tbl, int64_t tbl_stride, int K, int64_t n_out,
                                                          int rows_per_block, float* __restrict__ partial) {
+  pdl_wait(); pdl_trigger();
   __shared__ float s_acc[PCB_MAX_KERNEL_VOLUME * CA * 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int e = threadIdx.x; e < K * CA * 32; e += 256) s_acc[e] = 0.f;
@@ -534,6 +538,7 @@ __global__ void __launch_bounds__(256) wgrad_stem_kernel(const float* __restrict
 }
 
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int64_t n, float* __restrict__ dW, int accumulate) {
+  pdl_wait(); pdl_trigger();
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
   float s = 0.f;
@@ -598,7 +603,7 @@ int launch_conv(ConvArgs a, int nsplit, float* ws, cudaStream_t st) {
   if (int e = check_launch("conv_mma_kernel")) return e;
   if (nsplit > 1) {
     int64_t n4 = a.n_out * (a.Cout / 4);
-    conv_split_reduce_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(ws, nsplit, a.n_out, a.Cout, a.bias, a.Y, a.ldy, 0);
+    launch_kernel(conv_split_reduce_kernel, (unsigned)((n4 + 255) / 256), 256, 0, st, ws, nsplit, a.n_out, a.Cout, a.bias, a.Y, a.ldy, 0);
     return check_launch("conv_split_reduce_kernel");
   }
   return PCB_OK;
@@ -642,11 +647,12 @@ extern "C" int pcb_weight_prep(const float* W, int K, int Cin, int Cout, uint16_
 namespace pcb {
 int launch_wgrad_tcgen05(const uint16_t* Ahi, const uint16_t* Alo, int lda, const uint16_t* Bhi, const uint16_t* Blo, int ldb,
                          const int32_t* tbl, int64_t tbl_stride, int K, int64_t n_out, int Ca, int Cb, int rows_per_split, int splits,
-                         float* partial, int transpose_out, int tn, cudaStream_t st);
+                         float* partial, int transpose_out, int tn, cudaStream_t st, int a_fp16 = 0, int b_fp16 = 0);
 int launch_conv_tcgen05(const float* X, int ldx, const uint16_t* Xhi, const uint16_t* Xlo, int lds, const void* wt, const int32_t* tbl,
                         int64_t tbl_stride, const int* kmap, int K, int64_t n_out,
                         int Cin, int Cout, const uint16_t* wk_hi, const uint16_t* wk_lo, const float* bias, float* Y, int ldy,
-                        float* partial, int nsplit, int bn, int accumulate, cudaStream_t st, float* stats = nullptr, int64_t seg_n0 = 0);
+                        float* partial, int nsplit, int bn, int accumulate, cudaStream_t st, float* stats = nullptr, int64_t seg_n0 = 0,
+                        int x_fp16 = 0, int w_fp16 = 0);
 }
 
 extern "C" size_t pcb_conv_forward_ws_bytes(int K, int64_t n_out, int Cin, int Cout) {
@@ -672,7 +678,7 @@ extern "C" int pcb_conv_forward(const float* X, int ldx, const int32_t* tbl, int
     if (flags & PCB_CONV_ACCUMULATE) { set_error("PCB_CONV_ACCUMULATE needs the tcgen05 path"); return PCB_ERR_ARG; }
     if (!w_f32) { set_error("pcb_conv_forward: SIMT path needs w_f32 (Cin=%d Cout=%d)", Cin, Cout); return PCB_ERR_ARG; }
     int64_t total = n_out * Cout;
-    conv_simt_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(X, ldx, tbl, tbl_stride, km, K, n_out, Cin, Cout,
+    launch_kernel(conv_simt_kernel, (unsigned)((total + 255) / 256), 256, 0, st, X, ldx, tbl, tbl_stride, km, K, n_out, Cin, Cout,
                                                                       w_f32, bias, Y, ldy);
     return check_launch("conv_simt_kernel");
   }
@@ -691,7 +697,7 @@ extern "C" int pcb_conv_forward(const float* X, int ldx, const int32_t* tbl, int
                                     nsplit > 1 ? (float*)ws : nullptr, nsplit, pick_tile(Cout), accumulate, st)) return e;
     if (nsplit > 1) {
       int64_t n4 = n_out * (Cout / 4);
-      conv_split_reduce_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>((const float*)ws, nsplit, n_out, Cout, bias, Y, ldy,
+      launch_kernel(conv_split_reduce_kernel, (unsigned)((n4 + 255) / 256), 256, 0, st, (const float*)ws, nsplit, n_out, Cout, bias, Y, ldy,
                                                                              accumulate);
       return check_launch("conv_split_reduce_kernel");
     }
@@ -735,9 +741,9 @@ extern "C" int pcb_conv_wgrad(const float* A, int lda, const float* B, int ldb, 
     int64_t rpb = (n_out + nb - 1) / nb;
     rpb = (rpb + 7) / 8 * 8;
     nb = (int)((n_out + rpb - 1) / rpb);
-    wgrad_stem_kernel<3><<<nb, 256, 0, st>>>(A, lda, B, ldb, tbl, tbl_stride, K, n_out, (int)rpb, (float*)ws);
+    launch_kernel(wgrad_stem_kernel<3>, nb, 256, 0, st, A, lda, B, ldb, tbl, tbl_stride, K, n_out, (int)rpb, (float*)ws);
     if (int e = check_launch("wgrad_stem_kernel")) return e;
-    wgrad_reduce_kernel<<<(unsigned)((nW + 255) / 256), 256, 0, st>>>((const float*)ws, nb, nW, dW, (flags & PCB_CONV_ACCUMULATE) ? 1 : 0);
+    launch_kernel(wgrad_reduce_kernel, (unsigned)((nW + 255) / 256), 256, 0, st, (const float*)ws, nb, nW, dW, (flags & PCB_CONV_ACCUMULATE) ? 1 : 0);
     return check_launch("wgrad_reduce_kernel");
   }
   int tm = pick_tile(Ca), tn = pick_tile(Cb);
@@ -764,7 +770,7 @@ extern "C" int pcb_conv_wgrad(const float* A, int lda, const float* B, int ldb, 
     WG_CASE(32, 128);  WG_CASE(32, 96);  WG_CASE(32, 64);  WG_CASE(32, 32);
   }
   if (rc) return rc;
-  wgrad_reduce_kernel<<<(unsigned)((nW + 255) / 256), 256, 0, st>>>((const float*)ws, splits, nW, dW,
+  launch_kernel(wgrad_reduce_kernel, (unsigned)((nW + 255) / 256), 256, 0, st, (const float*)ws, splits, nW, dW,
                                                                     (flags & PCB_CONV_ACCUMULATE) ? 1 : 0);
   return check_launch("wgrad_reduce_kernel");
 }
@@ -778,7 +784,8 @@ namespace {
 __host__ __device__ inline int64_t tile_plane_bytes(int bn) { return 4ll * ((bn / 8) * 128 + 16); }
 
 __global__ void weight_tile_kernel(const float* __restrict__ W, int K, int Cin, int Cout, int bn_f, int bn_d,
-                                   unsigned char* __restrict__ fwd, unsigned char* __restrict__ dg) {
+                                   unsigned char* __restrict__ fwd, unsigned char* __restrict__ dg, int fwd_fp16) {
+  pdl_wait(); pdl_trigger();
   int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (e >= (int64_t)K * Cin * Cout) return;
   const float w = W[e];
@@ -793,8 +800,16 @@ __global__ void weight_tile_kernel(const float* __restrict__ W, int K, int Cin, 
     const int64_t blob = ((int64_t)(k * (Cin / 32) + ci / 32) * (Cout / bn_f) + co / bn_f) * 2 * plane;
     const int n = co % bn_f, c = ci % 32;
     const int64_t off = blob + (c / 8) * (plane / 4) + (n / 8) * 128 + (n % 8) * 16 + (c % 8) * 2;
-    *reinterpret_cast<__nv_bfloat16*>(fwd + off) = h;
-    *reinterpret_cast<__nv_bfloat16*>(fwd + off + plane) = l;
+    if (fwd_fp16) {          // fp16 hi/lo of W * 2^10: the lo plane stays in fp16's normal range for every weight that matters
+      const float ws = fminf(fmaxf(w * 1024.0f, -65000.f), 65000.f);
+      const __half fh = __float2half_rn(ws);
+      const __half fl = __float2half_rn(ws - __half2float(fh));
+      *reinterpret_cast<__half*>(fwd + off) = fh;
+      *reinterpret_cast<__half*>(fwd + off + plane) = fl;
+    } else {
+      *reinterpret_cast<__nv_bfloat16*>(fwd + off) = h;
+      *reinterpret_cast<__nv_bfloat16*>(fwd + off + plane) = l;
+    }
   }
   {   // data-gradient roles: N = Cin, contraction = Cout
     const int64_t plane = tile_plane_bytes(bn_d);
@@ -814,11 +829,11 @@ extern "C" size_t pcb_weight_tile_bytes(int K, int Cin, int Cout, int dgrad_role
   return (size_t)K * (Kc / 32) * (N / bn) * 2 * tile_plane_bytes(bn);
 }
 
-extern "C" int pcb_weight_tile(const float* W, int K, int Cin, int Cout, void* fwd_tiles, void* dgrad_tiles, void* stream) {
+extern "C" int pcb_weight_tile(const float* W, int K, int Cin, int Cout, void* fwd_tiles, void* dgrad_tiles, int flags, void* stream) {
   PCB_ARG(W && fwd_tiles && dgrad_tiles && K >= 1 && Cin % 32 == 0 && Cout % 32 == 0 && Cin >= 32 && Cout >= 32);
   int64_t n = (int64_t)K * Cin * Cout;
-  weight_tile_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(W, K, Cin, Cout, pick_tile(Cout), pick_tile(Cin),
-                                                                                   (unsigned char*)fwd_tiles, (unsigned char*)dgrad_tiles);
+  launch_kernel(weight_tile_kernel, (unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream, W, K, Cin, Cout, pick_tile(Cout), pick_tile(Cin),
+                (unsigned char*)fwd_tiles, (unsigned char*)dgrad_tiles, (flags & PCB_PLANES_B_FP16) ? 1 : 0);
   return check_launch("weight_tile_kernel");
 }
 
@@ -844,12 +859,13 @@ int conv_forward_split_impl(const uint16_t* Xhi, const uint16_t* Xlo, int lds, c
   if (nsplit > 1) PCB_ARG(ws && ws_bytes >= (size_t)nsplit * n_out * Cout * sizeof(float));
   if (stats) PCB_ARG(!bias && !accumulate && seg_n0 >= 1 && seg_n0 <= n_out && chunks && chunks0);
   if (int e = launch_conv_tcgen05(nullptr, 0, Xhi, Xlo, lds, w_tiles, tbl, tbl_stride, km, K, n_out, Cin, Cout, nullptr, nullptr, bias, Y, ldy,
-                                  nsplit > 1 ? (float*)ws : nullptr, nsplit, pick_tile(Cout), accumulate, st, stats, seg_n0)) return e;
+                                  nsplit > 1 ? (float*)ws : nullptr, nsplit, pick_tile(Cout), accumulate, st, stats, seg_n0,
+                                  (flags & PCB_PLANES_A_FP16) ? 1 : 0, (flags & PCB_PLANES_B_FP16) ? 1 : 0)) return e;
   if (stats) bn_partial_layout(n_out, seg_n0, nsplit == 1, chunks, chunks0);
   if (nsplit > 1) {
     if (stats) return bn_reduce_stats_launch((const float*)ws, nsplit, Y, ldy, n_out, seg_n0, Cout, stats, st);
     int64_t n4 = n_out * (Cout / 4);
-    conv_split_reduce_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>((const float*)ws, nsplit, n_out, Cout, bias, Y, ldy, accumulate);
+    launch_kernel(conv_split_reduce_kernel, (unsigned)((n4 + 255) / 256), 256, 0, st, (const float*)ws, nsplit, n_out, Cout, bias, Y, ldy, accumulate);
     return check_launch("conv_split_reduce_kernel");
   }
   return PCB_OK;
@@ -902,8 +918,8 @@ extern "C" int pcb_conv_wgrad_split(const uint16_t* Ahi, const uint16_t* Alo, in
   int64_t rps = (n_out + splits - 1) / splits;
   rps = (rps + 15) / 16 * 16;
   if (int e = launch_wgrad_tcgen05(Ahi, Alo, lda, Bhi, Blo, ldb, tbl, tbl_stride, K, n_out, Ca, Cb, (int)rps, splits, (float*)ws,
-                                   transpose_out, pick_tile(Cb), st)) return e;
-  wgrad_reduce_kernel<<<(unsigned)((nW + 255) / 256), 256, 0, st>>>((const float*)ws, splits, nW, dW,
+                                   transpose_out, pick_tile(Cb), st, (flags & PCB_PLANES_A_FP16) ? 1 : 0, (flags & PCB_PLANES_B_FP16) ? 1 : 0)) return e;
+  launch_kernel(wgrad_reduce_kernel, (unsigned)((nW + 255) / 256), 256, 0, st, (const float*)ws, splits, nW, dW,
                                                                     (flags & PCB_CONV_ACCUMULATE) ? 1 : 0);
   return check_launch("wgrad_reduce_kernel");
 }

@@ -110,6 +110,9 @@ struct Args {
   // consumer), stats[prow][2][Cout].  Rows [0, seg_n0) and [seg_n0, n_out) are separate BatchNorm batches: tile t writes
   // prow = t for segment 0 and prow = ceil(seg_n0/128) + t - floor(seg_n0/128) for segment 1 (bn_partial_layout in bn.cu).
   float* stats; int64_t seg_n0;
+  // operand formats of the tcgen05.mma instruction descriptor (bits 7-9: A = gathered rows, bits 10-12: B = weights; 0 fp16, 1 bf16)
+  // and the factor applied to the accumulators on the way out (2^-10 when the weight tiles hold fp16(W * 2^10))
+  uint32_t fmt_bits; float out_scale;
   int debug;            // timing experiments only (PCB_TC5_DEBUG): 1 skip A copies, 2 skip B copies, 4 skip MMAs, 8 skip proxy fence
 };
 
@@ -378,6 +381,7 @@ __global__ void __launch_bounds__(DPROD + 32, CTAS) conv_tcgen05_split_kernel(co
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(s_tmem)), "r"(S::TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
   }
+  pdl_wait(); pdl_trigger();        // barriers + TMEM are set up while the preceding kernel drains; no global memory touched before this
   for (int e = tid; e < p.K * BM; e += DTHR) {
     int k = e / BM, r = e - k * BM;
     int64_t row = row0 + r;
@@ -408,7 +412,7 @@ __global__ void __launch_bounds__(DPROD + 32, CTAS) conv_tcgen05_split_kernel(co
   const int it0 = (int)((int64_t)T * blockIdx.z / gridDim.z);
   const int it1 = (int)((int64_t)T * (blockIdx.z + 1) / gridDim.z);
   const int n_it = (p.debug & 16) ? 0 : it1 - it0;
-  constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  const uint32_t IDESC = (1u << 4) | p.fmt_bits | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
   if (warp < DPROD / 32) {
     // ===== producers.  Thread t always owns the same two 16-byte chunks of the A tile (row t>>2, chunk t&3, hi + lo
@@ -541,6 +545,10 @@ __global__ void __launch_bounds__(DPROD + 32, CTAS) conv_tcgen05_split_kernel(co
 #pragma unroll
         for (int e = 0; e < 16; ++e) r[e] = 0u;
       }
+      if (p.out_scale != 1.0f) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) * p.out_scale);
+      }
       if (do_stats) {
         float v1[16], v2[16];
         const bool in0 = !straddle || row < sn0;
@@ -598,7 +606,7 @@ int launch_split_cfg(const Args& a, int nsplit, cudaStream_t st) {
     attr_set = true;
   }
   dim3 grid((unsigned)((a.n_out + BM - 1) / BM), a.Cout / BN, nsplit);
-  conv_tcgen05_split_kernel<BN, DNS, DPROD, CTAS><<<grid, DPROD + 32, S::TOTAL, st>>>(a);
+  launch_kernel(conv_tcgen05_split_kernel<BN, DNS, DPROD, CTAS>, grid, DPROD + 32, S::TOTAL, st, a);
   return check_launch("conv_tcgen05_split_kernel");
 }
 
@@ -635,9 +643,12 @@ int launch(const Args& a, int nsplit, cudaStream_t st) {
 int launch_conv_tcgen05(const float* X, int ldx, const uint16_t* Xhi, const uint16_t* Xlo, int lds, const void* wt, const int32_t* tbl,
                         int64_t tbl_stride, const int* kmap, int K, int64_t n_out,
                         int Cin, int Cout, const uint16_t* wk_hi, const uint16_t* wk_lo, const float* bias, float* Y, int ldy,
-                        float* partial, int nsplit, int bn, int accumulate, cudaStream_t st, float* stats, int64_t seg_n0) {
+                        float* partial, int nsplit, int bn, int accumulate, cudaStream_t st, float* stats, int64_t seg_n0, int x_fp16,
+                        int w_fp16) {
   tc5::Args a;
   a.accumulate = accumulate;
+  a.fmt_bits = ((x_fp16 ? 0u : 1u) << 7) | ((w_fp16 ? 0u : 1u) << 10);
+  a.out_scale = w_fp16 ? 1.0f / 1024.0f : 1.0f;
   a.stats = (Xhi && !partial) ? stats : nullptr; a.seg_n0 = seg_n0;
   static int dbg = -1;
   if (dbg < 0) { const char* e = getenv("PCB_TC5_DEBUG"); dbg = e ? atoi(e) : 0; }
@@ -677,6 +688,7 @@ struct Args {
   int K; int64_t n_out; int Ca; int Cb; int rows_per_split;
   float* partial; int transpose_out;
   int ns;               // ring depth (host-chosen to fill shared memory)
+  uint32_t fmt_bits;    // instruction-descriptor formats: bits 7-9 gathered operand, bits 10-12 row-aligned operand (0 fp16, 1 bf16)
 };
 
 // channel-chunk (core-matrix) stride 144 B, not 128: a producer warp writes the 16 chunks of ONE row, and a 128-byte stride
@@ -722,14 +734,14 @@ __global__ void __launch_bounds__(NTHR, 1) wgrad_tcgen05_kernel(const Args p) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(s_tmem)), "r"(TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
   }
+  pdl_wait(); pdl_trigger();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_acc = *s_tmem;
   // MN-major A and B (bits 15, 16), bf16 inputs, fp32 accumulate, M = 128, N = TN.  The A descriptor spans 16 channel
   // chunks although only `ach` are staged: rows >= mrows of D are garbage and never read back.
-  constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(TN >> 3) << 17) |
-                             ((uint32_t)(WM >> 4) << 24);
+  const uint32_t IDESC = (1u << 4) | p.fmt_bits | (1u << 15) | (1u << 16) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(WM >> 4) << 24);
 
   if (warp < WPROD / 32) {
     constexpr int PF = 2;
@@ -878,7 +890,7 @@ int launch(Args a, int splits, cudaStream_t st) {
   const int groups = (a.K + GK - 1) / GK;
   dim3 grid((unsigned)(groups * ((a.Ca + WM - 1) / WM) * (a.Cb / TN)), splits);
   // + 4 KB: the M = 128 descriptor of a 96-channel block reads (and ignores) a few hundred bytes past the last staged chunk
-  wgrad_tcgen05_kernel<TN><<<grid, NTHR, ns * stage + (2 * ns + 1) * 8 + 64 + 4096, st>>>(a);
+  launch_kernel(wgrad_tcgen05_kernel<TN>, grid, NTHR, (size_t)(ns * stage + (2 * ns + 1) * 8 + 64 + 4096), st, a);
   return check_launch("wgrad_tcgen05_kernel");
 }
 
@@ -886,8 +898,9 @@ int launch(Args a, int splits, cudaStream_t st) {
 
 int launch_wgrad_tcgen05(const uint16_t* Ahi, const uint16_t* Alo, int lda, const uint16_t* Bhi, const uint16_t* Blo, int ldb,
                          const int32_t* tbl, int64_t tbl_stride, int K, int64_t n_out, int Ca, int Cb, int rows_per_split, int splits,
-                         float* partial, int transpose_out, int tn, cudaStream_t st) {
+                         float* partial, int transpose_out, int tn, cudaStream_t st, int a_fp16, int b_fp16) {
   wg::Args a;
+  a.fmt_bits = ((a_fp16 ? 0u : 1u) << 7) | ((b_fp16 ? 0u : 1u) << 10);
   a.Ahi = (const __nv_bfloat16*)Ahi; a.Alo = (const __nv_bfloat16*)Alo; a.lda = lda;
   a.Bhi = (const __nv_bfloat16*)Bhi; a.Blo = (const __nv_bfloat16*)Blo; a.ldb = ldb;
   a.tbl = tbl; a.tbl_stride = tbl_stride; a.K = K; a.n_out = n_out; a.Ca = Ca; a.Cb = Cb; a.rows_per_split = rows_per_split;

@@ -151,6 +151,7 @@ __global__ void pdist_unpack_kernel(const unsigned long long* __restrict__ packe
 
 __global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf, int64_t n, float lr,
                            float momentum, float wd, float gscale, int first) {
+  pdl_wait(); pdl_trigger();
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   int64_t n4 = n >> 2;
   if (i < n4) {
@@ -228,7 +229,7 @@ extern "C" int pcb_sgd_step(float* p, const float* g, float* buf, int64_t n, flo
   if (n == 0) return PCB_OK;
   PCB_ARG(p && g && buf);
   int64_t threads = (n >> 2) + (n & 3);
-  sgd_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p, g, buf, n, lr, momentum, weight_decay,
+  launch_kernel(sgd_kernel, (unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream, p, g, buf, n, lr, momentum, weight_decay,
                                                                                    grad_scale, first);
   return check_launch("sgd_kernel");
 }

@@ -22,6 +22,7 @@ int bn_backward_impl(const float* dY, int lddy, const float* X, int ldx, const f
 using namespace pcb;
 
 // ------------------------------------------------------------------------------------------------ per-launch timing
+#include <stdlib.h>
 #include <vector>
 namespace {
 struct ProfRec { cudaEvent_t e0, e1; int kind; };
@@ -37,6 +38,11 @@ cudaEvent_t prof_event() {
 }
 }  // namespace
 namespace pcb {
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("PCB_PDL"); on = (e && atoi(e) != 0) ? 1 : 0; }
+  return on == 1;
+}
 void prof_begin(cudaStream_t st) {
   if (!g_prof_on) return;
   g_prof_open = prof_event();
@@ -104,12 +110,14 @@ extern "C" int pcb_unit_forward(const pcb_unit* u, void* stream) {
   unsigned char* bn_ws = (unsigned char*)u->ws + conv_bytes;
   const size_t bn_bytes = u->ws_bytes - conv_bytes;
   bool have_stats = false;
+  const bool f16 = (u->flags & PCB_UNIT_FP16_FORWARD) != 0;      // activations (x, out planes) and forward weight tiles are fp16 hi/lo
   if (tensor_core_shape(u->Cin, u->Cout)) {
     PCB_ARG(u->x_hi && u->x_lo && u->wt_fwd);
     float* stats = (u->flags & PCB_UNIT_SEPARATE_STATS) ? nullptr : (float*)bn_ws;
     int chunks = 0, chunks0 = 0;
     if (int e = conv_forward_split_impl(u->x_hi, u->x_lo, u->x_lds, u->fwd_tbl, u->fwd_stride, u->fwd_kmap, u->K, u->n_out, u->Cin, u->Cout,
-                                        u->wt_fwd, nullptr, u->z_p, u->z_ld, u->ws, conv_bytes, 0, st, stats, u->n0, &chunks, &chunks0)) return e;
+                                        u->wt_fwd, nullptr, u->z_p, u->z_ld, u->ws, conv_bytes, f16 ? (PCB_PLANES_A_FP16 | PCB_PLANES_B_FP16) : 0,
+                                        st, stats, u->n0, &chunks, &chunks0)) return e;
     if (stats) {
       if (int e = bn_finalize_launch(stats, chunks, chunks0, u->n_out, u->n0, u->Cout, u->eps, u->momentum, u->mean, u->invstd,
                                      u->running_mean, u->running_var, st)) return e;
@@ -124,8 +132,8 @@ extern "C" int pcb_unit_forward(const pcb_unit* u, void* stream) {
     if (int e = pcb_bn_stats_seg(u->z_p, u->z_ld, u->n_out, u->n0, u->Cout, u->eps, u->momentum, u->mean, u->invstd, u->running_mean,
                                  u->running_var, bn_ws, bn_bytes, stream)) return e;
   }
-  return pcb_bn_apply_seg(u->z_p, u->z_ld, u->n_out, u->n0, u->Cout, u->mean, u->invstd, u->gamma, u->beta, u->res_p, u->res_ld, u->relu,
-                          u->out_p, u->out_ld, u->out_hi, u->out_lo, u->out_lds, stream);
+  return pcb_bn_apply_seg(u->z_p, u->z_ld, u->n_out, u->n0, u->Cout, u->mean, u->invstd, u->gamma, u->beta, u->res_p, u->res_ld,
+                          (u->relu ? PCB_BN_RELU : 0) | (f16 ? PCB_PLANES_A_FP16 : 0), u->out_p, u->out_ld, u->out_hi, u->out_lo, u->out_lds, stream);
 }
 
 extern "C" int pcb_unit_backward(const pcb_unit* u, void* stream) {
@@ -133,6 +141,7 @@ extern "C" int pcb_unit_backward(const pcb_unit* u, void* stream) {
   PCB_ARG(u->g_p && u->z_p && u->mean && u->invstd && u->gamma && u->dgamma && u->dbeta && u->dW && u->wg_tbl && u->ws);
   PCB_ARG(u->ws_bytes >= pcb_unit_ws_bytes(u->K, u->n_in, u->n_out, u->Cin, u->Cout));
   const bool tc = tensor_core_shape(u->Cin, u->Cout);
+  const bool f16 = (u->flags & PCB_UNIT_FP16_FORWARD) != 0;
   PCB_ARG(tc ? (u->dz_hi && u->dz_lo && u->x_hi && u->x_lo) : (u->dz_p && u->x_p));
   PCB_ARG(tc || u->gin_mode == 0);               // only the 3-channel stem is not tensor-core shaped: its input wants no gradient
   cudaStream_t st = (cudaStream_t)stream;
@@ -147,8 +156,10 @@ extern "C" int pcb_unit_backward(const pcb_unit* u, void* stream) {
     const uint16_t *Ahi, *Alo, *Bhi, *Blo; int lda, ldb, Ca, Cb, tr; int64_t rows;
     if (u->wg_gather_x) { Ahi = u->x_hi; Alo = u->x_lo; lda = u->x_lds; Bhi = u->dz_hi; Blo = u->dz_lo; ldb = u->dz_ld; Ca = u->Cin; Cb = u->Cout; tr = 0; rows = u->n_out; }
     else { Ahi = u->dz_hi; Alo = u->dz_lo; lda = u->dz_ld; Bhi = u->x_hi; Blo = u->x_lo; ldb = u->x_lds; Ca = u->Cout; Cb = u->Cin; tr = 1; rows = u->n_in; }
+    // the activation operand (x) is fp16 hi/lo when the forward pass ran on fp16 planes; the gradient operand (dz) is always bf16 hi/lo
+    const int fmt = !f16 ? 0 : (u->wg_gather_x ? PCB_PLANES_A_FP16 : PCB_PLANES_B_FP16);
     if (int e = pcb_conv_wgrad_split(Ahi, Alo, lda, Bhi, Blo, ldb, u->wg_tbl, u->wg_stride, u->K, rows, Ca, Cb, u->dW, tr, u->ws, conv_bytes,
-                                     PCB_CONV_ACCUMULATE, stream)) return e;
+                                     PCB_CONV_ACCUMULATE | fmt, stream)) return e;
   } else {
     PCB_ARG(u->wg_gather_x);
     if (int e = pcb_conv_wgrad(u->x_p, u->x_ld, u->dz_p, u->dz_ld, u->wg_tbl, u->wg_stride, u->K, u->n_out, u->Cin, u->Cout, u->dW, 0, u->ws,

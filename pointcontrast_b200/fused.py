@@ -251,6 +251,8 @@ class Runner:
         if Cin % 32 == 0 and Cout % 32 == 0:
             wt = conv._prepared.tiles(kern)[1 if transposed_roles else 0]          # pre-tiled split weights for these roles
             flags = 4 if accumulate else 0
+            if me.FWD_FP16 and not transposed_roles:          # forward roles: fp16 activation planes x fp16 weight tiles
+                flags |= me.PLANES_A_FP16 | me.PLANES_B_FP16
             wsb = lib.pcb_conv_forward_ws_bytes(K, n_out, Cin, Cout)
             ws = me.workspace(wsb, self.device, slot=2)
             assert x.hi, "tensor-core conv needs the split planes of its input"
@@ -279,8 +281,9 @@ class Runner:
         if tc:
             wsb = lib.pcb_conv_wgrad_split_ws_bytes(K, rows, Ca, Cb)
             ws = me.workspace(wsb, self.device, slot=0)
+            fmt = 0 if not me.FWD_FP16 else (me.PLANES_A_FP16 if plan.wg_gather_x else me.PLANES_B_FP16)      # the activation operand
             check(lib.pcb_conv_wgrad_split(A.hi, A.lo, A.ld, B.hi, B.lo, B.ld, ptr(plan.wg_tbl), plan.wg_tbl.shape[1], K, rows, Ca, Cb,
-                                           kern.grad.data_ptr(), tr, ptr(ws), wsb, 4, stream()))
+                                           kern.grad.data_ptr(), tr, ptr(ws), wsb, 4 | fmt, stream()))
         else:
             wsb = lib.pcb_conv_wgrad_ws_bytes(K, rows, Ca, Cb)
             ws = me.workspace(wsb, self.device, slot=0)
@@ -329,7 +332,7 @@ class Runner:
             assert residual.p, "a residual input needs its fp32 plane"
             u.res_p, u.res_ld = residual.p, residual.ld
         u.ws, u.ws_bytes = self.ws.data_ptr(), self.ws.numel()
-        u.flags = 1 if SEPARATE_STATS else 0
+        u.flags = (1 if SEPARATE_STATS else 0) | (2 if me.FWD_FP16 else 0)
         if me.PROFILE is not None:
             me.PROFILE.append(dict(kind="fwd", K=K, Cin=Cin, Cout=Cout, n_in=plan.n_in, n_out=plan.n_out, plan=plan, tc=tc))
         check(lib.pcb_unit_forward(ctypes.byref(u), self.st))
@@ -459,7 +462,7 @@ class Runner:
             fin = m.final
             if fin.out_channels % 32 == 0:
                 dfin = Buf.new(arena, d_out.shape[0], d_out.shape[1], fp32=False, split=True)
-                check(lib.pcb_split_rows(d_out.data_ptr(), d_out.shape[1], d_out.shape[0], d_out.shape[1], dfin.hi, dfin.lo, dfin.ld, st))
+                check(lib.pcb_split_rows(d_out.data_ptr(), d_out.shape[1], d_out.shape[0], d_out.shape[1], dfin.hi, dfin.lo, dfin.ld, 0, st))
             else:                                # e.g. 13 / 20 classes: the final layer's backward runs on the exact fp32 kernels
                 dfin = Buf(d_out, d_out.data_ptr(), d_out.shape[0], d_out.shape[1], d_out.shape[1], dev)
             if fin.bias is not None:

@@ -387,6 +387,10 @@ CONV_IMPL = _os.environ.get("PCB_CONV_IMPL", "tcgen05")     # "mma" (mma.sync) |
 # bench.py sets this to a list: every convolution / weight-gradient entry-point call then appends its description here, in
 # issue order -- the same order in which the library (pcb_profile_enable) brackets those calls with CUDA events.
 PROFILE = None
+# Fused executor: activations travel as fp16 hi/lo planes and the forward weight tiles are fp16 (22 mantissa bits per operand instead of
+# bf16 hi/lo's 16): the forward pass is what sets the whole-network gradient error (profiles/r2_results.md).  0: bf16 everywhere.
+FWD_FP16 = _os.environ.get("PCB_FWD_FP16", "1") == "1"
+PLANES_A_FP16, PLANES_B_FP16 = 8, 16
 
 
 def _prof_begin():
@@ -418,12 +422,12 @@ class _PreparedWeights:
 
     def tiles(self, kernel):
         """(forward, data-gradient) weights pre-tiled as shared-memory images for the split tcgen05 kernel (TMA bulk loads)."""
-        tag = (kernel.data_ptr(), kernel._version, tuple(kernel.shape), _WEIGHTS_EPOCH[0])
+        tag = (kernel.data_ptr(), kernel._version, tuple(kernel.shape), _WEIGHTS_EPOCH[0], FWD_FP16)
         if tag != self.tile_tag:
             K, Cin, Cout = kernel.shape
             f = torch.empty(lib.pcb_weight_tile_bytes(K, Cin, Cout, 0), dtype=torch.uint8, device=kernel.device)
             d = torch.empty(lib.pcb_weight_tile_bytes(K, Cin, Cout, 1), dtype=torch.uint8, device=kernel.device)
-            check(lib.pcb_weight_tile(ptr(kernel.detach()), K, Cin, Cout, ptr(f), ptr(d), stream()))
+            check(lib.pcb_weight_tile(ptr(kernel.detach()), K, Cin, Cout, ptr(f), ptr(d), PLANES_B_FP16 if FWD_FP16 else 0, stream()))
             self._tiles, self.tile_tag = (f, d), tag
         return self._tiles
 

@@ -54,12 +54,13 @@ def main():
     out = {"rows": [len(batch["sinput0_C"]), len(batch["sinput1_C"])], "fp32_cpu_floor": {"median": float(np.median(floor)), "max": float(floor.max())},
            "variants": {}}
 
-    def run(tag, simt_ops, aten_bn=False, use_fused=False):
+    def run(tag, simt_ops, aten_bn=False, use_fused=False, fp16=False):
         net = load_model("Res16UNet34C")(3, 32, cfg, D=3)
         net.load_state_dict(state)
         net = net.cuda().train()
         me.SIMT_OPS = set(simt_ops)
         fused.ENABLED = use_fused
+        saved_fmt, me.FWD_FP16 = me.FWD_FP16, fp16
         old_fwd = me.MinkowskiBatchNorm.forward
         if aten_bn:
             def fwd(self, inp):
@@ -69,7 +70,7 @@ def main():
             F = [net(me.SparseTensor(torch.from_numpy(batch[f"sinput{v}_F"]), coords=torch.from_numpy(batch[f"sinput{v}_C"])).to("cuda")).F for v in "01"]
             losses.point_nce_loss(F[0], F[1], q.cuda(), k.cuda(), 0.4).backward()
         finally:
-            me.SIMT_OPS = set(); fused.ENABLED = True; me.MinkowskiBatchNorm.forward = old_fwd
+            me.SIMT_OPS = set(); fused.ENABLED = True; me.MinkowskiBatchNorm.forward = old_fwd; me.FWD_FP16 = saved_fmt
         err = np.array([rel_err(p.grad, g) for p, g in zip(net.parameters(), g64)])
         ferr = max(float((F[i].detach().double().cpu() - F64[i]).abs().max() / F64[i].pow(2).mean().sqrt()) for i in range(2))
         w = int(np.argmax(err))
@@ -77,7 +78,8 @@ def main():
         print(tag, out["variants"][tag], file=sys.stderr, flush=True)
 
     run("tensor-core fwd+dgrad+wgrad (modular)", [])
-    run("fused executor (tensor-core, stacked off)", [], use_fused=True)
+    run("fused executor, bf16 hi/lo planes everywhere", [], use_fused=True)
+    run("fused executor, fp16 hi/lo activations + forward weights (default)", [], use_fused=True, fp16=True)
     run("exact fwd", ["fwd"])
     run("exact dgrad", ["dgrad"])
     run("exact wgrad", ["wgrad"])

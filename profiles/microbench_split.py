@@ -11,10 +11,10 @@ from pointcontrast_b200 import me, synth  # noqa: E402
 from pointcontrast_b200._lib import check, lib, ptr, stream  # noqa: E402
 
 
-def split(x):
+def split(x, flags=0):
     n, C = x.shape
     planes = torch.empty(2, n * C, dtype=torch.bfloat16, device="cuda")
-    check(lib.pcb_split_rows(ptr(x), C, n, C, planes[0].data_ptr(), planes[1].data_ptr(), C, stream()))
+    check(lib.pcb_split_rows(ptr(x), C, n, C, planes[0].data_ptr(), planes[1].data_ptr(), C, flags, stream()))
     return planes
 
 
@@ -64,7 +64,7 @@ def main():
             Xs, dYs = split(X), split(dY)
             ft = torch.empty(lib.pcb_weight_tile_bytes(27, cin, cout, 0), dtype=torch.uint8, device="cuda")
             dt = torch.empty(lib.pcb_weight_tile_bytes(27, cin, cout, 1), dtype=torch.uint8, device="cuda")
-            check(lib.pcb_weight_tile(ptr(W), 27, cin, cout, ptr(ft), ptr(dt), stream()))
+            check(lib.pcb_weight_tile(ptr(W), 27, cin, cout, ptr(ft), ptr(dt), 0, stream()))
             Y = torch.empty(n, cout, device="cuda"); dW = torch.empty(27, cin, cout, device="cuda")
             wsb = max(256, lib.pcb_conv_forward_ws_bytes(27, n, cin, cout)); ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
             wsb2 = lib.pcb_conv_wgrad_split_ws_bytes(27, n, cin, cout); ws2 = torch.empty(wsb2, dtype=torch.uint8, device="cuda")

@@ -29,11 +29,11 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-3
 
 
-def _split(x):
+def _split(x, flags=0):
     from pointcontrast_b200._lib import check, lib, ptr, stream
     n, C = x.shape
     planes = torch.empty(2, n * C, dtype=torch.bfloat16, device="cuda")
-    check(lib.pcb_split_rows(ptr(x), C, n, C, planes[0].data_ptr(), planes[1].data_ptr(), C, stream()))
+    check(lib.pcb_split_rows(ptr(x), C, n, C, planes[0].data_ptr(), planes[1].data_ptr(), C, flags, stream()))
     return planes
 
 
@@ -68,7 +68,7 @@ def test_direct_epilogue_conv_at_c1_rows(cin, cout):
     Wd = W.cuda()
     ft = torch.empty(lib.pcb_weight_tile_bytes(27, cin, cout, 0), dtype=torch.uint8, device="cuda")
     dt = torch.empty(lib.pcb_weight_tile_bytes(27, cin, cout, 1), dtype=torch.uint8, device="cuda")
-    check(lib.pcb_weight_tile(ptr(Wd), 27, cin, cout, ptr(ft), ptr(dt), stream()))
+    check(lib.pcb_weight_tile(ptr(Wd), 27, cin, cout, ptr(ft), ptr(dt), 0, stream()))
     ws = torch.empty(256, dtype=torch.uint8, device="cuda")
     X = x.float().cuda(); DY = dy.float().cuda()
     Xs, DYs = _split(X), _split(DY)
@@ -96,6 +96,22 @@ def test_direct_epilogue_conv_at_c1_rows(cin, cout):
                                    plan.wg_tbl.shape[1], 27, n, cin, cout, ptr(dW), 0, ptr(wws), wsb, 4, stream()))
     torch.cuda.synchronize()
     assert max_rel_err(dW - 0.125, oconv.kernel.grad) < TOL and rel_err(dW - 0.125, oconv.kernel.grad) < TOL / 10
+    # fp16 hi/lo activation planes x fp16 weight tiles (the fused executor's forward format, PCB_FWD_FP16): 2^-22 products
+    ft16 = torch.empty_like(ft); dt16 = torch.empty_like(dt)
+    check(lib.pcb_weight_tile(ptr(Wd), 27, cin, cout, ptr(ft16), ptr(dt16), 16, stream()))
+    assert torch.equal(dt16, dt)                                   # the data-gradient tiles stay bf16
+    Xs16 = _split(X, 8)
+    y16 = torch.empty(n, cout, device="cuda")
+    check(lib.pcb_conv_forward_split(Xs16[0].data_ptr(), Xs16[1].data_ptr(), cin, ptr(tbl), tbl.shape[1], None, 27, n, cin, cout, ptr(ft16),
+                                     ptr(bias.cuda()), ptr(y16), cout, ptr(ws), 256, 8 | 16, stream()))
+    e_bf16, e_fp16 = rel_err(y, yo), rel_err(y16, yo)
+    assert e_fp16 < 0.2 * e_bf16 and max_rel_err(y16, yo) < 1e-5, (e_bf16, e_fp16)
+    # weight gradient with MIXED operand formats: gathered activations fp16 hi/lo, row-aligned gradients bf16 hi/lo
+    dW16 = torch.zeros((27, cin, cout), device="cuda")
+    check(lib.pcb_conv_wgrad_split(Xs16[0].data_ptr(), Xs16[1].data_ptr(), cin, DYs[0].data_ptr(), DYs[1].data_ptr(), cout, ptr(plan.wg_tbl),
+                                   plan.wg_tbl.shape[1], 27, n, cin, cout, ptr(dW16), 0, ptr(wws), wsb, 4 | 8, stream()))
+    torch.cuda.synchronize()
+    assert max_rel_err(dW16, oconv.kernel.grad) < TOL and rel_err(dW16, oconv.kernel.grad) <= rel_err(dW - 0.125, oconv.kernel.grad) * 1.05
 
 
 # ----------------------------------------------------------------------------------------------- one full C1 pair

@@ -155,6 +155,8 @@ def test_fused_executor_matches_modular_path():
     q, k = loss_cpu.select_positives(pairs, rng.random(nq).astype(np.float32), 4096,
                                      rng.choice(nq, 4096, replace=False) if nq > 4096 else None)
     out = {}
+    saved_fmt = me.FWD_FP16
+    me.FWD_FP16 = False          # same operand format on both sides (the modular kernels split to bf16 hi/lo): this test is about the wiring
     for mode in (True, False):
         fused.ENABLED = mode
         try:
@@ -167,6 +169,8 @@ def test_fused_executor_matches_modular_path():
                          {n: b.clone() for n, b in net.named_buffers()})
         finally:
             fused.ENABLED = True
+            if not mode:
+                me.FWD_FP16 = saved_fmt
     a, b = out[True], out[False]
     assert max_rel_err(a[0], b[0]) < 1e-5 and max_rel_err(a[1], b[1]) < 1e-5 and abs(a[2] - b[2]) < 1e-5 * abs(b[2])
     worst = max((rel_err(a[3][n], b[3][n]), n) for n in b[3])

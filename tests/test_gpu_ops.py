@@ -245,11 +245,11 @@ def test_sgd_matches_torch():
     assert sd["param_groups"][0]["momentum"] == 0.8 and len(sd["state"]) == len(shapes)
 
 
-def _split(x):
+def _split(x, flags=0):
     from pointcontrast_b200._lib import check, lib, ptr, stream
     n, C = x.shape
     planes = torch.empty(2, n * C, dtype=torch.bfloat16, device="cuda")
-    check(lib.pcb_split_rows(ptr(x), C, n, C, planes[0].data_ptr(), planes[1].data_ptr(), C, stream()))
+    check(lib.pcb_split_rows(ptr(x), C, n, C, planes[0].data_ptr(), planes[1].data_ptr(), C, flags, stream()))
     return planes
 
 
@@ -305,7 +305,7 @@ def test_split_operand_conv_forward_matches_fp32_input_kernel(cin, cout):
     wsb = lib.pcb_conv_forward_ws_bytes(27, n, cin, cout); ws = torch.empty(max(wsb, 256), dtype=torch.uint8, device="cuda")
     ft = torch.empty(lib.pcb_weight_tile_bytes(27, cin, cout, 0), dtype=torch.uint8, device="cuda")
     dt = torch.empty(lib.pcb_weight_tile_bytes(27, cin, cout, 1), dtype=torch.uint8, device="cuda")
-    check(lib.pcb_weight_tile(ptr(W), 27, cin, cout, ptr(ft), ptr(dt), stream()))
+    check(lib.pcb_weight_tile(ptr(W), 27, cin, cout, ptr(ft), ptr(dt), 0, stream()))
     check(lib.pcb_conv_forward_split(Xs[0].data_ptr(), Xs[1].data_ptr(), cin, ptr(plan.fwd_tbl), plan.fwd_tbl.shape[1], None, 27, n, cin,
                                      cout, ptr(ft), None, ptr(got), cout, ptr(ws), wsb, 4, stream()))
     torch.cuda.synchronize()
