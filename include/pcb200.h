@@ -184,8 +184,8 @@ int pcb_split_rows(const float* X, int ldx, int64_t n, int C, uint16_t* hi, uint
 /* ----------------------------------------------------------------------------------------------- fused units */
 /* One "unit" of the Res16UNet graph = convolution -> BatchNorm (training statistics) -> [+ residual] -> [ReLU]
  * (`model/res16unet.py:206-268`, `model/modules/resnet_block.py:44-60`: a BasicBlock is two units).  pcb_unit_forward issues the whole
- * unit from ONE call -- the BatchNorm column sums come out of the convolution's epilogue (TMEM -> registers -> per-tile partial
- * sums) or out of the offset-split reduction pass, so the pre-normalisation tensor z is written once and read once --
+ * unit from ONE call -- on the small levels, where the convolution runs offset-split, its reduction pass also produces the BatchNorm
+ * column statistics (no separate pass over z) --
  * and pcb_unit_backward issues its reverse: ReLU mask + BatchNorm backward + residual-gradient fan-out in one elementwise
  * pass, then the weight gradient (accumulated into dW) and the data gradient (written or accumulated into gin).
  * The caller (pointcontrast_b200/fused.py; a C++ host would do the same) owns every buffer; the struct is plain data.
@@ -222,7 +222,7 @@ typedef struct pcb_unit {
   void* ws; size_t ws_bytes;
   int32_t flags;                                    /* PCB_UNIT_* */
 } pcb_unit;
-#define PCB_UNIT_SEPARATE_STATS 1   /* forward: BatchNorm statistics by a separate pass over z (cross-check of the fused epilogue) */
+#define PCB_UNIT_SEPARATE_STATS 1   /* forward: BatchNorm statistics always by a separate pass over z (cross-check of the fused reduce+statistics pass) */
 #define PCB_UNIT_FP16_FORWARD 2     /* activations travel as fp16 hi/lo planes (x_hi/x_lo, out_hi/out_lo) and wt_fwd holds fp16 tiles
                                        (pcb_weight_tile with PCB_PLANES_B_FP16): 2^-22 products in the forward pass; gradients
                                        (dz) and the data-gradient tiles stay bf16 hi/lo (fp32's exponent range) */

@@ -9,7 +9,6 @@ using namespace pcb;
 
 namespace {
 
-constexpr int ROWS_PER_CHUNK = 128;
 
 // fp32 x4 -> fp16 hi x4 + fp16 lo x4 (x ~= hi + lo to 2^-22 |x|, absolute floor 2^-25: fp16 subnormals): the operand format of the
 // FORWARD convolutions.  Activations are O(1) after BatchNorm; |x| is clamped to the fp16 range (65504) so that hi stays finite.
@@ -67,11 +66,20 @@ __device__ __forceinline__ void mask4_bf16(const __nv_bfloat16* m, float4& a) {
   a.z = pos(b.y & 0xFFFFu) ? a.z : 0.f; a.w = pos(b.y >> 16) ? a.w : 0.f;
 }
 
-template <bool TWO_INPUTS>
-__global__ void colsum_kernel(const float* __restrict__ A, int lda, const float* __restrict__ Bm, int ldb,
-                              const float* __restrict__ Mask, int ldm, const __nv_bfloat16* __restrict__ MaskH, int ldmh,
-                              int64_t n, int64_t n0, int chunks0, int C,
-                              const float* __restrict__ mean, const float* __restrict__ invstd, float* __restrict__ partial) {
+// ---- column reductions.  A CTA owns one CHUNK of R rows (R = chunk_rows(n): a power of two chosen so that a launch has a few
+// hundred CTAs whatever the level size; chunks never straddle the view boundary n0: CTAs [0, chunks0) cover segment 0, the rest
+// segment 1); block = (C/4) channel-vectors x RP row lanes, row loop unrolled for memory-level parallelism; one partial row
+// [2][C] per chunk, combined in fp64 by the finalize kernels (fixed order: deterministic).
+//   MODE 0  forward statistics of A:            partial = { sum(x), M2 = sum((x - chunk mean)^2) }, accumulated around a pivot
+//           (the chunk's first row) so that |mean| >> std does not cancel; the finalize kernel merges chunks with Chan's formula
+//   MODE 2  the same on A = sum_z P[z] (offset-split convolution partial planes), which is also written to Y
+//   MODE 1  backward sums: a = dY (ReLU-masked), partial = { sum(a), sum(a * xhat) }
+template <int MODE>
+__global__ void __launch_bounds__(256) colstat_kernel(const float* __restrict__ A, int lda, const float* __restrict__ Bm, int ldb,
+                                                      const __nv_bfloat16* __restrict__ MaskH, int ldmh, const float* __restrict__ MaskF,
+                                                      int ldmf, int nsplit, float* __restrict__ Y, int ldy, int64_t n, int64_t n0,
+                                                      int chunks0, int R, int C, const float* __restrict__ mean,
+                                                      const float* __restrict__ invstd, float* __restrict__ partial) {
   pdl_wait(); pdl_trigger();
   extern __shared__ float sm[];      // [RP][2][C]
   const int cv = C / 4;
@@ -79,30 +87,46 @@ __global__ void colsum_kernel(const float* __restrict__ A, int lda, const float*
   const int c4 = threadIdx.x % cv;
   const int rl = threadIdx.x / cv;
   const int seg = (int)blockIdx.x >= chunks0 ? 1 : 0;
-  const int64_t r0 = seg ? n0 + (int64_t)((int)blockIdx.x - chunks0) * ROWS_PER_CHUNK : (int64_t)blockIdx.x * ROWS_PER_CHUNK;
-  const int64_t r1 = min(seg ? n : n0, r0 + ROWS_PER_CHUNK);
+  const int64_t r0 = seg ? n0 + (int64_t)((int)blockIdx.x - chunks0) * R : (int64_t)blockIdx.x * R;
+  const int64_t r1 = min(seg ? n : n0, r0 + R);
+  const int64_t plane = n * cv;
+  auto load_a = [&](int64_t r) {
+    if (MODE == 2) {
+      float4 a = make_float4(0, 0, 0, 0);
+#pragma unroll 4
+      for (int z = 0; z < nsplit; ++z) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(A) + z * plane + r * cv + c4);
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+      }
+      return a;
+    }
+    return __ldg(reinterpret_cast<const float4*>(A + r * lda) + c4);
+  };
   float4 s1 = make_float4(0, 0, 0, 0), s2 = make_float4(0, 0, 0, 0);
-  float4 mu = make_float4(0, 0, 0, 0), is = make_float4(1, 1, 1, 1);
-  if (TWO_INPUTS && rl < rp) {
-    mu = reinterpret_cast<const float4*>(mean + seg * C)[c4];
-    is = reinterpret_cast<const float4*>(invstd + seg * C)[c4];
-  }
+  float4 mu = make_float4(0, 0, 0, 0), is = make_float4(1, 1, 1, 1), pv = make_float4(0, 0, 0, 0);
   if (rl < rp) {
+    if (MODE == 1) {
+      mu = reinterpret_cast<const float4*>(mean + seg * C)[c4];
+      is = reinterpret_cast<const float4*>(invstd + seg * C)[c4];
+    } else if (r0 < r1) {
+      pv = load_a(r0);               // pivot: the chunk's first row (every row lane reads the same line)
+    }
+#pragma unroll 4
     for (int64_t r = r0 + rl; r < r1; r += rp) {
-      float4 a = __ldg(reinterpret_cast<const float4*>(A + r * lda) + c4);
-      if (TWO_INPUTS) {
-        if (Mask) {
-          float4 m = __ldg(reinterpret_cast<const float4*>(Mask + r * ldm) + c4);
+      float4 a = load_a(r);
+      if (MODE == 2) *reinterpret_cast<float4*>(Y + r * ldy + c4 * 4) = a;
+      if (MODE == 1) {
+        if (MaskH) mask4_bf16(MaskH + r * ldmh + c4 * 4, a);
+        else if (MaskF) {
+          const float4 m = __ldg(reinterpret_cast<const float4*>(MaskF + r * ldmf) + c4);
           a.x = m.x > 0.f ? a.x : 0.f; a.y = m.y > 0.f ? a.y : 0.f; a.z = m.z > 0.f ? a.z : 0.f; a.w = m.w > 0.f ? a.w : 0.f;
-        } else if (MaskH) {
-          mask4_bf16(MaskH + r * ldmh + c4 * 4, a);
         }
-        float4 x = __ldg(reinterpret_cast<const float4*>(Bm + r * ldb) + c4);
-        // a = dY, second sum = dY * xhat
+        const float4 x = __ldg(reinterpret_cast<const float4*>(Bm + r * ldb) + c4);
         s1.x += a.x; s1.y += a.y; s1.z += a.z; s1.w += a.w;
         s2.x += a.x * ((x.x - mu.x) * is.x); s2.y += a.y * ((x.y - mu.y) * is.y);
         s2.z += a.z * ((x.z - mu.z) * is.z); s2.w += a.w * ((x.w - mu.w) * is.w);
       } else {
+        a.x -= pv.x; a.y -= pv.y; a.z -= pv.z; a.w -= pv.w;
         s1.x += a.x; s1.y += a.y; s1.z += a.z; s1.w += a.w;
         s2.x += a.x * a.x; s2.y += a.y * a.y; s2.z += a.z * a.z; s2.w += a.w * a.w;
       }
@@ -112,48 +136,18 @@ __global__ void colsum_kernel(const float* __restrict__ A, int lda, const float*
     reinterpret_cast<float4*>(d + C)[c4] = s2;
   }
   __syncthreads();
-  for (int e = threadIdx.x; e < 2 * C; e += blockDim.x) {
-    float s = 0.f;
-    for (int l = 0; l < rp; ++l) s += sm[(int64_t)l * 2 * C + e];
-    partial[(int64_t)blockIdx.x * 2 * C + e] = s;
-  }
-}
-
-// Offset-split convolutions (small levels): Y[row] = sum_z partial_conv[z][row]  AND the BatchNorm column sums of Y in the same
-// pass (same chunking / segment layout as colsum_kernel<false>), so the statistics cost no extra read of Y.
-__global__ void reduce_stats_kernel(const float* __restrict__ P, int nsplit, float* __restrict__ Y, int ldy, int64_t n, int64_t n0,
-                                    int chunks0, int C, float* __restrict__ partial) {
-  pdl_wait(); pdl_trigger();
-  extern __shared__ float sm[];      // [RP][2][C]
-  const int cv = C / 4;
-  const int rp = blockDim.x / cv;
-  const int c4 = threadIdx.x % cv;
-  const int rl = threadIdx.x / cv;
-  const int seg = (int)blockIdx.x >= chunks0 ? 1 : 0;
-  const int64_t r0 = seg ? n0 + (int64_t)((int)blockIdx.x - chunks0) * ROWS_PER_CHUNK : (int64_t)blockIdx.x * ROWS_PER_CHUNK;
-  const int64_t r1 = min(seg ? n : n0, r0 + ROWS_PER_CHUNK);
-  float4 s1 = make_float4(0, 0, 0, 0), s2 = make_float4(0, 0, 0, 0);
-  if (rl < rp) {
-    const int64_t plane = n * cv;
-    for (int64_t r = r0 + rl; r < r1; r += rp) {
-      float4 a = make_float4(0, 0, 0, 0);
-      for (int z = 0; z < nsplit; ++z) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(P) + z * plane + r * cv + c4);
-        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
-      }
-      *reinterpret_cast<float4*>(Y + r * ldy + c4 * 4) = a;
-      s1.x += a.x; s1.y += a.y; s1.z += a.z; s1.w += a.w;
-      s2.x += a.x * a.x; s2.y += a.y * a.y; s2.z += a.z * a.z; s2.w += a.w * a.w;
+  const float m = (float)(r1 > r0 ? r1 - r0 : 1);
+  for (int e = threadIdx.x; e < C; e += blockDim.x) {
+    float t1 = 0.f, t2 = 0.f;
+    for (int l = 0; l < rp; ++l) { t1 += sm[(int64_t)l * 2 * C + e]; t2 += sm[(int64_t)l * 2 * C + C + e]; }
+    if (MODE != 1) {                 // shifted sums -> { sum(x), M2 about the chunk mean }
+      const float p = MODE == 2 ? Y[r0 * ldy + e] : A[r0 * lda + e];
+      const float M2 = t2 - t1 * t1 / m;
+      t2 = M2 > 0.f ? M2 : 0.f;
+      t1 = t1 + m * p;
     }
-    float* d = sm + (int64_t)rl * 2 * C;
-    reinterpret_cast<float4*>(d)[c4] = s1;
-    reinterpret_cast<float4*>(d + C)[c4] = s2;
-  }
-  __syncthreads();
-  for (int e = threadIdx.x; e < 2 * C; e += blockDim.x) {
-    float s = 0.f;
-    for (int l = 0; l < rp; ++l) s += sm[(int64_t)l * 2 * C + e];
-    partial[(int64_t)blockIdx.x * 2 * C + e] = s;
+    partial[(int64_t)blockIdx.x * 2 * C + e] = t1;
+    partial[(int64_t)blockIdx.x * 2 * C + C + e] = t2;
   }
 }
 
@@ -161,28 +155,41 @@ __global__ void reduce_stats_kernel(const float* __restrict__ P, int nsplit, flo
 __device__ __forceinline__ void warp_sum2(const float* __restrict__ partial, int chunks, int C, int c, double& s1, double& s2) {
   const int lane = threadIdx.x & 31;
   s1 = 0.0; s2 = 0.0;
+#pragma unroll 4
   for (int k = lane; k < chunks; k += 32) { s1 += partial[(int64_t)k * 2 * C + c]; s2 += partial[(int64_t)k * 2 * C + C + c]; }
   for (int o = 16; o; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
 }
 
-// Segment s has chunks [s ? chunks0 : 0, ...) and n0 / n - n0 rows.  The running statistics see the segments one after
+// Forward statistics from the per-chunk { sum, M2 } partials (Chan et al. pairwise merge, fp64).  Segment s has chunks
+// [s ? chunks0 : 0, ...) of R rows (the last one shorter) and n0 / n - n0 rows.  The running statistics see the segments one after
 // the other, as two forward calls would (`ddp_trainer.py:290-297`: the model runs on view 0, then on view 1).
-__global__ void bn_finalize_kernel(const float* __restrict__ partial, int chunks, int chunks0, int64_t n, int64_t n0, int C, float eps,
+__global__ void bn_finalize_kernel(const float* __restrict__ partial, int chunks, int chunks0, int R, int64_t n, int64_t n0, int C, float eps,
                                    float momentum, float* __restrict__ mean, float* __restrict__ invstd, float* running_mean,
                                    float* running_var) {
   pdl_wait(); pdl_trigger();
   int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (c >= C) return;
+  const int lane = threadIdx.x & 31;
   const int nseg = n0 < n ? 2 : 1;
   for (int seg = 0; seg < nseg; ++seg) {
     const float* p = partial + (seg ? (int64_t)chunks0 * 2 * C : 0);
     const int ch = seg ? chunks - chunks0 : chunks0;
     const int64_t rows = seg ? n - n0 : n0;
-    double s1, s2;
-    warp_sum2(p, ch, C, c, s1, s2);
-    if ((threadIdx.x & 31) == 0) {
-      double m = s1 / (double)rows;
-      double var = s2 / (double)rows - m * m;
+    double s1 = 0.0;
+#pragma unroll 4
+    for (int k = lane; k < ch; k += 32) s1 += p[(int64_t)k * 2 * C + c];
+    for (int o = 16; o; o >>= 1) s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    const double m = s1 / (double)rows;
+    double M2 = 0.0;
+#pragma unroll 4
+    for (int k = lane; k < ch; k += 32) {
+      const double mk = (double)min((int64_t)R, rows - (int64_t)k * R);
+      const double d = (double)p[(int64_t)k * 2 * C + c] / mk - m;
+      M2 += (double)p[(int64_t)k * 2 * C + C + c] + mk * d * d;
+    }
+    for (int o = 16; o; o >>= 1) M2 += __shfl_xor_sync(0xffffffffu, M2, o);
+    if (lane == 0) {
+      double var = M2 / (double)rows;
       if (var < 0.0) var = 0.0;
       mean[seg * C + c] = (float)m;
       invstd[seg * C + c] = (float)(1.0 / sqrt(var + (double)eps));
@@ -291,7 +298,19 @@ __global__ void bn_bwd_apply_kernel(const float* dY, int lddy, const float* __re
   if (dXhi) store_split4(o, dXhi + row * lds + c4 * 4, dXlo + row * lds + c4 * 4);
 }
 
-inline int chunks_for(int64_t n) { return (int)((n + ROWS_PER_CHUNK - 1) / ROWS_PER_CHUNK); }
+// rows per chunk: a power of two in [16, 1024] near n / 512, so that every level launches a few hundred CTAs
+inline int chunk_rows(int64_t n) {
+  const int64_t t = n / 512;
+  int R = 16;
+  while (R < 1024 && (int64_t)R * 3 / 2 < t) R <<= 1;
+  return R;
+}
+inline int chunks_of(int64_t rows, int R) { return (int)((rows + R - 1) / R); }
+// chunks0 / chunks of rows [0, n0) / [0, n) cut into R-row chunks that never straddle n0
+inline void chunk_layout(int64_t n, int64_t n0, int R, int* chunks, int* chunks0) {
+  *chunks0 = chunks_of(n0 < n ? n0 : n, R);
+  *chunks = *chunks0 + (n0 < n ? chunks_of(n - n0, R) : 0);
+}
 
 inline int colsum_threads(int C) {       // (C/4) * row lanes, <= 256, at least one row lane
   int cv = C / 4;
@@ -303,8 +322,8 @@ inline int colsum_threads(int C) {       // (C/4) * row lanes, <= 256, at least 
 
 extern "C" size_t pcb_bn_ws_bytes(int64_t n, int C) {
   if (n < 1) n = 1;
-  // partial sums of <= chunks_for(n) + 1 chunks (two segments round up separately) + [2 segments][2][C] sums
-  return (size_t)(chunks_for(n) + 1 + 2) * 2 * C * sizeof(float) + 256;
+  // per-chunk partial sums (two segments round up separately) + [2 segments][2][C] sums
+  return (size_t)(chunks_of(n, chunk_rows(n)) + 2 + 2) * 2 * C * sizeof(float) + 256;
 }
 
 // n0: rows [0, n0) and [n0, n) are separate BatchNorm batches (n0 == n: one batch).  mean / invstd: [segments][C].
@@ -313,15 +332,16 @@ extern "C" int pcb_bn_stats_seg(const float* X, int ldx, int64_t n, int64_t n0, 
   PCB_ARG(X && mean && invstd && ws && n >= 1 && n0 >= 1 && n0 <= n && C >= 4 && C % 4 == 0 && C <= 1024 && ldx >= C && ldx % 4 == 0);
   PCB_ARG(ws_bytes >= pcb_bn_ws_bytes(n, C) - 256);
   cudaStream_t st = (cudaStream_t)stream;
-  const int chunks0 = chunks_for(n0);
-  const int chunks = chunks0 + (n0 < n ? chunks_for(n - n0) : 0);
+  const int R = chunk_rows(n);
+  int chunks, chunks0;
+  chunk_layout(n, n0, R, &chunks, &chunks0);
   const int thr = colsum_threads(C);
   const int rp = thr / (C / 4);
-  launch_kernel(colsum_kernel<false>, chunks, thr, (size_t)rp * 2 * C * sizeof(float), st, X, ldx, nullptr, 0, nullptr, 0, nullptr, 0, n, n0, chunks0, C,
-                                                                                 nullptr, nullptr, (float*)ws);
-  if (int e = check_launch("colsum_kernel")) return e;
-  launch_kernel(bn_finalize_kernel, (C + 7) / 8, 256, 0, st, (const float*)ws, chunks, chunks0, n, n0, C, eps, momentum, mean, invstd, running_mean,
-                                                      running_var);
+  launch_kernel(colstat_kernel<0>, chunks, thr, (size_t)rp * 2 * C * sizeof(float), st, X, ldx, nullptr, 0, nullptr, 0, nullptr, 0, 0, nullptr, 0,
+                n, n0, chunks0, R, C, nullptr, nullptr, (float*)ws);
+  if (int e = check_launch("colstat_kernel<fwd>")) return e;
+  launch_kernel(bn_finalize_kernel, (C + 7) / 8, 256, 0, st, (const float*)ws, chunks, chunks0, R, n, n0, C, eps, momentum, mean, invstd,
+                running_mean, running_var);
   return check_launch("bn_finalize_kernel");
 }
 
@@ -374,15 +394,16 @@ int bn_backward_impl(const float* dY, int lddy, const float* X, int ldx, const f
   PCB_ARG(gout_mode == 0 || (gout && ldg >= C && ldg % 4 == 0));
   PCB_ARG(ws_bytes >= pcb_bn_ws_bytes(n, C) - 256);
   const int nseg = n0 < n ? 2 : 1;
-  const int chunks0 = chunks_for(n0);
-  const int chunks = chunks0 + (nseg == 2 ? chunks_for(n - n0) : 0);
+  const int R = chunk_rows(n);
+  int chunks, chunks0;
+  chunk_layout(n, n0, R, &chunks, &chunks0);
   const int thr = colsum_threads(C);
   const int rp = thr / (C / 4);
   float* partial = (float*)ws;
   float* sums = partial + (size_t)chunks * 2 * C;        // [segments][2][C]: dbeta, dgamma of THIS call (the apply pass needs them)
-  launch_kernel(colsum_kernel<true>, chunks, thr, (size_t)rp * 2 * C * sizeof(float), st, dY, lddy, X, ldx, relu_out, ldm, (const __nv_bfloat16*)relu_hi,
-                                                                                ldmh, n, n0, chunks0, C, mean, invstd, partial);
-  if (int e = check_launch("colsum_kernel<bwd>")) return e;
+  launch_kernel(colstat_kernel<1>, chunks, thr, (size_t)rp * 2 * C * sizeof(float), st, dY, lddy, X, ldx, (const __nv_bfloat16*)relu_hi, ldmh,
+                relu_out, ldm, 0, nullptr, 0, n, n0, chunks0, R, C, mean, invstd, partial);
+  if (int e = check_launch("colstat_kernel<bwd>")) return e;
   launch_kernel(bn_bwd_finalize_kernel, (C + 7) / 8, 256, 0, st, partial, chunks, chunks0, nseg, C, dgamma, dbeta, accumulate_param_grads, sums);
   if (int e = check_launch("bn_bwd_finalize_kernel")) return e;
   int64_t n4 = n * (C / 4);
@@ -393,30 +414,23 @@ int bn_backward_impl(const float* dY, int lddy, const float* X, int ldx, const f
   return check_launch("bn_bwd_apply_kernel");
 }
 
-// Layout of the per-128-row-tile column sums written by a producer (conv epilogue / reduce_stats_kernel) for rows [0, n) with
-// segments [0, n0) and [n0, n): TILES ARE ALIGNED TO ROW 0 for the conv epilogue (conv_tile_aligned) -- the tile containing
-// row n0 contributes a row to both segments -- and aligned to each segment's first row for reduce_stats_kernel.
-void bn_partial_layout(int64_t n, int64_t n0, bool conv_tile_aligned, int* chunks, int* chunks0) {
-  if (n0 >= n) { *chunks0 = chunks_for(n); *chunks = *chunks0; return; }
-  *chunks0 = chunks_for(n0);
-  *chunks = *chunks0 + (conv_tile_aligned ? chunks_for(n) - (int)(n0 / ROWS_PER_CHUNK) : chunks_for(n - n0));
-}
-
-int bn_finalize_launch(const float* partial, int chunks, int chunks0, int64_t n, int64_t n0, int C, float eps, float momentum, float* mean,
-                       float* invstd, float* running_mean, float* running_var, cudaStream_t st) {
-  launch_kernel(bn_finalize_kernel, (C + 7) / 8, 256, 0, st, partial, chunks, chunks0, n, n0, C, eps, momentum, mean, invstd, running_mean, running_var);
-  return check_launch("bn_finalize_kernel");
-}
-
-// Y = sum of the nsplit partial planes P[z][n][C] (offset-split convolution), column sums of Y -> partial (segment-aligned chunks)
-int bn_reduce_stats_launch(const float* P, int nsplit, float* Y, int ldy, int64_t n, int64_t n0, int C, float* partial, cudaStream_t st) {
-  PCB_ARG(P && Y && partial && nsplit >= 1 && n >= 1 && n0 >= 1 && n0 <= n && C % 4 == 0 && C <= 1024 && ldy >= C && ldy % 4 == 0);
+// Forward statistics fused into the reduction pass of an offset-split convolution: Y = sum of the nsplit partial planes
+// P[z][n][C], BatchNorm statistics of Y (segments [0, n0) / [n0, n)) -> mean / invstd / running statistics.  ws: pcb_bn_ws_bytes(n, C).
+int bn_reduce_stats_launch(const float* P, int nsplit, float* Y, int ldy, int64_t n, int64_t n0, int C, float eps, float momentum,
+                           float* mean, float* invstd, float* running_mean, float* running_var, void* ws, size_t ws_bytes, cudaStream_t st) {
+  PCB_ARG(P && Y && ws && nsplit >= 1 && n >= 1 && n0 >= 1 && n0 <= n && C % 4 == 0 && C <= 1024 && ldy >= C && ldy % 4 == 0);
+  PCB_ARG(ws_bytes >= pcb_bn_ws_bytes(n, C) - 256);
+  const int R = chunk_rows(n);
   int chunks, chunks0;
-  bn_partial_layout(n, n0, false, &chunks, &chunks0);
+  chunk_layout(n, n0, R, &chunks, &chunks0);
   const int thr = colsum_threads(C);
   const int rp = thr / (C / 4);
-  launch_kernel(reduce_stats_kernel, chunks, thr, (size_t)rp * 2 * C * sizeof(float), st, P, nsplit, Y, ldy, n, n0, chunks0, C, partial);
-  return check_launch("reduce_stats_kernel");
+  launch_kernel(colstat_kernel<2>, chunks, thr, (size_t)rp * 2 * C * sizeof(float), st, P, 0, nullptr, 0, nullptr, 0, nullptr, 0, nsplit, Y, ldy,
+                n, n0, chunks0, R, C, nullptr, nullptr, (float*)ws);
+  if (int e = check_launch("colstat_kernel<reduce+stats>")) return e;
+  launch_kernel(bn_finalize_kernel, (C + 7) / 8, 256, 0, st, (const float*)ws, chunks, chunks0, R, n, n0, C, eps, momentum, mean, invstd,
+                running_mean, running_var);
+  return check_launch("bn_finalize_kernel");
 }
 }  // namespace pcb
 

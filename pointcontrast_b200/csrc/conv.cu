@@ -293,6 +293,40 @@ __global__ void conv_simt_kernel(const float* __restrict__ X, int ldx, const int
   Y[j * ldy + co] = acc;
 }
 
+// The stem layer (CIN = 3 -> 32 channels, exact fp32): one warp per output row, lane = output channel.  All K table entries of the
+// row are fetched first, then all gathered inputs (branch-free, clamped index), then the FMAs: K + K*CIN independent loads in flight
+// per warp instead of a dependent table -> feature chain per offset.  Weights [K][CIN][32] sit in shared memory.
+template <int CIN>
+__global__ void __launch_bounds__(256) conv_stem_kernel(const float* __restrict__ X, int ldx, const int32_t* __restrict__ tbl,
+                                                        int64_t tbl_stride, KMap kmap, int K, int64_t n_out, const float* __restrict__ W,
+                                                        const float* __restrict__ bias, float* __restrict__ Y, int ldy) {
+  pdl_wait(); pdl_trigger();
+  __shared__ float s_w[PCB_MAX_KERNEL_VOLUME * CIN * 32];
+  for (int e = threadIdx.x; e < K * CIN * 32; e += 256) s_w[e] = W[e];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t j = blockIdx.x * 8ll + (threadIdx.x >> 5);
+  if (j >= n_out) return;
+  int idx[PCB_MAX_KERNEL_VOLUME];
+#pragma unroll
+  for (int k = 0; k < PCB_MAX_KERNEL_VOLUME; ++k) idx[k] = k < K ? __ldg(tbl + (int64_t)kmap.v[k] * tbl_stride + j) : -1;
+  float x[PCB_MAX_KERNEL_VOLUME][CIN];
+#pragma unroll
+  for (int k = 0; k < PCB_MAX_KERNEL_VOLUME; ++k) {
+    const float* xr = X + (int64_t)(idx[k] >= 0 ? idx[k] : 0) * ldx;
+#pragma unroll
+    for (int c = 0; c < CIN; ++c) { const float v = __ldg(xr + c); x[k][c] = idx[k] >= 0 ? v : 0.f; }
+  }
+  float acc = bias ? bias[lane] : 0.f;
+#pragma unroll
+  for (int k = 0; k < PCB_MAX_KERNEL_VOLUME; ++k)
+    if (k < K) {
+#pragma unroll
+      for (int c = 0; c < CIN; ++c) acc = fmaf(x[k][c], s_w[(k * CIN + c) * 32 + lane], acc);
+    }
+  Y[j * ldy + lane] = acc;
+}
+
 // --------------------------------------------------------------------------------------------- weight gradient (tensor cores)
 constexpr int WK = 32;    // rows (reduction dim) per pipeline step
 
@@ -511,15 +545,15 @@ __global__ void __launch_bounds__(256) wgrad_stem_kernel(const float* __restrict
   const int64_t r1 = min(n_out, r0 + rows_per_block);
   for (int64_t j = r0 + warp; j < r1; j += 8) {
     const float dy = __ldg(B + j * ldb + lane);
+    int idx[PCB_MAX_KERNEL_VOLUME];       // all table entries of the row first, then all gathered inputs (branch-free): independent loads
+#pragma unroll
+    for (int k = 0; k < PCB_MAX_KERNEL_VOLUME; ++k) idx[k] = k < K ? __ldg(tbl + (int64_t)k * tbl_stride + j) : -1;
 #pragma unroll
     for (int k = 0; k < PCB_MAX_KERNEL_VOLUME; ++k) {
-      if (k < K) {
-        const int idx = __ldg(tbl + (int64_t)k * tbl_stride + j);
-        if (idx >= 0) {
+      const float* ar = A + (int64_t)(idx[k] >= 0 ? idx[k] : 0) * lda;
+      const float w = idx[k] >= 0 ? dy : 0.f;
 #pragma unroll
-          for (int c = 0; c < CA; ++c) acc[k][c] = fmaf(__ldg(A + (int64_t)idx * lda + c), dy, acc[k][c]);
-        }
-      }
+      for (int c = 0; c < CA; ++c) acc[k][c] = fmaf(__ldg(ar + c), w, acc[k][c]);
     }
   }
   for (int w = 0; w < 8; ++w) {          // warp after warp, in a fixed order: deterministic (no shared-memory atomics)
@@ -651,8 +685,7 @@ int launch_wgrad_tcgen05(const uint16_t* Ahi, const uint16_t* Alo, int lda, cons
 int launch_conv_tcgen05(const float* X, int ldx, const uint16_t* Xhi, const uint16_t* Xlo, int lds, const void* wt, const int32_t* tbl,
                         int64_t tbl_stride, const int* kmap, int K, int64_t n_out,
                         int Cin, int Cout, const uint16_t* wk_hi, const uint16_t* wk_lo, const float* bias, float* Y, int ldy,
-                        float* partial, int nsplit, int bn, int accumulate, cudaStream_t st, float* stats = nullptr, int64_t seg_n0 = 0,
-                        int x_fp16 = 0, int w_fp16 = 0);
+                        float* partial, int nsplit, int bn, int accumulate, cudaStream_t st, int x_fp16 = 0, int w_fp16 = 0);
 }
 
 extern "C" size_t pcb_conv_forward_ws_bytes(int K, int64_t n_out, int Cin, int Cout) {
@@ -677,6 +710,10 @@ extern "C" int pcb_conv_forward(const float* X, int ldx, const int32_t* tbl, int
   if (!tc_ok) {
     if (flags & PCB_CONV_ACCUMULATE) { set_error("PCB_CONV_ACCUMULATE needs the tcgen05 path"); return PCB_ERR_ARG; }
     if (!w_f32) { set_error("pcb_conv_forward: SIMT path needs w_f32 (Cin=%d Cout=%d)", Cin, Cout); return PCB_ERR_ARG; }
+    if (Cin == 3 && Cout == 32) {         // the stem layer
+      launch_kernel(conv_stem_kernel<3>, (unsigned)((n_out + 7) / 8), 256, 0, st, X, ldx, tbl, tbl_stride, km, K, n_out, w_f32, bias, Y, ldy);
+      return check_launch("conv_stem_kernel");
+    }
     int64_t total = n_out * Cout;
     launch_kernel(conv_simt_kernel, (unsigned)((total + 255) / 256), 256, 0, st, X, ldx, tbl, tbl_stride, km, K, n_out, Cin, Cout,
                                                                       w_f32, bias, Y, ldy);
@@ -838,17 +875,20 @@ extern "C" int pcb_weight_tile(const float* W, int K, int Cin, int Cout, void* f
 }
 
 namespace pcb {
-int bn_reduce_stats_launch(const float* P, int nsplit, float* Y, int ldy, int64_t n, int64_t n0, int C, float* partial, cudaStream_t st);
-void bn_partial_layout(int64_t n, int64_t n0, bool conv_tile_aligned, int* chunks, int* chunks0);
+int bn_reduce_stats_launch(const float* P, int nsplit, float* Y, int ldy, int64_t n, int64_t n0, int C, float eps, float momentum,
+                           float* mean, float* invstd, float* running_mean, float* running_var, void* ws, size_t ws_bytes, cudaStream_t st);
 
-// stats != NULL: also produce the BatchNorm column sums of Y (rows [0, seg_n0) and [seg_n0, n_out) separately) as per-128-row
-// partials [chunks][2][Cout] -- from the TMEM epilogue in direct mode, from the reduce pass in offset-split mode; *chunks / *chunks0
-// describe the layout for bn_finalize_launch.  Requires no bias and no accumulate (a BatchNorm follows the convolution).
+// bn != NULL: a BatchNorm follows this convolution (no bias, no accumulate).  When the convolution runs offset-split (small levels)
+// its reduction pass also produces the BatchNorm statistics (one read of the partial planes instead of reduce + a column-sum pass
+// over Y) and *bn_done = 1; in direct mode nothing changes and *bn_done = 0 (the caller runs pcb_bn_stats_seg: fusing the column
+// sums into the TMEM epilogue was measured SLOWER than the separate pass, profiles/r2_results.md).
+struct BnFuse { int64_t n0; float eps, momentum; float* mean; float* invstd; float* running_mean; float* running_var; void* ws; size_t ws_bytes; };
 int conv_forward_split_impl(const uint16_t* Xhi, const uint16_t* Xlo, int lds, const int32_t* tbl, int64_t tbl_stride, const int32_t* kmap,
                             int K, int64_t n_out, int Cin, int Cout, const void* w_tiles, const float* bias, float* Y, int ldy, void* ws,
-                            size_t ws_bytes, int flags, cudaStream_t st, float* stats, int64_t seg_n0, int* chunks, int* chunks0) {
+                            size_t ws_bytes, int flags, cudaStream_t st, const BnFuse* bn, int* bn_done) {
   PCB_ARG(K >= 1 && K <= PCB_MAX_KERNEL_VOLUME && n_out >= 0 && Cin % 32 == 0 && Cout % 32 == 0 && Cin >= 32 && Cout >= 32);
   PCB_ARG(lds >= Cin && lds % 8 == 0 && ldy >= Cout && ldy % 4 == 0);
+  if (bn_done) *bn_done = 0;
   if (n_out == 0) return PCB_OK;
   PCB_ARG(Xhi && Xlo && tbl && Y && w_tiles && tbl_stride >= n_out);
   ProfScope prof(st, 0);
@@ -857,13 +897,16 @@ int conv_forward_split_impl(const uint16_t* Xhi, const uint16_t* Xlo, int lds, c
   const int accumulate = (flags & PCB_CONV_ACCUMULATE) ? 1 : 0;
   const int nsplit = conv_splits(K, n_out, Cin, Cout);
   if (nsplit > 1) PCB_ARG(ws && ws_bytes >= (size_t)nsplit * n_out * Cout * sizeof(float));
-  if (stats) PCB_ARG(!bias && !accumulate && seg_n0 >= 1 && seg_n0 <= n_out && chunks && chunks0);
+  if (bn) PCB_ARG(!bias && !accumulate && bn->n0 >= 1 && bn->n0 <= n_out && bn_done);
   if (int e = launch_conv_tcgen05(nullptr, 0, Xhi, Xlo, lds, w_tiles, tbl, tbl_stride, km, K, n_out, Cin, Cout, nullptr, nullptr, bias, Y, ldy,
-                                  nsplit > 1 ? (float*)ws : nullptr, nsplit, pick_tile(Cout), accumulate, st, stats, seg_n0,
+                                  nsplit > 1 ? (float*)ws : nullptr, nsplit, pick_tile(Cout), accumulate, st,
                                   (flags & PCB_PLANES_A_FP16) ? 1 : 0, (flags & PCB_PLANES_B_FP16) ? 1 : 0)) return e;
-  if (stats) bn_partial_layout(n_out, seg_n0, nsplit == 1, chunks, chunks0);
   if (nsplit > 1) {
-    if (stats) return bn_reduce_stats_launch((const float*)ws, nsplit, Y, ldy, n_out, seg_n0, Cout, stats, st);
+    if (bn) {
+      *bn_done = 1;
+      return bn_reduce_stats_launch((const float*)ws, nsplit, Y, ldy, n_out, bn->n0, Cout, bn->eps, bn->momentum, bn->mean, bn->invstd,
+                                    bn->running_mean, bn->running_var, bn->ws, bn->ws_bytes, st);
+    }
     int64_t n4 = n_out * (Cout / 4);
     launch_kernel(conv_split_reduce_kernel, (unsigned)((n4 + 255) / 256), 256, 0, st, (const float*)ws, nsplit, n_out, Cout, bias, Y, ldy, accumulate);
     return check_launch("conv_split_reduce_kernel");
@@ -877,7 +920,7 @@ extern "C" int pcb_conv_forward_split(const uint16_t* Xhi, const uint16_t* Xlo, 
                                       const float* bias, float* Y, int ldy, void* ws, size_t ws_bytes,
                                       int flags, void* stream) {
   return pcb::conv_forward_split_impl(Xhi, Xlo, lds, tbl, tbl_stride, kmap, K, n_out, Cin, Cout, w_tiles, bias, Y, ldy, ws, ws_bytes, flags,
-                                      (cudaStream_t)stream, nullptr, 0, nullptr, nullptr);
+                                      (cudaStream_t)stream, nullptr, nullptr);
 }
 
 namespace {

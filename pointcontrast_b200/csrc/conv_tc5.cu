@@ -106,10 +106,6 @@ struct Args {
   float* Y; int ldy;
   float* partial;
   int accumulate;       // Y += result (direct mode only; the split mode accumulates in the reduce kernel)
-  // Direct mode only: per-128-row-tile column sums / sums of squares of the tile written to Y (the BatchNorm statistics of the
-  // consumer), stats[prow][2][Cout].  Rows [0, seg_n0) and [seg_n0, n_out) are separate BatchNorm batches: tile t writes
-  // prow = t for segment 0 and prow = ceil(seg_n0/128) + t - floor(seg_n0/128) for segment 1 (bn_partial_layout in bn.cu).
-  float* stats; int64_t seg_n0;
   // operand formats of the tcgen05.mma instruction descriptor (bits 7-9: A = gathered rows, bits 10-12: B = weights; 0 fp16, 1 bf16)
   // and the factor applied to the accumulators on the way out (2^-10 when the weight tiles hold fp16(W * 2^10))
   uint32_t fmt_bits; float out_scale;
@@ -324,22 +320,6 @@ __global__ void __launch_bounds__(NTHR, 2) conv_tcgen05_kernel(const Args p) {
 // One CTA per SM (the 6-stage ring fills the shared memory), accumulators in TMEM, same epilogue as above.
 constexpr int DEPTH = 4;
 
-// Sum over the 32 lanes of a warp of 16 values per lane, 16 shuffles: each exchange step halves the values a lane carries.
-// Returns the total of column bfly_col(lane) (both lanes of a pair 2j, 2j+1 hold the same column).
-__device__ __forceinline__ float bfly16(const float (&v)[16], int lane) {
-  float a[8], b[4], c[2];
-  const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) a[i] = (h16 ? v[i + 8] : v[i]) + __shfl_xor_sync(0xffffffffu, h16 ? v[i] : v[i + 8], 16);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) b[i] = (h8 ? a[i + 4] : a[i]) + __shfl_xor_sync(0xffffffffu, h8 ? a[i] : a[i + 4], 8);
-#pragma unroll
-  for (int i = 0; i < 2; ++i) c[i] = (h4 ? b[i + 2] : b[i]) + __shfl_xor_sync(0xffffffffu, h4 ? b[i] : b[i + 2], 4);
-  float d = (h2 ? c[1] : c[0]) + __shfl_xor_sync(0xffffffffu, h2 ? c[0] : c[1], 2);
-  return d + __shfl_xor_sync(0xffffffffu, d, 1);
-}
-__device__ __forceinline__ int bfly_col(int lane) { return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1); }
-
 template <int BN, int DNS>
 struct DSmem {
   static constexpr int B_SBO = 128;
@@ -518,15 +498,6 @@ __global__ void __launch_bounds__(DPROD + 32, CTAS) conv_tcgen05_split_kernel(co
     mbar_wait(done_bar, 0);
     tc_fence_after();
   }
-  // Column statistics of this tile (direct mode): warp (q, half) reduces its 32 rows x 16-column chunks by shuffles into
-  // s_st[q][segment][sum | sumsq][BN] (the pipeline stages are free by now); after the CTA barrier the four row quarters are
-  // added in a fixed order and written as one partial row per segment.
-  const bool do_stats = p.stats != nullptr && p.partial == nullptr;
-  const int64_t sn0 = p.seg_n0;
-  const bool two_seg = do_stats && sn0 < p.n_out;
-  const bool straddle = two_seg && row0 < sn0 && row0 + BM > sn0;
-  const int tile_seg = (two_seg && row0 >= sn0) ? 1 : 0;
-  float* s_st = reinterpret_cast<float*>(smem);
   if (warp < 8) {
     float* outp = p.partial ? p.partial + (int64_t)blockIdx.z * p.n_out * p.Cout : p.Y;
     const int ldo = p.partial ? p.Cout : p.ldy;
@@ -549,21 +520,6 @@ __global__ void __launch_bounds__(DPROD + 32, CTAS) conv_tcgen05_split_kernel(co
 #pragma unroll
         for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) * p.out_scale);
       }
-      if (do_stats) {
-        float v1[16], v2[16];
-        const bool in0 = !straddle || row < sn0;
-#pragma unroll
-        for (int e = 0; e < 16; ++e) { const float x = in0 ? __uint_as_float(r[e]) : 0.f; v1[e] = x; v2[e] = x * x; }
-        const float t1 = bfly16(v1, lane), t2 = bfly16(v2, lane);
-        const int sc = col + bfly_col(lane);
-        if (!(lane & 1)) { s_st[((q * 2 + 0) * 2 + 0) * BN + sc] = t1; s_st[((q * 2 + 0) * 2 + 1) * BN + sc] = t2; }
-        if (straddle) {         // CTA-uniform: only the one tile that contains row seg_n0
-#pragma unroll
-          for (int e = 0; e < 16; ++e) { const float x = in0 ? 0.f : __uint_as_float(r[e]); v1[e] = x; v2[e] = x * x; }
-          const float u1 = bfly16(v1, lane), u2 = bfly16(v2, lane);
-          if (!(lane & 1)) { s_st[((q * 2 + 1) * 2 + 0) * BN + sc] = u1; s_st[((q * 2 + 1) * 2 + 1) * BN + sc] = u2; }
-        }
-      }
       if (row < p.n_out) {
         float* dst = outp + row * ldo + n0 + col;
 #pragma unroll
@@ -581,19 +537,6 @@ __global__ void __launch_bounds__(DPROD + 32, CTAS) conv_tcgen05_split_kernel(co
   }
   tc_fence_before();
   __syncthreads();
-  if (do_stats) {
-    const int nseg_here = straddle ? 2 : 1;
-    const int64_t p0 = (sn0 + BM - 1) / BM, t0 = sn0 / BM;
-    for (int e = tid; e < nseg_here * 2 * BN; e += DTHR) {
-      const int sg = e / (2 * BN), rem = e - sg * 2 * BN, which = rem / BN, c = rem - which * BN;
-      float t = 0.f;
-#pragma unroll
-      for (int qq = 0; qq < 4; ++qq) t += s_st[((qq * 2 + sg) * 2 + which) * BN + c];
-      const int seg = straddle ? sg : tile_seg;
-      const int64_t prow = seg ? p0 + (int64_t)blockIdx.x - t0 : (int64_t)blockIdx.x;
-      p.stats[(prow * 2 + which) * p.Cout + n0 + c] = t;
-    }
-  }
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_acc), "r"(S::TMEM_COLS));
 }
 
@@ -643,13 +586,11 @@ int launch(const Args& a, int nsplit, cudaStream_t st) {
 int launch_conv_tcgen05(const float* X, int ldx, const uint16_t* Xhi, const uint16_t* Xlo, int lds, const void* wt, const int32_t* tbl,
                         int64_t tbl_stride, const int* kmap, int K, int64_t n_out,
                         int Cin, int Cout, const uint16_t* wk_hi, const uint16_t* wk_lo, const float* bias, float* Y, int ldy,
-                        float* partial, int nsplit, int bn, int accumulate, cudaStream_t st, float* stats, int64_t seg_n0, int x_fp16,
-                        int w_fp16) {
+                        float* partial, int nsplit, int bn, int accumulate, cudaStream_t st, int x_fp16, int w_fp16) {
   tc5::Args a;
   a.accumulate = accumulate;
   a.fmt_bits = ((x_fp16 ? 0u : 1u) << 7) | ((w_fp16 ? 0u : 1u) << 10);
   a.out_scale = w_fp16 ? 1.0f / 1024.0f : 1.0f;
-  a.stats = (Xhi && !partial) ? stats : nullptr; a.seg_n0 = seg_n0;
   static int dbg = -1;
   if (dbg < 0) { const char* e = getenv("PCB_TC5_DEBUG"); dbg = e ? atoi(e) : 0; }
   a.debug = dbg;

@@ -8,11 +8,10 @@
 #include "common.cuh"
 
 namespace pcb {
+struct BnFuse { int64_t n0; float eps, momentum; float* mean; float* invstd; float* running_mean; float* running_var; void* ws; size_t ws_bytes; };
 int conv_forward_split_impl(const uint16_t* Xhi, const uint16_t* Xlo, int lds, const int32_t* tbl, int64_t tbl_stride, const int32_t* kmap,
                             int K, int64_t n_out, int Cin, int Cout, const void* w_tiles, const float* bias, float* Y, int ldy, void* ws,
-                            size_t ws_bytes, int flags, cudaStream_t st, float* stats, int64_t seg_n0, int* chunks, int* chunks0);
-int bn_finalize_launch(const float* partial, int chunks, int chunks0, int64_t n, int64_t n0, int C, float eps, float momentum, float* mean,
-                       float* invstd, float* running_mean, float* running_var, cudaStream_t st);
+                            size_t ws_bytes, int flags, cudaStream_t st, const BnFuse* bn, int* bn_done);
 int bn_backward_impl(const float* dY, int lddy, const float* X, int ldx, const float* relu_out, int ldm, const uint16_t* relu_hi, int ldmh,
                      int64_t n, int64_t n0, int C, const float* mean, const float* invstd, const float* gamma, float* dX, int lddx,
                      float* dgamma, float* dbeta, int accumulate_param_grads, float* gout, int ldg, int gout_mode, uint16_t* dXhi,
@@ -109,20 +108,15 @@ extern "C" int pcb_unit_forward(const pcb_unit* u, void* stream) {
   const size_t conv_bytes = conv_part_bytes(u->K, u->n_in, u->n_out, u->Cin, u->Cout);
   unsigned char* bn_ws = (unsigned char*)u->ws + conv_bytes;
   const size_t bn_bytes = u->ws_bytes - conv_bytes;
-  bool have_stats = false;
+  int have_stats = 0;
   const bool f16 = (u->flags & PCB_UNIT_FP16_FORWARD) != 0;      // activations (x, out planes) and forward weight tiles are fp16 hi/lo
   if (tensor_core_shape(u->Cin, u->Cout)) {
     PCB_ARG(u->x_hi && u->x_lo && u->wt_fwd);
-    float* stats = (u->flags & PCB_UNIT_SEPARATE_STATS) ? nullptr : (float*)bn_ws;
-    int chunks = 0, chunks0 = 0;
+    BnFuse bn{u->n0, u->eps, u->momentum, u->mean, u->invstd, u->running_mean, u->running_var, bn_ws, bn_bytes};
+    const bool fuse = !(u->flags & PCB_UNIT_SEPARATE_STATS);
     if (int e = conv_forward_split_impl(u->x_hi, u->x_lo, u->x_lds, u->fwd_tbl, u->fwd_stride, u->fwd_kmap, u->K, u->n_out, u->Cin, u->Cout,
                                         u->wt_fwd, nullptr, u->z_p, u->z_ld, u->ws, conv_bytes, f16 ? (PCB_PLANES_A_FP16 | PCB_PLANES_B_FP16) : 0,
-                                        st, stats, u->n0, &chunks, &chunks0)) return e;
-    if (stats) {
-      if (int e = bn_finalize_launch(stats, chunks, chunks0, u->n_out, u->n0, u->Cout, u->eps, u->momentum, u->mean, u->invstd,
-                                     u->running_mean, u->running_var, st)) return e;
-      have_stats = true;
-    }
+                                        st, fuse ? &bn : nullptr, &have_stats)) return e;
   } else {
     PCB_ARG(u->x_p && u->W);
     if (int e = pcb_conv_forward(u->x_p, u->x_ld, u->fwd_tbl, u->fwd_stride, u->fwd_kmap, u->K, u->n_out, u->Cin, u->Cout, nullptr, nullptr,

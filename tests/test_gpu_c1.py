@@ -268,10 +268,9 @@ def test_reference_model_file_runs_on_cuda_fused():
         assert torch.equal(ref[4][n], own[4][n]), n
 
 
-def test_fused_epilogue_statistics_match_separate_pass(c1):
-    """BatchNorm statistics from the convolution's TMEM epilogue / offset-split reduction pass (default) vs a separate column-sum
-    pass over z (PCB_UNIT_SEPARATE_STATS): same numbers up to the fp32 order of the per-tile partial sums -- on the full-size
-    pair, which has direct-mode levels (tile straddling the view boundary included) and offset-split levels."""
+def test_fused_reduce_statistics_match_separate_pass(c1):
+    """BatchNorm statistics from the offset-split convolutions' reduction pass (default on the small levels) vs a separate
+    column-statistics pass over z everywhere (PCB_UNIT_SEPARATE_STATS): same numbers up to fp32 summation order."""
     from pointcontrast_b200 import fused
     from pointcontrast_b200.model import load_model
     b = c1["batch"]
