@@ -231,11 +231,18 @@ int pcb_unit_forward(const pcb_unit* u, void* stream);
 int pcb_unit_backward(const pcb_unit* u, void* stream);
 
 /* ----------------------------------------------------------------------------------------------- losses */
-/* PointInfoNCE on gathered rows q,k [n, D] (D % 4 == 0, D <= 128): loss = mean_i(logsumexp_j(q_i.k_j/T) - q_i.k_i/T).
- * Writes loss (device float), dq, dk (= d loss / d q, d k).  ws: pcb_nce_ws_bytes(n). */
+/* PointInfoNCE on gathered rows q,k [n, D]: loss = mean_i(logsumexp_j(q_i.k_j/T) - q_i.k_i/T).
+ * Writes loss (device float), dq, dk (= d loss / d q, d k).  ws: pcb_nce_ws_bytes(n).
+ * D = 32 or 64: fused tcgen05 kernels (nce_tc5.cu) -- q k^T tiles in Tensor Memory from fp16 hi/lo operands (|q|,|k| <= ~1: the
+ * L2-normalised features), softmax statistics and both gradients straight from the tiles, the n x n logits never stored.
+ * Other widths (or PCB_NCE_SIMT=1): exact fp32 SIMT kernels that materialise the logits in ws. */
 size_t pcb_nce_ws_bytes(int64_t n);
 int pcb_nce_forward_backward(const float* q, const float* k, int64_t n, int D, float inv_T, float* loss, float* dq,
                              float* dk, void* ws, size_t ws_bytes, void* stream);
+/* Row-wise L2 normalisation of the output features, y = x / ||x||_2 with no epsilon (`model/res16unet.py:262-266`), and its
+ * backward dx = (dy - y (y.dy)) / ||x||.  inv_norm: [n] scratch written by forward, read by backward. */
+int pcb_l2norm_forward(const float* X, int64_t n, int C, float* Y, float* inv_norm, void* stream);
+int pcb_l2norm_backward(const float* dY, const float* Y, const float* inv_norm, int64_t n, int C, float* dX, void* stream);
 /* minval[i] = min_j sqrt(sum_d (A[i,d]-B[j,d])^2 + 1e-7), argmin[i] = smallest such j.   packed: u64 scratch [P]. */
 int pcb_pdist_rowmin(const float* A, int64_t P, const float* B, int64_t S, int D, float* minval, int32_t* argmin,
                      uint64_t* packed, void* stream);

@@ -57,6 +57,8 @@ _SIGS = {
     "pcb_split_rows": (_i, [_p, _i, _l, _i, _p, _p, _i, _i, _p]),
     "pcb_nce_ws_bytes": (_sz, [_l]),
     "pcb_nce_forward_backward": (_i, [_p, _p, _l, _i, _f, _p, _p, _p, _p, _sz, _p]),
+    "pcb_l2norm_forward": (_i, [_p, _l, _i, _p, _p, _p]),
+    "pcb_l2norm_backward": (_i, [_p, _p, _p, _l, _i, _p, _p]),
     "pcb_pdist_rowmin": (_i, [_p, _l, _p, _l, _i, _p, _p, _p, _p]),
     "pcb_sgd_step": (_i, [_p, _p, _p, _l, _f, _f, _f, _f, _i, _p]),
     "pcb_profile_enable": (_i, [_i]),

@@ -4,6 +4,7 @@
 //   Hardest-contrastive: fused pairwise distance + row min/argmin (replaces the 537 MB broadcast `pdist`
 //   + .min(1), lib/ddp_trainer.py:182-184,215-219).
 // These are < 1 % of a training step; they are exact-fp32 SIMT kernels.
+#include <stdlib.h>
 #include "common.cuh"
 
 using namespace pcb;
@@ -184,13 +185,28 @@ int launch_sgemm(const float* A, int lda, const float* B, int ldb, float* C, int
 
 }  // namespace
 
-extern "C" size_t pcb_nce_ws_bytes(int64_t n) { return (size_t)n * n * sizeof(float) + (size_t)n * sizeof(float) + 512; }
+namespace pcb {
+bool nce_tc_supported(int64_t n, int D);
+size_t nce_tc_ws_bytes(int64_t n, int D);
+int nce_tc_forward_backward(const float* q, const float* k, int64_t n, int D, float inv_T, float* loss, float* dq, float* dk, void* ws,
+                            cudaStream_t st);
+}
+
+// scratch: the tensor-core path needs O(n * D) (partial statistics / gradients); the exact-fp32 SIMT path (feature widths other
+// than 32 / 64, or PCB_NCE_SIMT=1) materialises the n x n logits
+extern "C" size_t pcb_nce_ws_bytes(int64_t n) {
+  size_t simt = (size_t)n * n * sizeof(float) + (size_t)n * sizeof(float) + 512, tc = nce_tc_ws_bytes(n, 64);
+  return simt > tc ? simt : tc;
+}
 
 extern "C" int pcb_nce_forward_backward(const float* q, const float* k, int64_t n, int D, float inv_T, float* loss, float* dq,
                                         float* dk, void* ws, size_t ws_bytes, void* stream) {
   PCB_ARG(q && k && loss && dq && dk && ws && n >= 1 && n <= 46000 && D >= 1);
   PCB_ARG(ws_bytes >= pcb_nce_ws_bytes(n) - 512);
   cudaStream_t st = (cudaStream_t)stream;
+  static int force_simt = -1;
+  if (force_simt < 0) { const char* e = getenv("PCB_NCE_SIMT"); force_simt = (e && atoi(e)) ? 1 : 0; }
+  if (!force_simt && nce_tc_supported(n, D)) return nce_tc_forward_backward(q, k, n, D, inv_T, loss, dq, dk, ws, st);
   float* L = (float*)ws;
   float* rowloss = L + n * n;
   if (int e = launch_sgemm<false, true>(q, D, k, D, L, (int)n, (int)n, (int)n, D, inv_T, st)) return e;
@@ -200,6 +216,52 @@ extern "C" int pcb_nce_forward_backward(const float* q, const float* k, int64_t 
   if (int e = check_launch("mean_kernel")) return e;
   if (int e = launch_sgemm<false, false>(L, (int)n, k, D, dq, D, (int)n, D, (int)n, 1.f, st)) return e;    // dq = G k
   return launch_sgemm<true, false>(L, (int)n, q, D, dk, D, (int)n, D, (int)n, 1.f, st);                     // dk = G^T q
+}
+
+// ------------------------------------------------------------------------------------------------ L2 normalisation of feature rows
+// y = x / ||x||_2 per row, no epsilon (`model/res16unet.py:262-266`); one warp per row, lanes stride over the channels.
+namespace {
+__global__ void l2norm_fwd_kernel(const float* __restrict__ X, int64_t n, int C, float* __restrict__ Y, float* __restrict__ inv_norm) {
+  pdl_wait(); pdl_trigger();
+  const int lane = threadIdx.x & 31;
+  const int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n) return;
+  float ss = 0.f;
+  for (int c = lane; c < C; c += 32) { const float v = X[row * C + c]; ss = fmaf(v, v, ss); }
+  for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float inv = 1.0f / sqrtf(ss);
+  for (int c = lane; c < C; c += 32) Y[row * C + c] = X[row * C + c] * inv;
+  if (lane == 0) inv_norm[row] = inv;
+}
+// dx = (dy - y (y . dy)) / ||x||
+__global__ void l2norm_bwd_kernel(const float* __restrict__ dY, const float* __restrict__ Y, const float* __restrict__ inv_norm, int64_t n,
+                                  int C, float* __restrict__ dX) {
+  pdl_wait(); pdl_trigger();
+  const int lane = threadIdx.x & 31;
+  const int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n) return;
+  float dot = 0.f;
+  for (int c = lane; c < C; c += 32) dot = fmaf(Y[row * C + c], dY[row * C + c], dot);
+  for (int o = 16; o; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+  const float inv = inv_norm[row];
+  for (int c = lane; c < C; c += 32) dX[row * C + c] = (dY[row * C + c] - Y[row * C + c] * dot) * inv;
+}
+}  // namespace
+
+extern "C" int pcb_l2norm_forward(const float* X, int64_t n, int C, float* Y, float* inv_norm, void* stream) {
+  PCB_ARG(n >= 0 && C >= 1);
+  if (n == 0) return PCB_OK;
+  PCB_ARG(X && Y && inv_norm);
+  launch_kernel(l2norm_fwd_kernel, (unsigned)((n + 7) / 8), 256, 0, (cudaStream_t)stream, X, n, C, Y, inv_norm);
+  return check_launch("l2norm_fwd_kernel");
+}
+
+extern "C" int pcb_l2norm_backward(const float* dY, const float* Y, const float* inv_norm, int64_t n, int C, float* dX, void* stream) {
+  PCB_ARG(n >= 0 && C >= 1);
+  if (n == 0) return PCB_OK;
+  PCB_ARG(dY && Y && inv_norm && dX);
+  launch_kernel(l2norm_bwd_kernel, (unsigned)((n + 7) / 8), 256, 0, (cudaStream_t)stream, dY, Y, inv_norm, n, C, dX);
+  return check_launch("l2norm_bwd_kernel");
 }
 
 extern "C" int pcb_pdist_rowmin(const float* A, int64_t P, const float* B, int64_t S, int D, float* minval, int32_t* argmin,

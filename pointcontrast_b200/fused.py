@@ -577,7 +577,8 @@ def applicable(model, sinput):
 
 def _normalised(model, F):
     if getattr(model, "normalize_feature", False):       # `model/res16unet.py:262-266` (no epsilon)
-        return F / torch.norm(F, p=2, dim=1, keepdim=True)
+        from .losses import l2_normalize
+        return l2_normalize(F)
     return F
 
 

@@ -33,6 +33,34 @@ class _PointNCEFunction(torch.autograd.Function):
         return dq * g, dk * g, None
 
 
+class _L2NormFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        _lib.require_cuda(x)
+        x = x.contiguous()
+        n, C = x.shape
+        y = torch.empty_like(x)
+        inv = torch.empty(n, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            check(lib.pcb_l2norm_forward(ptr(x), n, C, ptr(y), ptr(inv), stream()))
+        ctx.save_for_backward(y, inv)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        y, inv = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = torch.empty_like(dy)
+        with torch.cuda.device(dy.device):
+            check(lib.pcb_l2norm_backward(ptr(dy), ptr(y), ptr(inv), y.shape[0], y.shape[1], ptr(dx), stream()))
+        return dx
+
+
+def l2_normalize(F):
+    """F / ||F||_2 per row, no epsilon (`model/res16unet.py:262-266`) -- one kernel forward, one backward."""
+    return _L2NormFunction.apply(F)
+
+
 def select_positives(pos_pairs, npos, generator=None):
     """`ddp_trainer.py:400-415`: one uniformly random key per unique query, then at most `npos` of them.
     pos_pairs: int tensor [P, 2] on the device, grouped by column 0.  Returns (q_rows, k_rows) int64."""

@@ -532,9 +532,7 @@ class MinkowskiNetwork(nn.Module):
             from . import fused
             if fused.applicable(self, args[0]):
                 x = args[0]
-                F = fused.run(self, x)
-                if getattr(self, "normalize_feature", False):        # `model/res16unet.py:262-266` (no epsilon)
-                    F = F / torch.norm(F, p=2, dim=1, keepdim=True)
+                F = fused._normalised(self, fused.run(self, x))      # `model/res16unet.py:262-266` (no epsilon)
                 return SparseTensor(F, coords_key=x.coords_key, coords_manager=x.coords_man)
         return super().__call__(*args, **kwargs)
 

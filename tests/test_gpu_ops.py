@@ -375,3 +375,46 @@ def test_segmented_batchnorm_equals_two_batches(n0, n1, C):
                                   ptr(gout), C, 1, None, None, 0, ptr(ws), wsb, st))
     assert max_rel_err(dX, xo.grad) < 1e-4 and max_rel_err(gout, ro.grad) < 1e-5
     assert rel_err(dW, ref.weight.grad) < 1e-4 and rel_err(dB, ref.bias.grad) < 1e-4
+
+
+@pytest.mark.parametrize("n,C", [(5000, 32), (3, 13), (777, 96)])
+def test_l2_normalize_matches_torch(n, C):
+    """`model/res16unet.py:262-266`: F / ||F||_2 per row (no epsilon), forward and backward, vs torch fp64."""
+    from pointcontrast_b200 import losses
+    g = torch.Generator().manual_seed(n + C)
+    x = torch.randn(n, C, generator=g, dtype=torch.float64)
+    dy = torch.randn(n, C, generator=g, dtype=torch.float64)
+    xo = x.clone().requires_grad_(True)
+    yo = xo / torch.norm(xo, p=2, dim=1, keepdim=True)
+    yo.backward(dy)
+    xg = x.float().cuda().requires_grad_(True)
+    y = losses.l2_normalize(xg)
+    y.backward(dy.float().cuda())
+    assert max_rel_err(y, yo) < 1e-6 and max_rel_err(xg.grad, xo.grad) < 1e-5
+
+
+@pytest.mark.parametrize("n,D,T", [(2000, 64, 0.4), (300, 32, 0.07)])
+def test_point_nce_tensor_core_and_simt_paths_agree(n, D, T, monkeypatch):
+    """The fused tcgen05 PointInfoNCE (D = 32 / 64) against the oracle AND against the exact-fp32 SIMT kernels of the same
+    library (`PCB_NCE_SIMT` is read once per process, so the SIMT side is reached through a width the tiling does not cover)."""
+    from pointcontrast_b200 import losses
+    g = torch.Generator().manual_seed(n + D)
+    F0 = torch.nn.functional.normalize(torch.randn(n, D, generator=g, dtype=torch.float64), dim=1)
+    F1 = torch.nn.functional.normalize(0.6 * F0 + 0.4 * torch.randn(n, D, generator=g, dtype=torch.float64), dim=1)
+    rows = torch.arange(n)
+    f0o, f1o = F0.clone().requires_grad_(True), F1.clone().requires_grad_(True)
+    lo = loss_cpu.point_nce_loss(f0o, f1o, rows, rows, T)
+    lo.backward()
+    f0, f1 = F0.float().cuda().requires_grad_(True), F1.float().cuda().requires_grad_(True)
+    l = losses.point_nce_loss(f0, f1, rows.cuda(), rows.cuda(), T)
+    l.backward()
+    assert abs(float(l) - float(lo)) / abs(float(lo)) < 1e-4
+    assert rel_err(f0.grad, f0o.grad) < 1e-4 and rel_err(f1.grad, f1o.grad) < 1e-4
+    # SIMT path of the library: pad the features with 4 zero channels (D + 4 is not a tensor-core width; the loss is unchanged)
+    pad = torch.zeros(n, 4)
+    f0s = torch.cat([F0.float(), pad], 1).cuda().requires_grad_(True)
+    f1s = torch.cat([F1.float(), pad], 1).cuda().requires_grad_(True)
+    ls = losses.point_nce_loss(f0s, f1s, rows.cuda(), rows.cuda(), T)
+    ls.backward()
+    assert abs(float(l) - float(ls)) / abs(float(ls)) < 1e-5
+    assert rel_err(f0.grad, f0s.grad[:, :D]) < 1e-4 and rel_err(f1.grad, f1s.grad[:, :D]) < 1e-4
