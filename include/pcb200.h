@@ -226,6 +226,7 @@ typedef struct pcb_unit {
 #define PCB_UNIT_FP16_FORWARD 2     /* activations travel as fp16 hi/lo planes (x_hi/x_lo, out_hi/out_lo) and wt_fwd holds fp16 tiles
                                        (pcb_weight_tile with PCB_PLANES_B_FP16): 2^-22 products in the forward pass; gradients
                                        (dz) and the data-gradient tiles stay bf16 hi/lo (fp32's exponent range) */
+#define PCB_UNIT_EVAL 4             /* forward only, eval-mode BatchNorm: normalise with running_mean / running_var (not updated) */
 size_t pcb_unit_ws_bytes(int K, int64_t n_in, int64_t n_out, int Cin, int Cout);
 int pcb_unit_forward(const pcb_unit* u, void* stream);
 int pcb_unit_backward(const pcb_unit* u, void* stream);

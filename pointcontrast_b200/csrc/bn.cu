@@ -312,6 +312,14 @@ inline void chunk_layout(int64_t n, int64_t n0, int R, int* chunks, int* chunks0
   *chunks = *chunks0 + (n0 < n ? chunks_of(n - n0, R) : 0);
 }
 
+// eval-mode BatchNorm: "statistics" = the running ones
+__global__ void bn_eval_stats_kernel(const float* __restrict__ running_mean, const float* __restrict__ running_var, int C, float eps,
+                                     float* __restrict__ mean, float* __restrict__ invstd) {
+  pdl_wait(); pdl_trigger();
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) { mean[c] = running_mean[c]; invstd[c] = 1.0f / sqrtf(running_var[c] + eps); }
+}
+
 inline int colsum_threads(int C) {       // (C/4) * row lanes, <= 256, at least one row lane
   int cv = C / 4;
   int rp = 256 / cv; if (rp < 1) rp = 1;
@@ -412,6 +420,12 @@ int bn_backward_impl(const float* dY, int lddy, const float* X, int ldx, const f
                                                                     invstd, gamma, sums, dX, lddx, gout, ldg, gout_mode,
                                                                     (__nv_bfloat16*)dXhi, (__nv_bfloat16*)dXlo, lds);
   return check_launch("bn_bwd_apply_kernel");
+}
+
+int bn_eval_stats_launch(const float* running_mean, const float* running_var, int C, float eps, float* mean, float* invstd, cudaStream_t st) {
+  PCB_ARG(running_mean && running_var && mean && invstd && C >= 1);
+  launch_kernel(bn_eval_stats_kernel, (C + 127) / 128, 128, 0, st, running_mean, running_var, C, eps, mean, invstd);
+  return check_launch("bn_eval_stats_kernel");
 }
 
 // Forward statistics fused into the reduction pass of an offset-split convolution: Y = sum of the nsplit partial planes

@@ -12,6 +12,7 @@ struct BnFuse { int64_t n0; float eps, momentum; float* mean; float* invstd; flo
 int conv_forward_split_impl(const uint16_t* Xhi, const uint16_t* Xlo, int lds, const int32_t* tbl, int64_t tbl_stride, const int32_t* kmap,
                             int K, int64_t n_out, int Cin, int Cout, const void* w_tiles, const float* bias, float* Y, int ldy, void* ws,
                             size_t ws_bytes, int flags, cudaStream_t st, const BnFuse* bn, int* bn_done);
+int bn_eval_stats_launch(const float* running_mean, const float* running_var, int C, float eps, float* mean, float* invstd, cudaStream_t st);
 int bn_backward_impl(const float* dY, int lddy, const float* X, int ldx, const float* relu_out, int ldm, const uint16_t* relu_hi, int ldmh,
                      int64_t n, int64_t n0, int C, const float* mean, const float* invstd, const float* gamma, float* dX, int lddx,
                      float* dgamma, float* dbeta, int accumulate_param_grads, float* gout, int ldg, int gout_mode, uint16_t* dXhi,
@@ -113,7 +114,7 @@ extern "C" int pcb_unit_forward(const pcb_unit* u, void* stream) {
   if (tensor_core_shape(u->Cin, u->Cout)) {
     PCB_ARG(u->x_hi && u->x_lo && u->wt_fwd);
     BnFuse bn{u->n0, u->eps, u->momentum, u->mean, u->invstd, u->running_mean, u->running_var, bn_ws, bn_bytes};
-    const bool fuse = !(u->flags & PCB_UNIT_SEPARATE_STATS);
+    const bool fuse = !(u->flags & (PCB_UNIT_SEPARATE_STATS | PCB_UNIT_EVAL));
     if (int e = conv_forward_split_impl(u->x_hi, u->x_lo, u->x_lds, u->fwd_tbl, u->fwd_stride, u->fwd_kmap, u->K, u->n_out, u->Cin, u->Cout,
                                         u->wt_fwd, nullptr, u->z_p, u->z_ld, u->ws, conv_bytes, f16 ? (PCB_PLANES_A_FP16 | PCB_PLANES_B_FP16) : 0,
                                         st, fuse ? &bn : nullptr, &have_stats)) return e;
@@ -122,7 +123,10 @@ extern "C" int pcb_unit_forward(const pcb_unit* u, void* stream) {
     if (int e = pcb_conv_forward(u->x_p, u->x_ld, u->fwd_tbl, u->fwd_stride, u->fwd_kmap, u->K, u->n_out, u->Cin, u->Cout, nullptr, nullptr,
                                  nullptr, nullptr, u->W, nullptr, u->z_p, u->z_ld, nullptr, 0, 0, stream)) return e;
   }
-  if (!have_stats) {
+  if (u->flags & PCB_UNIT_EVAL) {            // eval-mode BatchNorm (`downstream/semseg/lib/test.py:95-117`): normalise with the running statistics
+    PCB_ARG(u->n0 == u->n_out && u->running_mean && u->running_var);
+    if (int e = bn_eval_stats_launch(u->running_mean, u->running_var, u->Cout, u->eps, u->mean, u->invstd, st)) return e;
+  } else if (!have_stats) {
     if (int e = pcb_bn_stats_seg(u->z_p, u->z_ld, u->n_out, u->n0, u->Cout, u->eps, u->momentum, u->mean, u->invstd, u->running_mean,
                                  u->running_var, bn_ws, bn_bytes, stream)) return e;
   }

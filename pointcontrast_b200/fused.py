@@ -332,12 +332,13 @@ class Runner:
             assert residual.p, "a residual input needs its fp32 plane"
             u.res_p, u.res_ld = residual.p, residual.ld
         u.ws, u.ws_bytes = self.ws.data_ptr(), self.ws.numel()
-        u.flags = (1 if SEPARATE_STATS else 0) | (2 if me.FWD_FP16 else 0)
+        u.flags = (1 if SEPARATE_STATS else 0) | (2 if me.FWD_FP16 else 0) | (4 if self.eval_mode else 0)
         if me.PROFILE is not None:
             me.PROFILE.append(dict(kind="fwd", K=K, Cin=Cin, Cout=Cout, n_in=plan.n_in, n_out=plan.n_out, plan=plan, tc=tc))
         check(lib.pcb_unit_forward(ctypes.byref(u), self.st))
-        self.bns.append(bn)
-        self.units.append((u, conv, bn, a_in, out, plan, residual))
+        if not self.eval_mode:
+            self.bns.append(bn)
+            self.units.append((u, conv, bn, a_in, out, plan, residual))
         return out
 
     def _stat(self, C):
@@ -385,9 +386,11 @@ class Runner:
         cached[tuple(n)] = best
         return best
 
-    def forward(self, sinput, view0_rows=None, geom=None):
-        """`view0_rows`: the input is a `stack_views` tensor whose first `view0_rows` rows are view 0."""
+    def forward(self, sinput, view0_rows=None, geom=None, eval_mode=False):
+        """`view0_rows`: the input is a `stack_views` tensor whose first `view0_rows` rows are view 0.
+        `eval_mode`: forward only with eval-mode BatchNorm (running statistics); nothing is kept for a backward pass."""
         m = self.model
+        self.eval_mode = eval_mode
         feats = sinput.F
         _lib.require_cuda(feats)
         self.device = dev = feats.device
@@ -444,6 +447,9 @@ class Runner:
             for bn in self.bns:
                 bn.num_batches_tracked += g.calls
         self._fwd_hint = int(arena.total * 1.02) + (1 << 20)
+        if eval_mode:
+            self.units = self.arena = self.stats = None
+            return out_t, None
         tape = _Tape()
         tape.units, tape.arena, tape.x_last, tape.p_final, tape.stats, tape.geom, tape.ws = self.units, arena, x, p1[0], self.stats, g, self.ws
         self.units = self.arena = self.stats = None
@@ -573,6 +579,20 @@ def applicable_on(model, device):
 
 def applicable(model, sinput):
     return applicable_on(model, sinput.F.device)
+
+
+def applicable_eval(model, sinput):
+    """Inference (`model.eval()` under `torch.no_grad()`, `downstream/semseg/lib/test.py:95-117`): the same units, forward only."""
+    return (ENABLED and not model.training and not torch.is_grad_enabled() and sinput.F.is_cuda and me.CONV_IMPL == "tcgen05"
+            and not me.FORCE_SIMT and matches(model))
+
+
+def run_eval(model, sinput):
+    runner = model.__dict__.get("_fused_runner")
+    if runner is None:
+        runner = Runner(model)
+        model.__dict__["_fused_runner"] = runner
+    return runner.forward(sinput, None, None, eval_mode=True)[0]
 
 
 def _normalised(model, F):

@@ -530,6 +530,9 @@ class MinkowskiNetwork(nn.Module):
         kernels and schedule as this package's model.  Everything else goes through `forward` module by module."""
         if len(args) == 1 and not kwargs and isinstance(args[0], SparseTensor) and args[0].F.is_cuda:
             from . import fused
+            if fused.applicable_eval(self, args[0]):
+                x = args[0]
+                return SparseTensor(fused._normalised(self, fused.run_eval(self, x)), coords_key=x.coords_key, coords_manager=x.coords_man)
             if fused.applicable(self, args[0]):
                 x = args[0]
                 F = fused._normalised(self, fused.run(self, x))      # `model/res16unet.py:262-266` (no epsilon)
