@@ -107,7 +107,8 @@ int pcb_weight_prep(const float* W, int K, int Cin, int Cout, uint16_t* w_hi, ui
 #define PCB_CONV_ACCUMULATE 4  /* Y += result (pcb_conv_forward, tcgen05 path) / dW += result (pcb_conv_wgrad) */
 #define PCB_PLANES_A_FP16 8    /* split-operand calls: the GATHERED operand's planes are fp16 hi/lo (default: bf16 hi/lo) */
 #define PCB_PLANES_B_FP16 16   /* pcb_conv_forward_split: the weight tiles are fp16 x 2^10 (pcb_weight_tile with this flag);
-                                  pcb_conv_wgrad_split: the ROW-ALIGNED operand's planes are fp16 */
+                                  pcb_conv_wgrad_split: the ROW-ALIGNED operand's planes are fp16.  Both operands of a call must
+                                  use the same format (tcgen05.mma.kind::f16 rejects fp16 x bf16): set both flags or neither. */
 /* Small levels split the (offset, channel-chunk) loop over extra CTAs and reduce through `ws` (deterministic). */
 size_t pcb_conv_forward_ws_bytes(int K, int64_t n_out, int Cin, int Cout);
 int pcb_conv_forward(const float* X, int ldx, const int32_t* tbl, int64_t tbl_stride, const int32_t* kmap, int K,
@@ -156,7 +157,8 @@ int pcb_bn_backward(const float* dY, const float* X, int64_t n, int C, const flo
 /* Strided / row-segmented variants used by the fused network executor (pointcontrast_b200/fused.py).  All ld* are row strides
  * in floats (>= C, multiples of 4), so inputs/outputs may be column slices of wider (concatenated) buffers.
  *   apply   : Y = [relu]( (X-mean)*invstd*gamma+beta [+ residual] ), as fp32 (Y, may be NULL) and/or split planes (Yhi/Ylo);
- *             flags: PCB_BN_RELU, PCB_PLANES_A_FP16 (the planes are fp16 hi/lo instead of bf16 hi/lo)
+ *             flags: PCB_BN_RELU, PCB_PLANES_A_FP16 (Yhi/Ylo are fp16 hi/lo instead of bf16 hi/lo; Ybhi/Yblo, if non-NULL, then
+ *             receive the bf16 hi/lo planes as well)
  *   backward: g = dY * (relu_out > 0) if relu_out else dY;   dgamma/dbeta (+)= sum(g*xhat) / sum(g);
  *             dX = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat));   gout (=|+=) g  (gout_mode 0 none, 1 write, 2 add)
  *             -- gout is the gradient of the residual input of the forward unit; it may alias dY. */
@@ -169,7 +171,7 @@ int pcb_bn_stats_seg(const float* X, int ldx, int64_t n, int64_t n0, int C, floa
                      float* running_mean, float* running_var, void* ws, size_t ws_bytes, void* stream);
 int pcb_bn_apply_seg(const float* X, int ldx, int64_t n, int64_t n0, int C, const float* mean, const float* invstd,
                      const float* gamma, const float* beta, const float* residual, int ldr, int flags, float* Y, int ldy,
-                     uint16_t* Yhi, uint16_t* Ylo, int lds, void* stream);
+                     uint16_t* Yhi, uint16_t* Ylo, int lds, uint16_t* Ybhi, uint16_t* Yblo, void* stream);
 int pcb_bn_backward_seg(const float* dY, int lddy, const float* X, int ldx, const float* relu_out, int ldm, int64_t n, int64_t n0,
                         int C, const float* mean, const float* invstd, const float* gamma, float* dX, int lddx, float* dgamma,
                         float* dbeta, int accumulate_param_grads, float* gout, int ldg, int gout_mode, uint16_t* dXhi,
@@ -212,8 +214,11 @@ typedef struct pcb_unit {
   float eps, momentum;
   float* mean; float* invstd;                       /* [segments][Cout], written by forward, read by backward */
   const float* x_p; int32_t x_ld; const uint16_t* x_hi; const uint16_t* x_lo; int32_t x_lds;
+  const uint16_t* x_bhi; const uint16_t* x_blo;     /* PCB_UNIT_FP16_FORWARD: x once more as bf16 hi/lo planes (the weight gradient pairs it
+                                                       with the bf16 gradient planes: tcgen05.mma takes ONE format for both operands) */
   float* z_p; int32_t z_ld;
   float* out_p; int32_t out_ld; uint16_t* out_hi; uint16_t* out_lo; int32_t out_lds;
+  uint16_t* out_bhi; uint16_t* out_blo;             /* PCB_UNIT_FP16_FORWARD: bf16 hi/lo copy of `out` (row stride out_lds) */
   const float* res_p; int32_t res_ld;
   const float* g_p; int32_t g_ld;
   float* dz_p; uint16_t* dz_hi; uint16_t* dz_lo; int32_t dz_ld;
@@ -223,9 +228,12 @@ typedef struct pcb_unit {
   int32_t flags;                                    /* PCB_UNIT_* */
 } pcb_unit;
 #define PCB_UNIT_SEPARATE_STATS 1   /* forward: BatchNorm statistics always by a separate pass over z (cross-check of the fused reduce+statistics pass) */
-#define PCB_UNIT_FP16_FORWARD 2     /* activations travel as fp16 hi/lo planes (x_hi/x_lo, out_hi/out_lo) and wt_fwd holds fp16 tiles
-                                       (pcb_weight_tile with PCB_PLANES_B_FP16): 2^-22 products in the forward pass; gradients
-                                       (dz) and the data-gradient tiles stay bf16 hi/lo (fp32's exponent range) */
+#define PCB_UNIT_FP16_FORWARD 2     /* activations are gathered by the forward convolutions as fp16 hi/lo planes (x_hi/x_lo, out_hi/out_lo)
+                                       against fp16 weight tiles (pcb_weight_tile with PCB_PLANES_B_FP16): 2^-22 products in the
+                                       forward pass.  Gradients (dz) and the data-gradient tiles stay bf16 hi/lo (fp32's exponent
+                                       range); tcgen05.mma.kind::f16 rejects mixed fp16 x bf16 operands (illegal instruction,
+                                       profiles/probes/mixed_fmt_probe.cu), so every activation also carries bf16 hi/lo planes
+                                       (x_bhi/x_blo, out_bhi/out_blo) for the weight gradient. */
 #define PCB_UNIT_EVAL 4             /* forward only, eval-mode BatchNorm: normalise with running_mean / running_var (not updated) */
 size_t pcb_unit_ws_bytes(int K, int64_t n_in, int64_t n_out, int Cin, int Cout);
 int pcb_unit_forward(const pcb_unit* u, void* stream);

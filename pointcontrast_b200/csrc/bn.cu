@@ -205,7 +205,8 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, int chunks
 __global__ void bn_apply_kernel(const float* __restrict__ X, int ldx, int64_t n4, int cv, const float* __restrict__ mean,
                                 const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
                                 const float* __restrict__ residual, int ldr, int relu, float* __restrict__ Y, int ldy,
-                                __nv_bfloat16* __restrict__ Yhi, __nv_bfloat16* __restrict__ Ylo, int lds, int64_t n0, int fp16) {
+                                __nv_bfloat16* __restrict__ Yhi, __nv_bfloat16* __restrict__ Ylo, int lds, int64_t n0, int fp16,
+                                __nv_bfloat16* __restrict__ Ybhi, __nv_bfloat16* __restrict__ Yblo) {
   pdl_wait(); pdl_trigger();
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n4) return;
@@ -228,6 +229,7 @@ __global__ void bn_apply_kernel(const float* __restrict__ X, int ldx, int64_t n4
     if (fp16) store_split4_f16(y, Yhi + row * lds + c4 * 4, Ylo + row * lds + c4 * 4);
     else store_split4(y, Yhi + row * lds + c4 * 4, Ylo + row * lds + c4 * 4);
   }
+  if (Ybhi) store_split4(y, Ybhi + row * lds + c4 * 4, Yblo + row * lds + c4 * 4);
 }
 
 // dgamma = sum(dY*xhat), dbeta = sum(dY) over ALL rows (both segments: the parameters are shared);
@@ -370,21 +372,23 @@ extern "C" int pcb_split_rows(const float* X, int ldx, int64_t n, int C, uint16_
 
 extern "C" int pcb_bn_apply_seg(const float* X, int ldx, int64_t n, int64_t n0, int C, const float* mean, const float* invstd,
                                 const float* gamma, const float* beta, const float* residual, int ldr, int flags, float* Y, int ldy,
-                                uint16_t* Yhi, uint16_t* Ylo, int lds, void* stream) {
+                                uint16_t* Yhi, uint16_t* Ylo, int lds, uint16_t* Ybhi, uint16_t* Yblo, void* stream) {
   const int relu = flags & PCB_BN_RELU;
   PCB_ARG(n >= 0 && n0 >= 0 && n0 <= n && C >= 4 && C % 4 == 0 && ldx % 4 == 0 && ldx >= C && (!Y || (ldy % 4 == 0 && ldy >= C)));
   if (n == 0) return PCB_OK;
   PCB_ARG(X && (Y || Yhi) && mean && invstd && gamma && beta && (!residual || (ldr >= C && ldr % 4 == 0)));
   PCB_ARG(!Yhi || (Ylo && lds >= C && lds % 4 == 0));
+  PCB_ARG(!Ybhi || (Yblo && Yhi));
   int64_t n4 = n * (C / 4);
   launch_kernel(bn_apply_kernel, (unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream, X, ldx, n4, C / 4, mean, invstd, gamma, beta, residual,
-                ldr, relu, Y, ldy, (__nv_bfloat16*)Yhi, (__nv_bfloat16*)Ylo, lds, n0, (flags & PCB_PLANES_A_FP16) ? 1 : 0);
+                ldr, relu, Y, ldy, (__nv_bfloat16*)Yhi, (__nv_bfloat16*)Ylo, lds, n0, (flags & PCB_PLANES_A_FP16) ? 1 : 0,
+                (__nv_bfloat16*)Ybhi, (__nv_bfloat16*)Yblo);
   return check_launch("bn_apply_kernel");
 }
 
 extern "C" int pcb_bn_apply(const float* X, int64_t n, int C, const float* mean, const float* invstd, const float* gamma,
                             const float* beta, const float* residual, int relu, float* Y, void* stream) {
-  return pcb_bn_apply_seg(X, C, n, n, C, mean, invstd, gamma, beta, residual, C, relu, Y, C, nullptr, nullptr, 0, stream);
+  return pcb_bn_apply_seg(X, C, n, n, C, mean, invstd, gamma, beta, residual, C, relu, Y, C, nullptr, nullptr, 0, nullptr, nullptr, stream);
 }
 
 namespace pcb {

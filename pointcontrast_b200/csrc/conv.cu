@@ -293,38 +293,40 @@ __global__ void conv_simt_kernel(const float* __restrict__ X, int ldx, const int
   Y[j * ldy + co] = acc;
 }
 
-// The stem layer (CIN = 3 -> 32 channels, exact fp32): one warp per output row, lane = output channel.  All K table entries of the
-// row are fetched first, then all gathered inputs (branch-free, clamped index), then the FMAs: K + K*CIN independent loads in flight
-// per warp instead of a dependent table -> feature chain per offset.  Weights [K][CIN][32] sit in shared memory.
+// The stem layer (CIN = 3 -> 32 channels, exact fp32).  Thread = output row (consecutive threads -> consecutive rows: the table reads
+// tbl[k][j] are coalesced), all 32 output channels of the row in registers, weights [K][CIN][32] broadcast from shared memory.
 template <int CIN>
-__global__ void __launch_bounds__(256) conv_stem_kernel(const float* __restrict__ X, int ldx, const int32_t* __restrict__ tbl,
+__global__ void __launch_bounds__(128) conv_stem_kernel(const float* __restrict__ X, int ldx, const int32_t* __restrict__ tbl,
                                                         int64_t tbl_stride, KMap kmap, int K, int64_t n_out, const float* __restrict__ W,
                                                         const float* __restrict__ bias, float* __restrict__ Y, int ldy) {
   pdl_wait(); pdl_trigger();
-  __shared__ float s_w[PCB_MAX_KERNEL_VOLUME * CIN * 32];
-  for (int e = threadIdx.x; e < K * CIN * 32; e += 256) s_w[e] = W[e];
+  __shared__ __align__(16) float s_w[PCB_MAX_KERNEL_VOLUME * CIN * 32];
+  for (int e = threadIdx.x; e < K * CIN * 32; e += 128) s_w[e] = W[e];
   __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const int64_t j = blockIdx.x * 8ll + (threadIdx.x >> 5);
+  const int64_t j = blockIdx.x * 128ll + threadIdx.x;
   if (j >= n_out) return;
-  int idx[PCB_MAX_KERNEL_VOLUME];
+  float acc[32];
 #pragma unroll
-  for (int k = 0; k < PCB_MAX_KERNEL_VOLUME; ++k) idx[k] = k < K ? __ldg(tbl + (int64_t)kmap.v[k] * tbl_stride + j) : -1;
-  float x[PCB_MAX_KERNEL_VOLUME][CIN];
+  for (int co = 0; co < 32; ++co) acc[co] = bias ? bias[co] : 0.f;
+  for (int k = 0; k < K; ++k) {
+    const int idx = __ldg(tbl + (int64_t)kmap.v[k] * tbl_stride + j);
+    if (idx < 0) continue;
+    const float* xr = X + (int64_t)idx * ldx;
 #pragma unroll
-  for (int k = 0; k < PCB_MAX_KERNEL_VOLUME; ++k) {
-    const float* xr = X + (int64_t)(idx[k] >= 0 ? idx[k] : 0) * ldx;
+    for (int c = 0; c < CIN; ++c) {
+      const float x = __ldg(xr + c);
+      const float4* w = reinterpret_cast<const float4*>(s_w + (k * CIN + c) * 32);
 #pragma unroll
-    for (int c = 0; c < CIN; ++c) { const float v = __ldg(xr + c); x[k][c] = idx[k] >= 0 ? v : 0.f; }
-  }
-  float acc = bias ? bias[lane] : 0.f;
-#pragma unroll
-  for (int k = 0; k < PCB_MAX_KERNEL_VOLUME; ++k)
-    if (k < K) {
-#pragma unroll
-      for (int c = 0; c < CIN; ++c) acc = fmaf(x[k][c], s_w[(k * CIN + c) * 32 + lane], acc);
+      for (int q = 0; q < 8; ++q) {
+        const float4 v = w[q];
+        acc[q * 4 + 0] = fmaf(x, v.x, acc[q * 4 + 0]); acc[q * 4 + 1] = fmaf(x, v.y, acc[q * 4 + 1]);
+        acc[q * 4 + 2] = fmaf(x, v.z, acc[q * 4 + 2]); acc[q * 4 + 3] = fmaf(x, v.w, acc[q * 4 + 3]);
+      }
     }
-  Y[j * ldy + lane] = acc;
+  }
+  float4* yo = reinterpret_cast<float4*>(Y + j * ldy);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) yo[q] = make_float4(acc[q * 4], acc[q * 4 + 1], acc[q * 4 + 2], acc[q * 4 + 3]);
 }
 
 // --------------------------------------------------------------------------------------------- weight gradient (tensor cores)
@@ -525,50 +527,56 @@ __global__ void wgrad_simt_kernel(const WgradArgs p) {
   }
 }
 
-// Stem layer (3 input channels -> 32): exact fp32.  One warp per table row, lane = output channel, all K offsets of the row
-// handled in registers (K x Ca accumulators per lane), block-level reduction in shared memory, one partial tile per CTA.
+// Stem layer (CA = 3 input channels -> 32), exact fp32, deterministic.  A CTA walks tiles of 64 table rows: the gathered inputs of
+// the tile, xs[row][k][c] (table reads coalesced along the rows), and the 64 x 32 dY tile are staged in shared memory; thread
+// (kc, co) then owns output dW[k][c][co] for ~K*CA/8 values of kc and accumulates over the tile's rows from shared memory
+// (xs broadcast within a warp, dY conflict-free).  One partial tile [K*CA*32] per CTA, summed by wgrad_reduce_kernel.
 template <int CA>
 __global__ void __launch_bounds__(256) wgrad_stem_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
                                                          const int32_t* __restrict__ tbl, int64_t tbl_stride, int K, int64_t n_out,
                                                          int rows_per_block, float* __restrict__ partial) {
   pdl_wait(); pdl_trigger();
-  __shared__ float s_acc[PCB_MAX_KERNEL_VOLUME * CA * 32];
+  constexpr int TR = 64, KC = PCB_MAX_KERNEL_VOLUME * CA, PER = (KC + 7) / 8;
+  __shared__ float s_x[TR][KC + 1];
+  __shared__ float s_dy[TR][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int e = threadIdx.x; e < K * CA * 32; e += 256) s_acc[e] = 0.f;
-  __syncthreads();
-  float acc[PCB_MAX_KERNEL_VOLUME][CA];
+  const int nkc = K * CA;
+  float acc[PER];
 #pragma unroll
-  for (int k = 0; k < PCB_MAX_KERNEL_VOLUME; ++k)
-#pragma unroll
-    for (int c = 0; c < CA; ++c) acc[k][c] = 0.f;
+  for (int i = 0; i < PER; ++i) acc[i] = 0.f;
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
   const int64_t r1 = min(n_out, r0 + rows_per_block);
-  for (int64_t j = r0 + warp; j < r1; j += 8) {
-    const float dy = __ldg(B + j * ldb + lane);
-    int idx[PCB_MAX_KERNEL_VOLUME];       // all table entries of the row first, then all gathered inputs (branch-free): independent loads
+  for (int64_t t0 = r0; t0 < r1; t0 += TR) {
+    const int rows = (int)min((int64_t)TR, r1 - t0);
+    __syncthreads();
+    for (int e = threadIdx.x; e < K * TR; e += 256) {          // (k, row): consecutive threads -> consecutive rows of one table row
+      const int k = e / TR, r = e - k * TR;
+      int idx = -1;
+      if (r < rows) idx = __ldg(tbl + (int64_t)k * tbl_stride + t0 + r);
+      const float* ar = A + (int64_t)(idx >= 0 ? idx : 0) * lda;
 #pragma unroll
-    for (int k = 0; k < PCB_MAX_KERNEL_VOLUME; ++k) idx[k] = k < K ? __ldg(tbl + (int64_t)k * tbl_stride + j) : -1;
-#pragma unroll
-    for (int k = 0; k < PCB_MAX_KERNEL_VOLUME; ++k) {
-      const float* ar = A + (int64_t)(idx[k] >= 0 ? idx[k] : 0) * lda;
-      const float w = idx[k] >= 0 ? dy : 0.f;
-#pragma unroll
-      for (int c = 0; c < CA; ++c) acc[k][c] = fmaf(__ldg(ar + c), w, acc[k][c]);
+      for (int c = 0; c < CA; ++c) s_x[r][k * CA + c] = idx >= 0 ? __ldg(ar + c) : 0.f;
     }
-  }
-  for (int w = 0; w < 8; ++w) {          // warp after warp, in a fixed order: deterministic (no shared-memory atomics)
-    if (warp == w) {
-#pragma unroll
-      for (int k = 0; k < PCB_MAX_KERNEL_VOLUME; ++k)
-        if (k < K) {
-#pragma unroll
-          for (int c = 0; c < CA; ++c) s_acc[(k * CA + c) * 32 + lane] += acc[k][c];
-        }
+    for (int e = threadIdx.x; e < TR * 32; e += 256) {
+      const int r = e >> 5, co = e & 31;
+      s_dy[r][co] = r < rows ? __ldg(B + (t0 + r) * ldb + co) : 0.f;
     }
     __syncthreads();
+    for (int r = 0; r < rows; ++r) {
+      const float dy = s_dy[r][lane];
+#pragma unroll
+      for (int i = 0; i < PER; ++i) {
+        const int kc = warp + 8 * i;
+        if (kc < nkc) acc[i] = fmaf(s_x[r][kc], dy, acc[i]);
+      }
+    }
   }
-  float* out = partial + (int64_t)blockIdx.x * K * CA * 32;
-  for (int e = threadIdx.x; e < K * CA * 32; e += 256) out[e] = s_acc[e];
+  float* out = partial + (int64_t)blockIdx.x * nkc * 32;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int kc = warp + 8 * i;
+    if (kc < nkc) out[kc * 32 + lane] = acc[i];
+  }
 }
 
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int64_t n, float* __restrict__ dW, int accumulate) {
@@ -711,7 +719,7 @@ extern "C" int pcb_conv_forward(const float* X, int ldx, const int32_t* tbl, int
     if (flags & PCB_CONV_ACCUMULATE) { set_error("PCB_CONV_ACCUMULATE needs the tcgen05 path"); return PCB_ERR_ARG; }
     if (!w_f32) { set_error("pcb_conv_forward: SIMT path needs w_f32 (Cin=%d Cout=%d)", Cin, Cout); return PCB_ERR_ARG; }
     if (Cin == 3 && Cout == 32) {         // the stem layer
-      launch_kernel(conv_stem_kernel<3>, (unsigned)((n_out + 7) / 8), 256, 0, st, X, ldx, tbl, tbl_stride, km, K, n_out, w_f32, bias, Y, ldy);
+      launch_kernel(conv_stem_kernel<3>, (unsigned)((n_out + 127) / 128), 128, 0, st, X, ldx, tbl, tbl_stride, km, K, n_out, w_f32, bias, Y, ldy);
       return check_launch("conv_stem_kernel");
     }
     int64_t total = n_out * Cout;
@@ -776,7 +784,7 @@ extern "C" int pcb_conv_wgrad(const float* A, int lda, const float* B, int ldb, 
     PCB_ARG(blocks >= 1);
     int nb = blocks < 2 * num_sms() ? blocks : 2 * num_sms();
     int64_t rpb = (n_out + nb - 1) / nb;
-    rpb = (rpb + 7) / 8 * 8;
+    rpb = (rpb + 63) / 64 * 64;
     nb = (int)((n_out + rpb - 1) / rpb);
     launch_kernel(wgrad_stem_kernel<3>, nb, 256, 0, st, A, lda, B, ldb, tbl, tbl_stride, K, n_out, (int)rpb, (float*)ws);
     if (int e = check_launch("wgrad_stem_kernel")) return e;
@@ -955,6 +963,8 @@ extern "C" int pcb_conv_wgrad_split(const uint16_t* Ahi, const uint16_t* Alo, in
     return PCB_OK;
   }
   PCB_ARG(Ahi && Alo && Bhi && Blo && tbl && ws && tbl_stride >= n_out);
+  // tcgen05.mma.kind::f16 takes ONE 16-bit format for both operands (fp16 x bf16 is an illegal instruction)
+  PCB_ARG(((flags & PCB_PLANES_A_FP16) != 0) == ((flags & PCB_PLANES_B_FP16) != 0));
   ProfScope prof(st, 1);
   const int splits = wgrad_split_splits(K, n_out, Ca, Cb);
   PCB_ARG(ws_bytes >= (size_t)splits * nW * sizeof(float));

@@ -104,6 +104,7 @@ extern "C" size_t pcb_unit_ws_bytes(int K, int64_t n_in, int64_t n_out, int Cin,
 extern "C" int pcb_unit_forward(const pcb_unit* u, void* stream) {
   PCB_ARG(u && u->K >= 1 && u->K <= PCB_MAX_KERNEL_VOLUME && u->n_out >= 1 && u->n_in >= 1 && u->n0 >= 1 && u->n0 <= u->n_out);
   PCB_ARG(u->fwd_tbl && u->z_p && u->out_hi && u->out_lo && u->mean && u->invstd && u->gamma && u->beta && u->ws);
+  PCB_ARG(!(u->flags & PCB_UNIT_FP16_FORWARD) || (u->flags & PCB_UNIT_EVAL) || (u->out_bhi && u->out_blo));
   PCB_ARG(u->ws_bytes >= pcb_unit_ws_bytes(u->K, u->n_in, u->n_out, u->Cin, u->Cout));
   cudaStream_t st = (cudaStream_t)stream;
   const size_t conv_bytes = conv_part_bytes(u->K, u->n_in, u->n_out, u->Cin, u->Cout);
@@ -131,7 +132,8 @@ extern "C" int pcb_unit_forward(const pcb_unit* u, void* stream) {
                                  u->running_var, bn_ws, bn_bytes, stream)) return e;
   }
   return pcb_bn_apply_seg(u->z_p, u->z_ld, u->n_out, u->n0, u->Cout, u->mean, u->invstd, u->gamma, u->beta, u->res_p, u->res_ld,
-                          (u->relu ? PCB_BN_RELU : 0) | (f16 ? PCB_PLANES_A_FP16 : 0), u->out_p, u->out_ld, u->out_hi, u->out_lo, u->out_lds, stream);
+                          (u->relu ? PCB_BN_RELU : 0) | (f16 ? PCB_PLANES_A_FP16 : 0), u->out_p, u->out_ld, u->out_hi, u->out_lo, u->out_lds,
+                          f16 ? u->out_bhi : nullptr, f16 ? u->out_blo : nullptr, stream);
 }
 
 extern "C" int pcb_unit_backward(const pcb_unit* u, void* stream) {
@@ -151,13 +153,15 @@ extern "C" int pcb_unit_backward(const pcb_unit* u, void* stream) {
                                u->dz_hi, u->dz_lo, u->dz_ld, bn_ws, u->ws_bytes - conv_bytes, st)) return e;
   // 2. weight gradient, accumulated into dW (the flat parameter-gradient buffer)
   if (tc) {
+    // the activation operand as bf16 hi/lo planes (its fp16 planes serve the forward pass only): both MMA operands share one format
+    const uint16_t* xh = f16 ? u->x_bhi : u->x_hi;
+    const uint16_t* xl = f16 ? u->x_blo : u->x_lo;
+    PCB_ARG(xh && xl);
     const uint16_t *Ahi, *Alo, *Bhi, *Blo; int lda, ldb, Ca, Cb, tr; int64_t rows;
-    if (u->wg_gather_x) { Ahi = u->x_hi; Alo = u->x_lo; lda = u->x_lds; Bhi = u->dz_hi; Blo = u->dz_lo; ldb = u->dz_ld; Ca = u->Cin; Cb = u->Cout; tr = 0; rows = u->n_out; }
-    else { Ahi = u->dz_hi; Alo = u->dz_lo; lda = u->dz_ld; Bhi = u->x_hi; Blo = u->x_lo; ldb = u->x_lds; Ca = u->Cout; Cb = u->Cin; tr = 1; rows = u->n_in; }
-    // the activation operand (x) is fp16 hi/lo when the forward pass ran on fp16 planes; the gradient operand (dz) is always bf16 hi/lo
-    const int fmt = !f16 ? 0 : (u->wg_gather_x ? PCB_PLANES_A_FP16 : PCB_PLANES_B_FP16);
+    if (u->wg_gather_x) { Ahi = xh; Alo = xl; lda = u->x_lds; Bhi = u->dz_hi; Blo = u->dz_lo; ldb = u->dz_ld; Ca = u->Cin; Cb = u->Cout; tr = 0; rows = u->n_out; }
+    else { Ahi = u->dz_hi; Alo = u->dz_lo; lda = u->dz_ld; Bhi = xh; Blo = xl; ldb = u->x_lds; Ca = u->Cout; Cb = u->Cin; tr = 1; rows = u->n_in; }
     if (int e = pcb_conv_wgrad_split(Ahi, Alo, lda, Bhi, Blo, ldb, u->wg_tbl, u->wg_stride, u->K, rows, Ca, Cb, u->dW, tr, u->ws, conv_bytes,
-                                     PCB_CONV_ACCUMULATE | fmt, stream)) return e;
+                                     PCB_CONV_ACCUMULATE, stream)) return e;
   } else {
     PCB_ARG(u->wg_gather_x);
     if (int e = pcb_conv_wgrad(u->x_p, u->x_ld, u->dz_p, u->dz_ld, u->wg_tbl, u->wg_stride, u->K, u->n_out, u->Cin, u->Cout, u->dW, 0, u->ws,

@@ -183,29 +183,43 @@ class Arena:
         return p
 
 
+def _grow_hint(old, used):
+    """Arena size for the next pass: never shrinks and moves in 64 MiB steps, so that after a few steps every pass asks the
+    caching allocator for the SAME block size (alternating batch sizes would otherwise leave it a zoo of multi-GB blocks)."""
+    step = 64 << 20
+    need = (int(used * 1.03) + step - 1) // step * step
+    return max(old, need)
+
+
 class Buf:
     """Matrix [n, C] with row stride ld.  `p`: fp32 storage (or 0), `hi`/`lo`: the same values as bf16 split planes (or 0)
     -- the operand format of the tensor-core kernels.  Storage belongs to an Arena (or `owner` keeps a tensor alive)."""
-    __slots__ = ("owner", "p", "hi", "lo", "n", "C", "ld", "slot", "_grad", "parent", "col", "device")
+    __slots__ = ("owner", "p", "hi", "lo", "bh", "bl", "n", "C", "ld", "slot", "_grad", "parent", "col", "device")
 
-    def __init__(self, owner, p, n, C, ld, device, hi=0, lo=0, parent=None, col=0):
+    def __init__(self, owner, p, n, C, ld, device, hi=0, lo=0, parent=None, col=0, bh=0, bl=0):
         self.owner, self.p, self.hi, self.lo, self.n, self.C, self.ld, self.device = owner, p, hi, lo, n, C, ld, device
+        self.bh, self.bl = bh, bl             # me.FWD_FP16: hi/lo are fp16 planes (forward gathers), bh/bl the bf16 planes (weight gradient)
         self.parent, self.col = parent, col
         self._grad = None
         self.slot = parent.slot if parent is not None else [False]     # [gradient buffer initialised?]
 
     @staticmethod
-    def new(arena, n, C, fp32=True, split=False):
+    def new(arena, n, C, fp32=True, split=False, dual=False):
+        """split: 16-bit hi/lo planes; dual: the activation format of me.FWD_FP16 (fp16 hi/lo + bf16 hi/lo)."""
         p = arena.alloc(4 * n * C) if fp32 else 0
-        hi = lo = 0
+        hi = lo = bh = bl = 0
         if split:
-            hi = arena.alloc(4 * n * C)
+            hi = arena.alloc((8 if dual else 4) * n * C)
             lo = hi + 2 * n * C
-        return Buf(None, p, n, C, C, arena.device, hi, lo)
+            if dual:
+                bh = lo + 2 * n * C
+                bl = bh + 2 * n * C
+        return Buf(None, p, n, C, C, arena.device, hi, lo, bh=bh, bl=bl)
 
     def cols(self, c0, C):
         return Buf(self.owner, self.p + 4 * c0 if self.p else 0, self.n, C, self.ld, self.device, self.hi + 2 * c0 if self.hi else 0,
-                   self.lo + 2 * c0 if self.lo else 0, parent=self, col=c0)
+                   self.lo + 2 * c0 if self.lo else 0, parent=self, col=c0, bh=self.bh + 2 * c0 if self.bh else 0,
+                   bl=self.bl + 2 * c0 if self.bl else 0)
 
     def grad(self, arena):
         """fp32 gradient buffer with the same geometry (column slices share their parent's buffer)."""
@@ -281,9 +295,10 @@ class Runner:
         if tc:
             wsb = lib.pcb_conv_wgrad_split_ws_bytes(K, rows, Ca, Cb)
             ws = me.workspace(wsb, self.device, slot=0)
-            fmt = 0 if not me.FWD_FP16 else (me.PLANES_A_FP16 if plan.wg_gather_x else me.PLANES_B_FP16)      # the activation operand
-            check(lib.pcb_conv_wgrad_split(A.hi, A.lo, A.ld, B.hi, B.lo, B.ld, ptr(plan.wg_tbl), plan.wg_tbl.shape[1], K, rows, Ca, Cb,
-                                           kern.grad.data_ptr(), tr, ptr(ws), wsb, 4 | fmt, stream()))
+            pl = lambda b: (b.bh, b.bl) if b.bh else (b.hi, b.lo)          # activations: their bf16 planes (gradients only have those)
+            (ah, al), (bh, bl) = pl(A), pl(B)
+            check(lib.pcb_conv_wgrad_split(ah, al, A.ld, bh, bl, B.ld, ptr(plan.wg_tbl), plan.wg_tbl.shape[1], K, rows, Ca, Cb,
+                                           kern.grad.data_ptr(), tr, ptr(ws), wsb, 4, stream()))
         else:
             wsb = lib.pcb_conv_wgrad_ws_bytes(K, rows, Ca, Cb)
             ws = me.workspace(wsb, self.device, slot=0)
@@ -303,7 +318,7 @@ class Runner:
         tc = Cin % 32 == 0 and Cout % 32 == 0
         z = Buf.new(arena, n, Cout)
         if out is None:
-            out = Buf.new(arena, n, Cout, fp32=need_f32, split=True)
+            out = Buf.new(arena, n, Cout, fp32=need_f32, split=True, dual=self.dual)
         u = PcbUnit()
         u.n_in, u.n_out, u.n0 = plan.n_in, n, n0
         u.K, u.Cin, u.Cout, u.relu = K, Cin, Cout, 1 if relu else 0
@@ -315,6 +330,8 @@ class Runner:
             tiles = conv._prepared.tiles(kern)
             u.wt_fwd, u.wt_dg = tiles[0].data_ptr(), tiles[1].data_ptr()
             u.x_hi, u.x_lo, u.x_lds = a_in.hi, a_in.lo, a_in.ld
+            if a_in.bh:
+                u.x_bhi, u.x_blo = a_in.bh, a_in.bl
         if a_in.p:
             u.x_p, u.x_ld = a_in.p, a_in.ld
         u.gamma, u.beta = bn.weight.data_ptr(), bn.bias.data_ptr()
@@ -328,6 +345,8 @@ class Runner:
         if out.p:
             u.out_p, u.out_ld = out.p, out.ld
         u.out_hi, u.out_lo, u.out_lds = out.hi, out.lo, out.ld
+        if out.bh:
+            u.out_bhi, u.out_blo = out.bh, out.bl
         if residual is not None:
             assert residual.p, "a residual input needs its fp32 plane"
             u.res_p, u.res_ld = residual.p, residual.ld
@@ -391,6 +410,7 @@ class Runner:
         `eval_mode`: forward only with eval-mode BatchNorm (running statistics); nothing is kept for a backward pass."""
         m = self.model
         self.eval_mode = eval_mode
+        self.dual = me.FWD_FP16 and not eval_mode          # bf16 copies of the activations are only needed by the weight gradient
         feats = sinput.F
         _lib.require_cuda(feats)
         self.device = dev = feats.device
@@ -419,10 +439,10 @@ class Runner:
             fin = m.final
             fin_tc = fin.in_channels % 32 == 0 and fin.out_channels % 32 == 0
             # concatenation buffers (left = decoder branch, right = encoder skip); consumed by convolutions only: split planes
-            cat8 = Buf.new(arena, n[0], P[7] + m.INIT_DIM, fp32=False, split=True)
-            cat7 = Buf.new(arena, n[1], P[6] + P[0], fp32=False, split=True)
-            cat6 = Buf.new(arena, n[2], P[5] + P[1], fp32=False, split=True)
-            cat5 = Buf.new(arena, n[3], P[4] + P[2], fp32=False, split=True)
+            cat8 = Buf.new(arena, n[0], P[7] + m.INIT_DIM, fp32=False, split=True, dual=self.dual)
+            cat7 = Buf.new(arena, n[1], P[6] + P[0], fp32=False, split=True, dual=self.dual)
+            cat6 = Buf.new(arena, n[2], P[5] + P[1], fp32=False, split=True, dual=self.dual)
+            cat5 = Buf.new(arena, n[3], P[4] + P[2], fp32=False, split=True, dual=self.dual)
             out_p1 = self._unit(m.conv0p1s1, m.bn0, a0, p0, True, out=cat8.cols(P[7], m.INIT_DIM))
             x = self._unit(m.conv1p1s2, m.bn1, out_p1, down[0], True, need_f32=m.block1[0].downsample is None)
             b1 = self._stage(m.block1, x, p3[1], p1[1], out=cat7.cols(P[6], P[0]))
@@ -446,7 +466,7 @@ class Runner:
                        bias=fin.bias.detach().reshape(-1) if fin.bias is not None else None, plan=p1[0])
             for bn in self.bns:
                 bn.num_batches_tracked += g.calls
-        self._fwd_hint = int(arena.total * 1.02) + (1 << 20)
+        self._fwd_hint = _grow_hint(self._fwd_hint, arena.total)
         if eval_mode:
             self.units = self.arena = self.stats = None
             return out_t, None
@@ -515,7 +535,7 @@ class Runner:
                 check(lib.pcb_unit_backward(ctypes.byref(u), st))
                 if after_unit is not None:
                     after_unit(conv)
-            self._bwd_hint = int(arena.total * 1.02) + (1 << 20)
+            self._bwd_hint = _grow_hint(self._bwd_hint, arena.total)
             # the arenas (and the geometry's tables) are released here, in stream order after the last kernel that reads them
 
 

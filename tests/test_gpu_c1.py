@@ -66,8 +66,8 @@ def test_direct_epilogue_conv_at_c1_rows(cin, cout):
     yo.backward(dy)
     # CUDA path through the C ABI
     Wd = W.cuda()
-    ft = torch.empty(lib.pcb_weight_tile_bytes(27, cin, cout, 0), dtype=torch.uint8, device="cuda")
-    dt = torch.empty(lib.pcb_weight_tile_bytes(27, cin, cout, 1), dtype=torch.uint8, device="cuda")
+    ft = torch.zeros(lib.pcb_weight_tile_bytes(27, cin, cout, 0), dtype=torch.uint8, device="cuda")
+    dt = torch.zeros(lib.pcb_weight_tile_bytes(27, cin, cout, 1), dtype=torch.uint8, device="cuda")
     check(lib.pcb_weight_tile(ptr(Wd), 27, cin, cout, ptr(ft), ptr(dt), 0, stream()))
     ws = torch.empty(256, dtype=torch.uint8, device="cuda")
     X = x.float().cuda(); DY = dy.float().cuda()
@@ -97,7 +97,7 @@ def test_direct_epilogue_conv_at_c1_rows(cin, cout):
     torch.cuda.synchronize()
     assert max_rel_err(dW - 0.125, oconv.kernel.grad) < TOL and rel_err(dW - 0.125, oconv.kernel.grad) < TOL / 10
     # fp16 hi/lo activation planes x fp16 weight tiles (the fused executor's forward format, PCB_FWD_FP16): 2^-22 products
-    ft16 = torch.empty_like(ft); dt16 = torch.empty_like(dt)
+    ft16 = torch.zeros_like(ft); dt16 = torch.zeros_like(dt)
     check(lib.pcb_weight_tile(ptr(Wd), 27, cin, cout, ptr(ft16), ptr(dt16), 16, stream()))
     assert torch.equal(dt16, dt)                                   # the data-gradient tiles stay bf16
     Xs16 = _split(X, 8)
@@ -106,13 +106,8 @@ def test_direct_epilogue_conv_at_c1_rows(cin, cout):
                                      ptr(bias.cuda()), ptr(y16), cout, ptr(ws), 256, 8 | 16, stream()))
     e_bf16, e_fp16 = rel_err(y, yo), rel_err(y16, yo)
     assert e_fp16 < 0.2 * e_bf16 and max_rel_err(y16, yo) < 1e-5, (e_bf16, e_fp16)
-    # weight gradient with MIXED operand formats: gathered activations fp16 hi/lo, row-aligned gradients bf16 hi/lo
-    dW16 = torch.zeros((27, cin, cout), device="cuda")
-    check(lib.pcb_conv_wgrad_split(Xs16[0].data_ptr(), Xs16[1].data_ptr(), cin, DYs[0].data_ptr(), DYs[1].data_ptr(), cout, ptr(plan.wg_tbl),
-                                   plan.wg_tbl.shape[1], 27, n, cin, cout, ptr(dW16), 0, ptr(wws), wsb, 4 | 8, stream()))
-    torch.cuda.synchronize()
-    assert max_rel_err(dW16, oconv.kernel.grad) < TOL and rel_err(dW16, oconv.kernel.grad) <= rel_err(dW - 0.125, oconv.kernel.grad) * 1.05
-
+    # (tcgen05.mma rejects mixed fp16 x bf16 operands -- profiles/probes/mixed_fmt_probe.cu -- so the weight gradient keeps reading
+    #  the bf16 planes of the activations, checked above)
 
 # ----------------------------------------------------------------------------------------------- one full C1 pair
 def _oracle(state, batch, dtype):

@@ -356,7 +356,7 @@ def test_segmented_batchnorm_equals_two_batches(n0, n1, C):
     hi = torch.empty(n, C, dtype=torch.bfloat16, device=dev); lo = torch.empty(n, C, dtype=torch.bfloat16, device=dev)
     st = stream()
     check(lib.pcb_bn_stats_seg(ptr(X), C, n, n0, C, 1e-5, 0.1, ptr(mean), ptr(invstd), ptr(rm), ptr(rv), ptr(ws), wsb, st))
-    check(lib.pcb_bn_apply_seg(ptr(X), C, n, n0, C, ptr(mean), ptr(invstd), ptr(W), ptr(B), ptr(R), C, 1, ptr(Y), C, ptr(hi), ptr(lo), C, st))
+    check(lib.pcb_bn_apply_seg(ptr(X), C, n, n0, C, ptr(mean), ptr(invstd), ptr(W), ptr(B), ptr(R), C, 1, ptr(Y), C, ptr(hi), ptr(lo), C, None, None, st))
     for s, (a, e) in enumerate(((0, n0), (n0, n))):
         m = x[a:e].mean(0); v = x[a:e].var(0, unbiased=False)
         assert rel_err(mean[s], m) < 1e-5
