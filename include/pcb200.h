@@ -248,6 +248,11 @@ int pcb_unit_backward(const pcb_unit* u, void* stream);
 size_t pcb_nce_ws_bytes(int64_t n);
 int pcb_nce_forward_backward(const float* q, const float* k, int64_t n, int D, float inv_T, float* loss, float* dq,
                              float* dk, void* ws, size_t ws_bytes, void* stream);
+/* nn.CrossEntropyLoss(ignore_index) on logits [n, C] with int64 targets (`downstream/semseg/lib/train.py:68,120`): writes the mean loss
+ * over the non-ignored rows (device float) and dlogits = grad_scale * d loss / d logits.  ws: pcb_ce_ws_bytes(n). */
+size_t pcb_ce_ws_bytes(int64_t n);
+int pcb_ce_forward_backward(const float* logits, const int64_t* target, int64_t n, int C, int64_t ignore_index, float grad_scale,
+                            float* loss, float* dlogits, void* ws, size_t ws_bytes, void* stream);
 /* Row-wise L2 normalisation of the output features, y = x / ||x||_2 with no epsilon (`model/res16unet.py:262-266`), and its
  * backward dx = (dy - y (y.dy)) / ||x||.  inv_norm: [n] scratch written by forward, read by backward. */
 int pcb_l2norm_forward(const float* X, int64_t n, int C, float* Y, float* inv_norm, void* stream);
@@ -257,9 +262,10 @@ int pcb_pdist_rowmin(const float* A, int64_t P, const float* B, int64_t S, int D
                      uint64_t* packed, void* stream);
 
 /* ----------------------------------------------------------------------------------------------- optimiser */
-/* torch.optim.SGD semantics on a flat buffer:  d = g*grad_scale + wd*p;  buf = first ? d : momentum*buf + d;  p -= lr*buf */
+/* torch.optim.SGD semantics on a flat buffer:  d = g*grad_scale + wd*p;  buf = first ? d : momentum*buf + (1-dampening)*d;  p -= lr*buf
+ * (pretraining: dampening 0, `lib/ddp_trainer.py:107-111`; semseg finetuning: 0.1, `downstream/semseg/lib/solvers.py:50-57`) */
 int pcb_sgd_step(float* p, const float* g, float* buf, int64_t n, float lr, float momentum, float weight_decay,
-                 float grad_scale, int first, void* stream);
+                 float grad_scale, int first, float dampening, void* stream);
 
 #ifdef __cplusplus
 }

@@ -151,7 +151,7 @@ __global__ void pdist_unpack_kernel(const unsigned long long* __restrict__ packe
 }
 
 __global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf, int64_t n, float lr,
-                           float momentum, float wd, float gscale, int first) {
+                           float momentum, float wd, float gscale, int first, float keep) {
   pdl_wait(); pdl_trigger();
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   int64_t n4 = n >> 2;
@@ -160,7 +160,8 @@ __global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, f
     float4 G = __ldg(reinterpret_cast<const float4*>(g) + i);
     float4 Bf = first ? make_float4(0, 0, 0, 0) : reinterpret_cast<float4*>(buf)[i];
     float4 d = make_float4(G.x * gscale + wd * P.x, G.y * gscale + wd * P.y, G.z * gscale + wd * P.z, G.w * gscale + wd * P.w);
-    if (first) Bf = d; else { Bf.x = momentum * Bf.x + d.x; Bf.y = momentum * Bf.y + d.y; Bf.z = momentum * Bf.z + d.z; Bf.w = momentum * Bf.w + d.w; }
+    if (first) Bf = d;
+    else { Bf.x = momentum * Bf.x + keep * d.x; Bf.y = momentum * Bf.y + keep * d.y; Bf.z = momentum * Bf.z + keep * d.z; Bf.w = momentum * Bf.w + keep * d.w; }
     P.x -= lr * Bf.x; P.y -= lr * Bf.y; P.z -= lr * Bf.z; P.w -= lr * Bf.w;
     reinterpret_cast<float4*>(buf)[i] = Bf;
     reinterpret_cast<float4*>(p)[i] = P;
@@ -168,7 +169,7 @@ __global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, f
     int64_t e = (n4 << 2) + (i - n4);
     if (e < n) {
       float d = g[e] * gscale + wd * p[e];
-      float b = first ? d : momentum * buf[e] + d;
+      float b = first ? d : momentum * buf[e] + keep * d;
       buf[e] = b;
       p[e] -= lr * b;
     }
@@ -285,13 +286,91 @@ extern "C" int pcb_pdist_rowmin(const float* A, int64_t P, const float* B, int64
   return check_launch("pdist_unpack_kernel");
 }
 
+// ------------------------------------------------------------------------------------------------ cross-entropy (semantic segmentation)
+// nn.CrossEntropyLoss(ignore_index) over logits [n, C] (`downstream/semseg/lib/train.py:68,120`): loss = mean over the rows whose
+// target != ignore of (logsumexp(x) - x[target]); dlogits = (softmax(x) - onehot) * scale / count on those rows, 0 elsewhere.
+// One warp per row (C <= 1024), two passes: per-row loss + validity, then the mean, then the gradient.
+namespace {
+__global__ void ce_rows_kernel(const float* __restrict__ X, const int64_t* __restrict__ target, int64_t n, int C, int64_t ignore,
+                               float* __restrict__ rowloss, float* __restrict__ rowlse) {
+  pdl_wait(); pdl_trigger();
+  const int lane = threadIdx.x & 31;
+  const int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n) return;
+  const int64_t t = target[row];
+  float m = -INFINITY;
+  for (int c = lane; c < C; c += 32) m = fmaxf(m, X[row * C + c]);
+  for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += expf(X[row * C + c] - m);
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) {
+    const float lse = m + logf(s);
+    rowlse[row] = lse;
+    rowloss[row] = (t == ignore || t < 0 || t >= C) ? 0.f : lse - X[row * C + t];
+  }
+}
+// out[0] = sum(rowloss) / count, out[1] = count   (count = rows with a valid target; fp64, fixed order)
+__global__ void ce_mean_kernel(const float* __restrict__ rowloss, const int64_t* __restrict__ target, int64_t n, int C, int64_t ignore,
+                               float* __restrict__ out) {
+  pdl_wait(); pdl_trigger();
+  __shared__ double s_sum[32];
+  __shared__ double s_cnt[32];
+  double s = 0.0, cnt = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const int64_t t = target[i];
+    if (!(t == ignore || t < 0 || t >= C)) { s += rowloss[i]; cnt += 1.0; }
+  }
+  for (int o = 16; o; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); cnt += __shfl_xor_sync(0xffffffffu, cnt, o); }
+  if ((threadIdx.x & 31) == 0) { s_sum[threadIdx.x >> 5] = s; s_cnt[threadIdx.x >> 5] = cnt; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ts = 0.0, tc = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { ts += s_sum[w]; tc += s_cnt[w]; }
+    out[0] = (float)(ts / tc);       // 0/0 = nan when every row is ignored, as torch
+    out[1] = (float)tc;
+  }
+}
+__global__ void ce_grad_kernel(const float* __restrict__ X, const int64_t* __restrict__ target, const float* __restrict__ rowlse,
+                               const float* __restrict__ stats, int64_t n, int C, int64_t ignore, float scale, float* __restrict__ dX) {
+  pdl_wait(); pdl_trigger();
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= n * C) return;
+  const int64_t row = e / C;
+  const int c = (int)(e - row * C);
+  const int64_t t = target[row];
+  float g = 0.f;
+  if (!(t == ignore || t < 0 || t >= C)) g = (expf(X[e] - rowlse[row]) - (c == t ? 1.f : 0.f)) * (scale / stats[1]);
+  dX[e] = g;
+}
+}  // namespace
+
+extern "C" size_t pcb_ce_ws_bytes(int64_t n) { return (size_t)(2 * n + 4) * sizeof(float) + 256; }
+
+extern "C" int pcb_ce_forward_backward(const float* logits, const int64_t* target, int64_t n, int C, int64_t ignore_index, float grad_scale,
+                                       float* loss, float* dlogits, void* ws, size_t ws_bytes, void* stream) {
+  PCB_ARG(logits && target && loss && dlogits && ws && n >= 1 && C >= 1 && C <= 1024 && ws_bytes >= pcb_ce_ws_bytes(n) - 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  float* rowloss = (float*)ws;
+  float* rowlse = rowloss + n;
+  float* stats = rowlse + n;
+  launch_kernel(ce_rows_kernel, (unsigned)((n + 7) / 8), 256, 0, st, logits, target, n, C, ignore_index, rowloss, rowlse);
+  if (int e = check_launch("ce_rows_kernel")) return e;
+  launch_kernel(ce_mean_kernel, 1, 1024, 0, st, (const float*)rowloss, target, n, C, ignore_index, stats);
+  if (int e = check_launch("ce_mean_kernel")) return e;
+  PCB_CUDA(cudaMemcpyAsync(loss, stats, sizeof(float), cudaMemcpyDeviceToDevice, st));
+  launch_kernel(ce_grad_kernel, (unsigned)((n * C + 255) / 256), 256, 0, st, logits, target, (const float*)rowlse, (const float*)stats, n, C,
+                ignore_index, grad_scale, dlogits);
+  return check_launch("ce_grad_kernel");
+}
+
 extern "C" int pcb_sgd_step(float* p, const float* g, float* buf, int64_t n, float lr, float momentum, float weight_decay,
-                            float grad_scale, int first, void* stream) {
+                            float grad_scale, int first, float dampening, void* stream) {
   PCB_ARG(n >= 0);
   if (n == 0) return PCB_OK;
   PCB_ARG(p && g && buf);
   int64_t threads = (n >> 2) + (n & 3);
   launch_kernel(sgd_kernel, (unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream, p, g, buf, n, lr, momentum, weight_decay,
-                                                                                   grad_scale, first);
+                grad_scale, first, 1.0f - dampening);
   return check_launch("sgd_kernel");
 }

@@ -61,6 +61,34 @@ def l2_normalize(F):
     return _L2NormFunction.apply(F)
 
 
+class _CrossEntropyFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, target, ignore_index):
+        _lib.require_cuda(logits)
+        logits = logits.contiguous().float()
+        target = target.contiguous().long()
+        n, C = logits.shape
+        loss = torch.empty((), dtype=torch.float32, device=logits.device)
+        dlogits = torch.empty_like(logits)
+        with torch.cuda.device(logits.device):
+            wsb = lib.pcb_ce_ws_bytes(n)
+            ws = workspace(wsb, logits.device, slot=1)
+            check(lib.pcb_ce_forward_backward(ptr(logits), ptr(target), n, C, int(ignore_index), 1.0, ptr(loss), ptr(dlogits), ptr(ws), wsb,
+                                              stream()))
+        ctx.save_for_backward(dlogits)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (dlogits,) = ctx.saved_tensors
+        return dlogits * g, None, None
+
+
+def cross_entropy(logits, target, ignore_index=255):
+    """`nn.CrossEntropyLoss(ignore_index=config.data.ignore_label)(soutput.F, target)` (`downstream/semseg/lib/train.py:68,120`)."""
+    return _CrossEntropyFunction.apply(logits, target, ignore_index)
+
+
 def select_positives(pos_pairs, npos, generator=None):
     """`ddp_trainer.py:400-415`: one uniformly random key per unique query, then at most `npos` of them.
     pos_pairs: int tensor [P, 2] on the device, grouped by column 0.  Returns (q_rows, k_rows) int64."""

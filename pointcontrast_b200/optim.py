@@ -1,9 +1,10 @@
 """Flat-buffer SGD: all parameters (and their gradients) are views into one contiguous fp32 buffer, so the
 optimiser step is ONE kernel launch and the DDP gradient all-reduce is one (chunkable) buffer.
 
-Semantics and state_dict layout are those of `torch.optim.SGD(momentum, weight_decay)` as used at
-`pretrain/pointcontrast/lib/ddp_trainer.py:107-111` (no dampening, no nesterov), so `ExponentialLR`
-(`:113`) and the checkpoint's `optimizer` entry (`:155-161`) work unchanged.
+Semantics and state_dict layout are those of `torch.optim.SGD(momentum, dampening, weight_decay)` as used at
+`pretrain/pointcontrast/lib/ddp_trainer.py:107-111` (no dampening) and `downstream/semseg/lib/solvers.py:50-57` (dampening 0.1);
+no nesterov.  `ExponentialLR` (`ddp_trainer.py:113`), `PolyLR` below and the checkpoint's `optimizer` entry
+(`ddp_trainer.py:155-161`) work unchanged.
 """
 import torch
 
@@ -12,11 +13,11 @@ from .me import bump_weights_epoch
 
 
 class FlatSGD(torch.optim.Optimizer):
-    def __init__(self, params, lr, momentum=0.0, weight_decay=0.0):
+    def __init__(self, params, lr, momentum=0.0, weight_decay=0.0, dampening=0.0):
         params = list(params)
         if any(isinstance(p, dict) for p in params):
             raise NotImplementedError("FlatSGD supports a single parameter group")
-        super().__init__(params, dict(lr=lr, momentum=momentum, weight_decay=weight_decay, dampening=0, nesterov=False))
+        super().__init__(params, dict(lr=lr, momentum=momentum, weight_decay=weight_decay, dampening=dampening, nesterov=False))
         ps = self.param_groups[0]["params"]
         dev = ps[0].device
         if dev.type != "cuda" or any(p.device != dev or p.dtype != torch.float32 for p in ps):
@@ -61,7 +62,7 @@ class FlatSGD(torch.optim.Optimizer):
         with torch.cuda.device(self.flat_param.device):
             check(lib.pcb_sgd_step(ptr(self.flat_param), ptr(self.flat_grad), ptr(self.flat_buf), self.flat_param.numel(),
                                    float(grp["lr"]), float(grp["momentum"]), float(grp["weight_decay"]), float(self.grad_scale),
-                                   1 if self._first else 0, stream()))
+                                   1 if self._first else 0, float(grp.get("dampening", 0.0)), stream()))
         bump_weights_epoch()           # the kernel wrote the parameters behind torch's back: drop cached bf16 copies
         if self._first:
             for p, b in zip(ps, self._views(self.flat_buf)):
@@ -80,3 +81,11 @@ class FlatSGD(torch.optim.Optimizer):
                     self.state[p]["momentum_buffer"] = b
                     loaded = True
         self._first = not loaded
+
+
+class PolyLR(torch.optim.lr_scheduler.LambdaLR):
+    """DeepLab polynomial decay, `downstream/semseg/lib/solvers.py:27-32`: lr = base * (1 - step / (max_iter + 1)) ** power,
+    stepped once per optimiser step (`lib/train.py:159-160`)."""
+
+    def __init__(self, optimizer, max_iter, power=0.9, last_step=-1):
+        super().__init__(optimizer, lambda s: (1 - s / (max_iter + 1)) ** power, last_step)

@@ -418,3 +418,43 @@ def test_point_nce_tensor_core_and_simt_paths_agree(n, D, T, monkeypatch):
     ls.backward()
     assert abs(float(l) - float(ls)) / abs(float(ls)) < 1e-5
     assert rel_err(f0.grad, f0s.grad[:, :D]) < 1e-4 and rel_err(f1.grad, f1s.grad[:, :D]) < 1e-4
+
+
+@pytest.mark.parametrize("n,C", [(5000, 13), (333, 20), (64, 32)])
+def test_cross_entropy_with_ignore_index_matches_torch(n, C):
+    """`nn.CrossEntropyLoss(ignore_index=255)` (`downstream/semseg/lib/train.py:68,120`), loss and gradient, vs torch fp64."""
+    from pointcontrast_b200 import losses
+    g = torch.Generator().manual_seed(n + C)
+    x = torch.randn(n, C, generator=g, dtype=torch.float64) * 3
+    t = torch.randint(0, C, (n,), generator=g)
+    t[torch.rand(n, generator=g) < 0.2] = 255
+    xo = x.clone().requires_grad_(True)
+    lo = torch.nn.functional.cross_entropy(xo, t, ignore_index=255)
+    (lo * 0.5).backward()
+    xg = x.float().cuda().requires_grad_(True)
+    l = losses.cross_entropy(xg, t.cuda(), 255)
+    (l * 0.5).backward()
+    assert abs(float(l.detach()) - float(lo.detach())) / abs(float(lo.detach())) < 1e-5
+    assert max_rel_err(xg.grad, xo.grad) < 1e-5
+
+
+def test_sgd_with_dampening_and_poly_lr_match_torch():
+    """`downstream/semseg/lib/solvers.py:27-32,50-57`: SGD(momentum 0.9, dampening 0.1, wd 1e-4) under PolyLR(power 0.9)."""
+    from pointcontrast_b200 import optim as pco
+    g = torch.Generator().manual_seed(3)
+    shapes = [(27, 32, 64), (64,), (1, 13)]
+    ps = [torch.randn(s, generator=g) for s in shapes]
+    ref = [p.clone().requires_grad_(True) for p in ps]
+    mine = [torch.nn.Parameter(p.clone().cuda()) for p in ps]
+    o_ref = torch.optim.SGD(ref, lr=0.01, momentum=0.9, dampening=0.1, weight_decay=1e-4)
+    o = pco.FlatSGD(mine, lr=0.01, momentum=0.9, dampening=0.1, weight_decay=1e-4)
+    s_ref = torch.optim.lr_scheduler.LambdaLR(o_ref, lambda s: (1 - s / (10 + 1)) ** 0.9)
+    s = pco.PolyLR(o, max_iter=10, power=0.9)
+    for step in range(4):
+        for r, m in zip(ref, mine):
+            gr = torch.randn(r.shape, generator=g)
+            r.grad = gr.clone(); m.grad.copy_(gr.cuda())
+        o_ref.step(); o.step(); s_ref.step(); s.step()
+        assert abs(s.get_last_lr()[0] - s_ref.get_last_lr()[0]) < 1e-12
+        for r, m in zip(ref, mine):
+            assert torch.allclose(m.detach().cpu(), r.detach(), rtol=1e-6, atol=1e-7)

@@ -109,3 +109,24 @@ def test_stacked_views_are_block_diagonal_on_the_oracle():
                 want = set(zip(m0[k][0].tolist(), m0[k][1].tolist())) | set(zip((m1[k][0] + n0).tolist(), (m1[k][1] + n0c).tolist()))
                 assert set(zip(ms[k][0].tolist(), ms[k][1].tolist())) == want
         ts *= 2
+
+
+def test_poly_lr_and_lenient_loader_host_logic():
+    """`downstream/semseg/lib/solvers.py:27-32` and `lib/utils.py:19-43` (host-side pieces of the finetune step; no GPU needed)."""
+    import torch
+    from pointcontrast_b200 import semseg
+    from pointcontrast_b200.model import load_model
+    from pointcontrast_b200.optim import PolyLR
+    from tests import refload
+    p = torch.nn.Parameter(torch.zeros(3))
+    opt = torch.optim.SGD([p], lr=0.01)
+    sch = PolyLR(opt, max_iter=60000, power=0.9)
+    for s in range(1, 4):
+        opt.step(); sch.step()
+        assert abs(sch.get_last_lr()[0] - 0.01 * (1 - s / 60001) ** 0.9) < 1e-15
+    cfg13 = refload.default_config(); cfg13["net"]["normalize_feature"] = False
+    pre = load_model("Res16UNet34C")(3, 32, refload.default_config(), D=3)
+    net = load_model("Res16UNet34C")(3, 13, cfg13, D=3)
+    kept = semseg.load_state_with_same_shape(net, {"module.encoder." + k if False else "module." + k: v for k, v in pre.state_dict().items()})
+    assert set(pre.state_dict()) - set(kept) == {"final.kernel", "final.bias"}
+    assert all(torch.equal(net.state_dict()[k], pre.state_dict()[k]) for k in kept)
