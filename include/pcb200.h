@@ -86,6 +86,22 @@ int pcb_kernel_map(const uint64_t* out_keys, int64_t n_out, const uint64_t* tabl
 /* counts[k] = number of non-negative entries of row k (device int64 [K]). */
 int pcb_kernel_map_count(const int32_t* tbl, int K, int64_t n_out, int64_t* counts, void* stream);
 
+/* ----------------------------------------------------------------------------------------------- data preparation */
+/* One point per occupied voxel: voxel index = floor(xyz / voxel_size) per axis (fp32, |index| < 2^20).  Writes the M occupied voxels'
+ * indices (int32 [M,3], sorted by (x,y,z)) and sel[M] = the smallest index of a point in each voxel -- np.unique(return_index=True) /
+ * `ME.utils.sparse_quantize(xyz / voxel_size, return_index=True)` of `pretrain/pointcontrast/lib/ddp_data_loaders.py:228-241`.
+ * out_coords / sel hold up to n rows.  SYNCHRONISES the stream once to return *m_out. */
+size_t pcb_voxelize_ws_bytes(int64_t n);
+int pcb_voxelize(const float* xyz, int64_t n, float voxel_size, int32_t* out_coords, int32_t* sel, int64_t* m_out, void* ws,
+                 size_t ws_bytes, void* stream);
+/* All (i, j) with |src_i - dst_j| < radius (fp32, strict), i ascending, j ascending within i -- `get_matching_indices`
+ * (`ddp_data_loaders.py:36-49`: an open3d KD-tree radius search per source point; radius = 1.5 voxels) on a hashed uniform grid of
+ * cell size `radius`.  *n_pairs = total number of pairs (SYNCHRONISES once); at most `cap` of them are written ([cap,2] int32;
+ * pairs == NULL: count only). */
+size_t pcb_radius_pairs_ws_bytes(int64_t ns, int64_t nd);
+int pcb_radius_pairs(const float* src, int64_t ns, const float* dst, int64_t nd, float radius, int32_t* pairs, int64_t cap,
+                     int64_t* n_pairs, void* ws, size_t ws_bytes, void* stream);
+
 /* ----------------------------------------------------------------------------------------------- convolution */
 /* fp32 W[K][Cin][Cout] -> bf16 hi/lo split planes in the same layout (w_hi, w_lo) and per-offset transposed
  * [K][Cout][Cin] (wt_hi, wt_lo).  x ~= hi + lo with |x - hi - lo| <= 2^-17 |x|. */

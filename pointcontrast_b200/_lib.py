@@ -34,6 +34,10 @@ _SIGS = {
     "pcb_hash_build": (_i, [_p, _l, _p, _p, _l, _p, _p]),
     "pcb_coords_stride_ws_bytes": (_sz, [_l]),
     "pcb_coords_stride": (_i, [_p, _l, C.c_int32, _p, _p, C.POINTER(C.c_int64), _p, _sz, _p]),
+    "pcb_voxelize_ws_bytes": (_sz, [_l]),
+    "pcb_voxelize": (_i, [_p, _l, _f, _p, _p, C.POINTER(C.c_int64), _p, _sz, _p]),
+    "pcb_radius_pairs_ws_bytes": (_sz, [_l, _l]),
+    "pcb_radius_pairs": (_i, [_p, _l, _p, _l, _f, _p, _l, C.POINTER(C.c_int64), _p, _sz, _p]),
     "pcb_kernel_map": (_i, [_p, _l, _p, _p, _l, _p, _i, _p, _p]),
     "pcb_kernel_map_count": (_i, [_p, _i, _l, _p, _p]),
     "pcb_weight_prep": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _p]),

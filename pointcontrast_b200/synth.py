@@ -62,6 +62,23 @@ def _voxelize(xyz, voxel):
     return c[sel].astype(np.int32), sel
 
 
+def synth_pair_raw(seed, scale=0.9, n_raw=300_000):
+    """The two raw (un-voxelised) views of `synth_pair(seed, scale)` as float32 point clouds in their own frames, and the
+    ground-truth transform T01 [4,4] taking view-0 coordinates to view-1 coordinates -- the inputs of the reference loader's
+    per-sample work (`ddp_data_loaders.py:196-245`), for `pointcontrast_b200.voxel.make_pair`."""
+    rng = np.random.default_rng(seed + 7_000_003)
+    world = synth_room(seed, scale, n_raw)
+    Wd = _W * scale
+    v0 = world[world[:, 0] < 0.65 * Wd]
+    v1 = world[world[:, 0] > 0.25 * Wd]
+    R0, R1 = _rot(rng), _rot(rng)
+    m0, m1 = v0.mean(0), v1.mean(0)
+    T = np.eye(4)
+    T[:3, :3] = R1 @ R0.T
+    T[:3, 3] = R1 @ (m0 - m1)
+    return {"p0": ((v0 - m0) @ R0.T).astype(np.float32), "p1": ((v1 - m1) @ R1.T).astype(np.float32), "T01": T}
+
+
 def synth_pair(seed, scale=0.9, voxel=0.025, n_raw=300_000, search_mult=1.5):
     """One scene pair: two overlapping, independently rotated, voxelised views + correspondences."""
     rng = np.random.default_rng(seed + 7_000_003)
