@@ -64,3 +64,39 @@ def test_make_pair_on_the_synthetic_generator_views():
     got = {tuple(x) for x in out["corr"].cpu().numpy().tolist()}
     assert len(got ^ ref) <= max(2, len(ref) // 1000), (len(got), len(ref), len(got ^ ref))
     assert abs(len(got) - len(host["corr"])) <= 0.05 * len(host["corr"])
+
+
+def test_scannet_pair_dataset_end_to_end(tmp_path):
+    """`.npz{pcd}` frames + pair list on disk -> `ScanNetMatchPairDataset` (GPU voxelisation / matching) -> `PairLoader` batch dict
+    -> one PointInfoNCE training iteration of the trainer (`ddp_data_loaders.py:144-309` feeding `ddp_trainer.py:380-440`)."""
+    from pointcontrast_b200 import scannet_pairs as SP, synth
+    from pointcontrast_b200.config import default_config
+    from pointcontrast_b200.trainer import get_trainer
+    from tests import refload
+    (tmp_path / "scene0000_00" / "pcd").mkdir(parents=True)
+    lines = []
+    for s in range(2):
+        raw = synth.synth_pair_raw(40 + s, scale=0.2, n_raw=60_000)
+        # frames are stored in a common world frame: put view 1's points into view 0's frame (x0 = R^T (x1 - t))
+        T = raw["T01"]
+        np.savez(tmp_path / "scene0000_00" / "pcd" / f"{2 * s}.npz", pcd=raw["p0"].astype(np.float64))
+        np.savez(tmp_path / "scene0000_00" / "pcd" / f"{2 * s + 1}.npz", pcd=(raw["p1"].astype(np.float64) - T[:3, 3]) @ T[:3, :3])
+        lines.append(f"scene0000_00/pcd/{2 * s}.npz scene0000_00/pcd/{2 * s + 1}.npz 0.4")
+    (tmp_path / "overlap-30-full.txt").write_text("\n".join(lines) + "\n")
+    dcfg = refload.Cfg(data=dict(voxel_size=0.025, dataset_root_dir=str(tmp_path), scannet_match_dir="overlap-30-full.txt"),
+                       trainer=dict(positive_pair_search_voxel_size_multiplier=1.5, min_scale=0.8, max_scale=1.2, rotation_range=360))
+    ds = SP.ScanNetMatchPairDataset("train", transform=SP.Jitter(), config=dcfg, manual_seed=True, device="cuda")
+    assert len(ds) == 2
+    xyz0, xyz1, c0, c1, f0, f1, matches, trans = ds[0]
+    assert c0.shape[1] == 3 and len(c0) == len(xyz0) == len(f0) and len(matches) > 100 and trans.shape == (4, 4)
+    assert (c0 == np.floor(xyz0 / np.float32(0.025)).astype(np.int32)).all()
+    d = np.linalg.norm((xyz0[matches[:, 0]] @ trans[:3, :3].T + trans[:3, 3]) - xyz1[matches[:, 1]], axis=1)
+    assert d.max() < 1.5 * 0.025 * 1.2 * 1.001                 # every pair within the (scaled) search radius
+    loader = SP.PairLoader(ds, batch_size=2, shuffle=False)
+    batch = next(iter(loader))
+    assert batch["sinput0_C"].dtype == torch.int32 and batch["sinput0_C"][:, 0].max() == 1 and batch["correspondences"].shape[1] == 2
+    cfg = default_config(["trainer.batch_size=2", "misc.nceT=0.4"])
+    torch.manual_seed(0)
+    tr = get_trainer("PointNCELossTrainer")(cfg, loader)
+    loss = tr._train_iter(iter(loader), None)
+    assert np.isfinite(loss) and 0 < loss < 20

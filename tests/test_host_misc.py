@@ -130,3 +130,36 @@ def test_poly_lr_and_lenient_loader_host_logic():
     kept = semseg.load_state_with_same_shape(net, {"module.encoder." + k if False else "module." + k: v for k, v in pre.state_dict().items()})
     assert set(pre.state_dict()) - set(kept) == {"final.kernel", "final.bias"}
     assert all(torch.equal(net.state_dict()[k], pre.state_dict()[k]) for k in kept)
+
+
+def test_scannet_pair_formats_and_samplers(tmp_path):
+    """On-disk formats of the reference's preprocessing (`point_cloud_extractor.py:80`, `generate_list.py:20-28`), the collate
+    layout (`ddp_data_loaders.py:52-112`) and the distributed infinite sampler (`lib/data_sampler.py:40-70`) -- host logic."""
+    import torch
+    from pointcontrast_b200 import scannet_pairs as SP
+    rng = np.random.default_rng(0)
+    (tmp_path / "scene0000_00" / "pcd").mkdir(parents=True)
+    for i in range(3):
+        np.savez(tmp_path / "scene0000_00" / "pcd" / f"{i}.npz", pcd=rng.normal(size=(50, 3)))
+    with open(tmp_path / "overlap-30-full.txt", "w") as f:
+        f.write("scene0000_00/pcd/0.npz scene0000_00/pcd/1.npz 0.45\nscene0000_00/pcd/1.npz scene0000_00/pcd/2.npz 0.31\n")
+    pairs = SP.read_pair_list(tmp_path / "overlap-30-full.txt")
+    assert pairs == [("scene0000_00/pcd/0.npz", "scene0000_00/pcd/1.npz"), ("scene0000_00/pcd/1.npz", "scene0000_00/pcd/2.npz")]
+    assert SP.load_frame(tmp_path / pairs[0][0]).shape == (50, 3)
+    # rotation law == expm(cross(I, axis * theta))
+    from scipy.linalg import expm
+    ax, th = np.array([0.3, -0.2, 0.4]), 1.1
+    assert np.allclose(SP.rotation_about(ax, th), expm(np.cross(np.eye(3), ax / np.linalg.norm(ax) * th)), atol=1e-12)
+    T = SP.sample_random_trans(rng.normal(size=(20, 3)), np.random.RandomState(0))
+    assert np.allclose(T[:3, :3] @ T[:3, :3].T, np.eye(3), atol=1e-12)
+    # collate: batch index first, correspondences offset by the rows of the previous samples
+    s0 = (np.zeros((4, 3), np.float32), np.zeros((5, 3), np.float32), np.arange(12).reshape(4, 3), np.arange(15).reshape(5, 3),
+          np.ones((4, 3), np.float32), np.ones((5, 3), np.float32), np.array([[0, 1], [3, 4]]), np.eye(4))
+    s1 = (np.zeros((2, 3), np.float32), np.zeros((3, 3), np.float32), np.arange(6).reshape(2, 3), np.arange(9).reshape(3, 3),
+          np.ones((2, 3), np.float32), np.ones((3, 3), np.float32), np.zeros((0, 2), np.int64), np.eye(4))
+    b = SP.default_collate_pair_fn([s0, s1])
+    assert b["sinput0_C"].shape == (6, 4) and b["sinput0_C"][:, 0].tolist() == [0, 0, 0, 0, 1, 1] and b["sinput0_C"].dtype == torch.int32
+    assert b["correspondences"].tolist() == [[0, 1], [3, 4], [4, 5]] and b["len_batch"] == [[4, 5], [2, 3]] and b["T_gt"].shape == (8, 4)
+    # two ranks partition each permutation pass
+    a, c = SP.DistributedInfSampler(10, 2, 0, shuffle=False), SP.DistributedInfSampler(10, 2, 1, shuffle=False)
+    assert [next(a) for _ in range(5)] == [0, 2, 4, 6, 8] and [next(c) for _ in range(5)] == [1, 3, 5, 7, 9]
