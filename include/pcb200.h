@@ -132,6 +132,12 @@ int pcb_conv_forward(const float* X, int ldx, const int32_t* tbl, int64_t tbl_st
                      const uint16_t* wk_hi, const uint16_t* wk_lo, const float* w_f32, const float* bias, float* Y,
                      int ldy, void* ws, size_t ws_bytes, int flags, void* stream);
 
+/* Y[j, :] = sum_k X[tbl[kmap[k]][j], :];  cnt[j] (optional) = number of neighbours present.  The sum / average pooling and unpooling
+ * layers of the sibling models (MinkowskiSumPooling / AvgPooling / PoolingTranspose / AvgUnpooling, `model/modules/common.py:170-214`,
+ * `model/resnet.py:63`) and their backward passes (the same sum over the transposed table).  C % 4 == 0. */
+int pcb_gather_sum(const float* X, int ldx, const int32_t* tbl, int64_t tbl_stride, const int32_t* kmap, int K, int64_t n_out, int C,
+                   float* Y, int ldy, float* cnt, void* stream);
+
 /* dW[k] = sum_j A[tbl[k][j], :]^T . B[j, :]       A: gathered [*, Ca] (lda), B: contiguous rows [n_out, Cb] (ldb).
  *   transpose_out = 0: dW is [K][Ca][Cb];  1: dW is [K][Cb][Ca]. */
 size_t pcb_conv_wgrad_ws_bytes(int K, int64_t n_out, int Ca, int Cb);

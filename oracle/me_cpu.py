@@ -353,25 +353,61 @@ class MinkowskiReLU(nn.Module):
         return SparseTensor(torch.relu(x.F), coords_key=x.coords_key, coords_manager=x.coords_man)
 
 
+# Pooling layers of the sibling models (`model/resnet.py:63`, `model/modules/common.py:170-214`), restated with the
+# same kernel maps: sum pooling = the convolution of (5) with every W[k] = identity; average pooling divides by the number of inputs
+# present; the transposed / unpooling variants use the swapped map of (8).
+class _PoolBase(nn.Module):
+    AVERAGE, TRANSPOSE = False, False
+
+    def __init__(self, kernel_size=-1, stride=1, dilation=1, kernel_generator=None, dimension=-1):
+        super().__init__()
+        if kernel_generator is None:
+            kernel_generator = KernelGenerator(kernel_size, stride, dilation, dimension=dimension)
+        self.kernel_generator = kernel_generator
+        self.stride = _as_list(stride, dimension)
+
+    def forward(self, x):
+        cm = x.coords_man
+        if not self.TRANSPOSE:
+            out_key = cm.stride(x.coords_key, self.stride)
+        else:
+            out_key = CoordsKey(cm.D, tuple(t // s for t, s in zip(x.coords_key.ts, self.stride)))
+        maps = cm.get_kernel_map(x.coords_key, out_key, self.kernel_generator, self.TRANSPOSE)
+        n_out = len(cm.levels[out_key.ts])
+        y = x.F.new_zeros((n_out, x.F.shape[1]))
+        cnt = x.F.new_zeros((n_out, 1))
+        for i, j in maps:
+            if len(i):
+                y = y.index_add(0, j, x.F.index_select(0, i))
+                cnt = cnt.index_add(0, j, x.F.new_ones((len(j), 1)))
+        if self.AVERAGE:
+            y = y / cnt.clamp(min=1)
+        return SparseTensor(y, coords_key=out_key, coords_manager=cm)
+
+
+class MinkowskiSumPooling(_PoolBase):
+    pass
+
+
+class MinkowskiAvgPooling(_PoolBase):
+    AVERAGE = True
+
+
+class MinkowskiPoolingTranspose(_PoolBase):
+    TRANSPOSE = True
+
+
+class MinkowskiAvgUnpooling(_PoolBase):
+    AVERAGE, TRANSPOSE = True, True
+
+
 class _Unsupported(nn.Module):
     def __init__(self, *a, **k):
         super().__init__()
-        raise NotImplementedError(type(self).__name__ + " is not on the Res16UNet34C hot path")
+        raise NotImplementedError(f"oracle: {type(self).__name__} is restated by plain torch in the tests that need it")
 
 
 class MinkowskiGlobalPooling(_Unsupported):
-    pass
-
-
-class MinkowskiSumPooling(_Unsupported):
-    pass
-
-
-class MinkowskiAvgPooling(_Unsupported):
-    pass
-
-
-class MinkowskiAvgUnpooling(_Unsupported):
     pass
 
 

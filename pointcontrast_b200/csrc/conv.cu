@@ -272,6 +272,31 @@ __global__ void conv_split_reduce_kernel(const float* __restrict__ partial, int 
   *dst = s;
 }
 
+// --------------------------------------------------------------------------------------------- pooling (table gather-sum)
+// Y[j, :] = sum_k X[tbl[kmap[k]][j], :]  (cnt[j] = number of present neighbours): the kernel of MinkowskiSumPooling / AvgPooling /
+// PoolingTranspose / AvgUnpooling and of their backward passes (the same sum over the transposed table) -- the sibling models'
+// pooling layers (`model/resnet.py:63`, `model/modules/common.py:170-214`).  One thread per (row, 4 channels).
+__global__ void gather_sum_kernel(const float* __restrict__ X, int ldx, const int32_t* __restrict__ tbl, int64_t tbl_stride, KMap kmap, int K,
+                                  int64_t n_out, int C, float* __restrict__ Y, int ldy, float* __restrict__ cnt) {
+  pdl_wait(); pdl_trigger();
+  const int cv = C / 4;
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= n_out * cv) return;
+  const int64_t j = e / cv;
+  const int c4 = (int)(e - j * cv);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  int present = 0;
+  for (int k = 0; k < K; ++k) {
+    const int idx = __ldg(tbl + (int64_t)kmap.v[k] * tbl_stride + j);
+    if (idx < 0) continue;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(X + (int64_t)idx * ldx) + c4);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    ++present;
+  }
+  *reinterpret_cast<float4*>(Y + j * ldy + c4 * 4) = acc;
+  if (cnt && c4 == 0) cnt[j] = (float)present;
+}
+
 // --------------------------------------------------------------------------------------------- forward (exact fp32 SIMT)
 __global__ void conv_simt_kernel(const float* __restrict__ X, int ldx, const int32_t* __restrict__ tbl, int64_t tbl_stride,
                                  KMap kmap, int K, int64_t n_out, int Cin, int Cout, const float* __restrict__ W,
@@ -755,6 +780,19 @@ extern "C" int pcb_conv_forward(const float* X, int ldx, const int32_t* tbl, int
     case 64: return launch_conv<64>(a, nsplit, (float*)ws, st);
     default: return launch_conv<32>(a, nsplit, (float*)ws, st);
   }
+}
+
+extern "C" int pcb_gather_sum(const float* X, int ldx, const int32_t* tbl, int64_t tbl_stride, const int32_t* kmap, int K, int64_t n_out, int C,
+                              float* Y, int ldy, float* cnt, void* stream) {
+  PCB_ARG(K >= 1 && K <= PCB_MAX_KERNEL_VOLUME && n_out >= 0 && C >= 4 && C % 4 == 0 && ldx >= C && ldy >= C && ldx % 4 == 0 && ldy % 4 == 0);
+  if (n_out == 0) return PCB_OK;
+  PCB_ARG(X && tbl && Y && tbl_stride >= n_out);
+  KMap km;
+  for (int k = 0; k < K; ++k) { km.v[k] = kmap ? kmap[k] : k; PCB_ARG(km.v[k] >= 0 && km.v[k] < PCB_MAX_KERNEL_VOLUME); }
+  const int64_t total = n_out * (C / 4);
+  launch_kernel(gather_sum_kernel, (unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream, X, ldx, tbl, tbl_stride, km, K, n_out, C, Y, ldy,
+                cnt);
+  return check_launch("gather_sum_kernel");
 }
 
 extern "C" size_t pcb_conv_wgrad_ws_bytes(int K, int64_t n_out, int Ca, int Cb) {

@@ -679,30 +679,156 @@ class MinkowskiReLU(nn.Module):
         return SparseTensor(f, coords_key=input.coords_key, coords_manager=input.coords_man)
 
 
-class _NotOnHotPath(nn.Module):
-    def __init__(self, *a, **k):
+# ------------------------------------------------------------------------------------------------ pooling & per-instance ops
+# The layers the sibling models use next to the hot path (`model/resnet.py:63`, `model/modules/common.py:19-30,170-214`,
+# `downstream/semseg/lib/layers.py:12-90`).  Pooling runs on the neighbour tables with one gather-sum kernel (`pcb_gather_sum`);
+# the per-instance reductions (global pooling, broadcast, instance norm) are segment sums over the batch index.
+def _gather_sum(x, tbl, kmap, K, n_out, want_count=False):
+    x = x.contiguous()
+    C = x.shape[1]
+    pad = (-C) % 4
+    if pad:
+        x = torch.nn.functional.pad(x, (0, pad))
+    y = torch.empty(n_out, C + pad, dtype=torch.float32, device=x.device)
+    cnt = torch.empty(n_out, dtype=torch.float32, device=x.device) if want_count else None
+    km = _c_int_array(kmap) if kmap is not None else None
+    with torch.cuda.device(x.device):
+        check(lib.pcb_gather_sum(ptr(x), C + pad, ptr(tbl), tbl.shape[1], km, K, n_out, C + pad, ptr(y), C + pad, ptr(cnt), stream()))
+    return (y[:, :C] if pad else y), cnt
+
+
+class _PoolFunction(torch.autograd.Function):
+    """y[j] = sum_k x[fwd_tbl[k][j]] (/ count[j] if average); backward: the same sum over the transposed table."""
+
+    @staticmethod
+    def forward(ctx, x, plan, average):
+        _lib.require_cuda(x)
+        y, cnt = _gather_sum(x.float(), plan.fwd_tbl, plan.fwd_kmap, plan.K, plan.n_out, want_count=average)
+        ctx.plan, ctx.cnt = plan, None
+        if average:
+            cnt = cnt.clamp_(min=1.0)[:, None]
+            y = y / cnt
+            ctx.cnt = cnt
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        plan = ctx.plan
+        if ctx.cnt is not None:
+            dy = dy / ctx.cnt
+        dx, _ = _gather_sum(dy.contiguous(), plan.dg_tbl, plan.dg_kmap, plan.K, plan.n_in)
+        return dx, None, None
+
+
+class _PoolingBase(nn.Module):
+    AVERAGE, TRANSPOSE = False, False
+
+    def __init__(self, kernel_size=-1, stride=1, dilation=1, kernel_generator=None, dimension=-1):
         super().__init__()
-        raise NotImplementedError(f"{type(self).__name__} is not on the Res16UNet34C hot path (SURVEY.md 8f-4)")
+        if dimension <= 0:
+            raise ValueError("dimension must be positive")
+        if kernel_generator is None:
+            kernel_generator = KernelGenerator(kernel_size, stride, dilation, dimension=dimension)
+        self.kernel_generator = kernel_generator
+        self.stride = _listify(stride, dimension)
+        self.dimension = dimension
+
+    def forward(self, input):
+        cm = input.coords_man
+        if not self.TRANSPOSE:
+            out_key = cm.stride(input.coords_key, self.stride)
+        else:
+            ts = tuple(t // s for t, s in zip(input.coords_key.ts, self.stride))
+            if ts not in cm.levels:
+                raise _lib.PcbError(f"{type(self).__name__} needs the cached finer coordinate map")
+            out_key = CoordsKey(cm.D, ts)
+        plan = cm.conv_plan(input.coords_key, out_key, self.kernel_generator, self.TRANSPOSE)
+        return SparseTensor(_PoolFunction.apply(input.F, plan, self.AVERAGE), coords_key=out_key, coords_manager=cm)
 
 
-class MinkowskiGlobalPooling(_NotOnHotPath):
+class MinkowskiSumPooling(_PoolingBase):
     pass
 
 
-class MinkowskiSumPooling(_NotOnHotPath):
-    pass
+class MinkowskiAvgPooling(_PoolingBase):
+    AVERAGE = True
 
 
-class MinkowskiAvgPooling(_NotOnHotPath):
-    pass
+class MinkowskiPoolingTranspose(_PoolingBase):
+    TRANSPOSE = True
 
 
-class MinkowskiAvgUnpooling(_NotOnHotPath):
-    pass
+class MinkowskiAvgUnpooling(_PoolingBase):
+    AVERAGE, TRANSPOSE = True, True
 
 
-class MinkowskiInstanceNorm(_NotOnHotPath):
-    pass
+def _instances(input):
+    """(batch index per row as int64 [N], number of instances) of a SparseTensor."""
+    b = input.C[:, 0].long()
+    return b, int(b.max().item()) + 1 if b.numel() else 0
+
+
+class MinkowskiGlobalPooling(nn.Module):
+    """Per-instance mean (or sum) of the features: one row per batch index, on the origin coordinate map (tensor stride 0)."""
+
+    def __init__(self, average=True, dimension=-1):
+        super().__init__()
+        self.average = average
+
+    def forward(self, input):
+        _lib.require_cuda(input.F)
+        b, nb = _instances(input)
+        out = torch.zeros(nb, input.F.shape[1], dtype=input.F.dtype, device=input.F.device).index_add_(0, b, input.F)
+        if self.average:
+            out = out / torch.bincount(b, minlength=nb).clamp(min=1)[:, None].to(out.dtype)
+        return _GlobalTensor(out, input)
+
+
+class _GlobalTensor:
+    """Result of a global pooling: one feature row per instance (`.F`), remembering the tensor it was pooled from."""
+
+    def __init__(self, feats, source):
+        self.F, self.coords_key, self.coords_man = feats, source.coords_key, source.coords_man
+
+    feats = property(lambda self: self.F)
+
+
+class _BroadcastBase(nn.Module):
+    def __init__(self, dimension=-1):
+        super().__init__()
+
+    def forward(self, input, input_glob):
+        b, _ = _instances(input)
+        return SparseTensor(self._op(input.F, input_glob.F[b]), coords_key=input.coords_key, coords_manager=input.coords_man)
+
+
+class MinkowskiBroadcastAddition(_BroadcastBase):
+    _op = staticmethod(torch.add)
+
+
+class MinkowskiBroadcastMultiplication(_BroadcastBase):
+    _op = staticmethod(torch.mul)
+
+
+class MinkowskiInstanceNorm(nn.Module):
+    """Per-instance, per-channel normalisation over the instance's rows, affine (`model/modules/common.py:22-23`)."""
+
+    def __init__(self, num_features, D=-1, dimension=-1, eps=1e-6):
+        super().__init__()
+        self.num_features, self.eps = num_features, eps
+        self.weight = nn.Parameter(torch.ones(1, num_features))
+        self.bias = nn.Parameter(torch.zeros(1, num_features))
+
+    def forward(self, input):
+        _lib.require_cuda(input.F)
+        x = input.F
+        b, nb = _instances(input)
+        cnt = torch.bincount(b, minlength=nb).clamp(min=1)[:, None].to(x.dtype)
+        mean = torch.zeros(nb, x.shape[1], dtype=x.dtype, device=x.device).index_add_(0, b, x) / cnt
+        xc = x - mean[b]
+        var = torch.zeros(nb, x.shape[1], dtype=x.dtype, device=x.device).index_add_(0, b, xc * xc) / cnt
+        y = xc * torch.rsqrt(var + self.eps)[b] * self.weight + self.bias
+        return SparseTensor(y, coords_key=input.coords_key, coords_manager=input.coords_man)
 
 
 def cat(*tensors):

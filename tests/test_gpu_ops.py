@@ -458,3 +458,58 @@ def test_sgd_with_dampening_and_poly_lr_match_torch():
         assert abs(s.get_last_lr()[0] - s_ref.get_last_lr()[0]) < 1e-12
         for r, m in zip(ref, mine):
             assert torch.allclose(m.detach().cpu(), r.detach(), rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("kind", ["sum", "avg", "unpool", "pool_tr", "sum_k3"])
+def test_pooling_layers_match_oracle(kind):
+    """MinkowskiSumPooling / AvgPooling / PoolingTranspose / AvgUnpooling forward and backward vs the oracle's
+    restatement on the same kernel maps (fp64)."""
+    from pointcontrast_b200 import me
+    rng = np.random.default_rng(len(kind))
+    coords = surface_coords(rng, 4000)
+    C = 24 if kind != "sum_k3" else 6           # 6: not a multiple of 4 (padded internally)
+    g = torch.Generator().manual_seed(3)
+    cls = {"sum": "MinkowskiSumPooling", "avg": "MinkowskiAvgPooling", "unpool": "MinkowskiAvgUnpooling", "pool_tr": "MinkowskiPoolingTranspose",
+           "sum_k3": "MinkowskiSumPooling"}[kind]
+    ks, st = ([3, 3, 3], 1) if kind == "sum_k3" else ([2, 2, 2], 2)
+    layer, olayer = getattr(me, cls)(kernel_size=ks, stride=st, dimension=3), getattr(OR, cls)(kernel_size=ks, stride=st, dimension=3)
+    st0 = me.SparseTensor(torch.zeros(len(coords), 1, device="cuda"), coords=torch.from_numpy(coords))
+    ost0 = OR.SparseTensor(torch.zeros(len(coords), 1, dtype=torch.float64), coords=torch.from_numpy(coords))
+    if kind in ("unpool", "pool_tr"):
+        key = st0.coords_man.stride(st0.coords_key, [2, 2, 2]); okey = ost0.coords_man.stride(ost0.coords_key, [2, 2, 2])
+    else:
+        key, okey = st0.coords_key, ost0.coords_key
+    n_in = st0.coords_man.num_rows(key)
+    x = torch.randn(n_in, C, generator=g, dtype=torch.float64)
+    xg, xo = x.float().cuda().requires_grad_(True), x.clone().requires_grad_(True)
+    y = layer(me.SparseTensor(xg, coords_key=key, coords_manager=st0.coords_man))
+    yo = olayer(OR.SparseTensor(xo, coords_key=okey, coords_manager=ost0.coords_man))
+    assert y.F.shape == yo.F.shape and y.coords_key.ts == yo.coords_key.ts
+    dy = torch.randn(yo.F.shape, generator=g, dtype=torch.float64)
+    y.F.backward(dy.float().cuda()); yo.F.backward(dy)
+    assert max_rel_err(y.F, yo.F) < 1e-5 and max_rel_err(xg.grad, xo.grad) < 1e-5
+
+
+def test_global_pooling_broadcast_and_instance_norm():
+    """Per-instance ops of `downstream/semseg/lib/layers.py:12-90` / `model/modules/common.py:22-23` against plain torch per batch index."""
+    from pointcontrast_b200 import me
+    rng = np.random.default_rng(2)
+    coords = surface_coords(rng, 3000, batches=3)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(len(coords), 16, generator=g, dtype=torch.float64)
+    b = torch.from_numpy(coords[:, 0]).long()
+    st = me.SparseTensor(x.float().cuda(), coords=torch.from_numpy(coords))
+    glob = me.MinkowskiGlobalPooling(dimension=3)(st)
+    ref = torch.stack([x[b == i].mean(0) for i in range(3)])
+    assert max_rel_err(glob.F, ref) < 1e-5
+    added = me.MinkowskiBroadcastAddition(dimension=3)(st, glob)
+    assert max_rel_err(added.F, x + ref[b]) < 1e-5
+    mul = me.MinkowskiBroadcastMultiplication(dimension=3)(st, glob)
+    assert max_rel_err(mul.F, x * ref[b]) < 1e-5
+    inorm = me.MinkowskiInstanceNorm(16, D=3).cuda()
+    y = inorm(st).F
+    refn = torch.empty_like(x)
+    for i in range(3):
+        xi = x[b == i]
+        refn[b == i] = (xi - xi.mean(0)) / torch.sqrt(xi.var(0, unbiased=False) + 1e-6)
+    assert max_rel_err(y, refn) < 1e-4
