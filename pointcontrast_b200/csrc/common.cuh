@@ -67,10 +67,13 @@ inline void launch_kernel(void (*kernel)(Exp...), dim3 grid, dim3 block, size_t 
   cudaLaunchKernelEx(&cfg, kernel, static_cast<Act&&>(args)...);       // errors surface through check_launch (cudaGetLastError)
 }
 
+inline int current_device() { int dev = 0; cudaGetDevice(&dev); return (dev >= 0 && dev < 64) ? dev : 0; }
+
 inline int num_sms() {
-  static int n = 0;
-  if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
-  return n;
+  static int n[64] = {};
+  const int dev = current_device();
+  if (!n[dev]) { cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev); if (n[dev] <= 0) n[dev] = 148; }
+  return n[dev];
 }
 
 }  // namespace pcb

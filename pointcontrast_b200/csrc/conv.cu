@@ -659,10 +659,11 @@ int conv_splits(int K, int64_t n_out, int Cin, int Cout) {
 template <int BN>
 int launch_conv(ConvArgs a, int nsplit, float* ws, cudaStream_t st) {
   using S = ConvSmem<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};          // per device: the opt-in is a per-device function attribute
+  const int dev_ = current_device();
+  if (!attr_set[dev_]) {
     PCB_CUDA(cudaFuncSetAttribute(conv_mma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-    attr_set = true;
+    attr_set[dev_] = true;
   }
   a.partial = nsplit > 1 ? ws : nullptr;
   dim3 grid((unsigned)((a.n_out + BM - 1) / BM), a.Cout / BN, nsplit);
@@ -679,10 +680,11 @@ int launch_conv(ConvArgs a, int nsplit, float* ws, cudaStream_t st) {
 template <int TM, int TN>
 int launch_wgrad(const WgradArgs& a, int splits, cudaStream_t st) {
   using S = WgradSmem<TM, TN>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};          // per device: the opt-in is a per-device function attribute
+  const int dev_ = current_device();
+  if (!attr_set[dev_]) {
     PCB_CUDA(cudaFuncSetAttribute(wgrad_mma_kernel<TM, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-    attr_set = true;
+    attr_set[dev_] = true;
   }
   dim3 grid((unsigned)(a.K * (a.Ca / TM) * (a.Cb / TN)), splits);
   wgrad_mma_kernel<TM, TN><<<grid, NTHR, S::TOTAL, st>>>(a);

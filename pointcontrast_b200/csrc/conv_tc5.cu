@@ -485,10 +485,11 @@ __global__ void __launch_bounds__(DPROD + 32, CTAS) conv_tcgen05_split_kernel(co
 template <int BN, int DNS, int DPROD, int CTAS>
 int launch_split_cfg(const Args& a, int nsplit, cudaStream_t st) {
   using S = DSmem<BN, DNS>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};          // per device: the opt-in is a per-device function attribute
+  const int dev_ = current_device();
+  if (!attr_set[dev_]) {
     PCB_CUDA(cudaFuncSetAttribute(conv_tcgen05_split_kernel<BN, DNS, DPROD, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-    attr_set = true;
+    attr_set[dev_] = true;
   }
   dim3 grid((unsigned)((a.n_out + BM - 1) / BM), a.Cout / BN, nsplit);
   launch_kernel(conv_tcgen05_split_kernel<BN, DNS, DPROD, CTAS>, grid, DPROD + 32, S::TOTAL, st, a);
@@ -507,10 +508,11 @@ int launch_split(const Args& a, int nsplit, cudaStream_t st) {
 template <int BN, bool SPLIT>
 int launch2(const Args& a, int nsplit, cudaStream_t st) {
   using S = Smem<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};          // per device: the opt-in is a per-device function attribute
+  const int dev_ = current_device();
+  if (!attr_set[dev_]) {
     PCB_CUDA(cudaFuncSetAttribute(conv_tcgen05_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-    attr_set = true;
+    attr_set[dev_] = true;
   }
   dim3 grid((unsigned)((a.n_out + BM - 1) / BM), a.Cout / BN, nsplit);
   conv_tcgen05_kernel<BN, SPLIT><<<grid, NTHR, S::TOTAL, st>>>(a);
@@ -758,11 +760,12 @@ __global__ void __launch_bounds__(NTHR, 1) wgrad_tcgen05_kernel(const Args p) {
 
 template <int TN>
 int launch(Args a, int splits, cudaStream_t st) {
-  static bool attr_set = false;
+  static bool attr_set[64] = {};          // per device: the opt-in is a per-device function attribute
   constexpr int MAX_SMEM = 220 * 1024;
-  if (!attr_set) {
+  const int dev_ = current_device();
+  if (!attr_set[dev_]) {
     PCB_CUDA(cudaFuncSetAttribute(wgrad_tcgen05_kernel<TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
-    attr_set = true;
+    attr_set[dev_] = true;
   }
   const int mrows_max = a.Ca < WM ? a.Ca : WM;
   const int stage = stage_bytes(mrows_max, TN);

@@ -314,6 +314,9 @@ class SparseTensor:
                  allow_duplicate_coords=False, tensor_stride=1):
         if not isinstance(feats, torch.Tensor):
             raise TypeError("feats must be a torch.Tensor")
+        if allow_duplicate_coords or force_creation:
+            raise NotImplementedError("allow_duplicate_coords / force_creation are not supported: coordinates must be unique "
+                                      "(the reference voxelises before building the tensor, `lib/ddp_data_loaders.py:228-241`)")
         if coords_manager is None:
             if coords is None:
                 raise ValueError("either coords or (coords_key, coords_manager) is required")
@@ -656,6 +659,8 @@ class MinkowskiBatchNorm(nn.Module):
         super().__init__()
         if not (affine and track_running_stats):
             raise NotImplementedError("only affine, running-stat-tracking BatchNorm is on the hot path")
+        if momentum is None:
+            raise NotImplementedError("momentum=None (cumulative moving average) is not on the hot path; pass a float")
         self.bn = nn.BatchNorm1d(num_features, eps=eps, momentum=momentum, affine=affine,
                                  track_running_stats=track_running_stats)
 
