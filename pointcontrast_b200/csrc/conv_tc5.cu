@@ -864,16 +864,20 @@ __global__ void __launch_bounds__(NTHR, 1) wgrad_tcgen05_kernel(const Args p) {
     const int32_t* trow = p.tbl + (int64_t)(k0 + 2 * kh) * p.tbl_stride;
     const int32_t* trow_other = p.tbl + (int64_t)(k0 + 2 * (1 - kh)) * p.tbl_stride;
     const bool g0 = 2 * kh < nk, g1 = 2 * kh + 1 < nk, o0 = 2 * (1 - kh) < nk, o1 = 2 * (1 - kh) + 1 < nk;
-    int n0i = -1, n1i = -1, n2i = -1, n3i = -1;      // table entries of the next step: own offset pair + (B loaders) the other pair
-    int fetched = 0, loaded = 0;
-    auto fetch = [&]() {                               // independent loads only: nothing here waits on a previous load
-      const int64_t row = r_begin + (int64_t)fetched * WK + r;
-      const bool live = fetched < nsteps && row < r_end;
-      n0i = (live && g0) ? __ldg(trow + row) : -1;
-      n1i = (live && g1) ? __ldg(trow + p.tbl_stride + row) : -1;
-      n2i = (live && b_on && o0) ? __ldg(trow_other + row) : -1;
-      n3i = (live && b_on && o1) ? __ldg(trow_other + p.tbl_stride + row) : -1;
-      ++fetched;
+    // Table entries are fetched TF steps ahead of the data loads that depend on them (a register ring, shifted once per step),
+    // the data loads PF steps ahead of the shared-memory stores: neither dependent global-load latency (table -> row segment ->
+    // st.shared, ~900 cycles each under load) sits on the per-step critical path.  (ncu, round 2: with the table only ONE step ahead
+    // the producers spent 60 % of their samples in long-scoreboard stalls on exactly these two hops and a step took ~1800 cycles.)
+    constexpr int TF = 3;
+    int tq[TF][4];             // [steps loaded .. loaded + TF - 1][own offset pair (2) + (B loaders) the other pair (2)]
+    int loaded = 0;
+    auto fetch_into = [&](int (&d)[4], int step) {          // independent loads only: nothing here waits on a previous load
+      const int64_t row = r_begin + (int64_t)step * WK + r;
+      const bool live = step < nsteps && row < r_end;
+      d[0] = (live && g0) ? __ldg(trow + row) : -1;
+      d[1] = (live && g1) ? __ldg(trow + p.tbl_stride + row) : -1;
+      d[2] = (live && b_on && o0) ? __ldg(trow_other + row) : -1;
+      d[3] = (live && b_on && o1) ? __ldg(trow_other + p.tbl_stride + row) : -1;
     };
     struct Regs { uint4 h0, l0, h1, l1, hb, lb; };
     const uint4 Z = make_uint4(0, 0, 0, 0);
@@ -883,9 +887,14 @@ __global__ void __launch_bounds__(NTHR, 1) wgrad_tcgen05_kernel(const Args p) {
     auto load = [&](Regs& v) {
       if (loaded < nsteps) {
         const int64_t row = r_begin + (int64_t)loaded * WK + r;
-        const int c0 = n0i, c1 = n1i;
-        const bool any = (c0 >= 0) | (c1 >= 0) | (n2i >= 0) | (n3i >= 0);      // the B row is needed if ANY of the four offsets has a neighbour
-        fetch();
+        const int c0 = tq[0][0], c1 = tq[0][1];
+        const bool any = (c0 >= 0) | (c1 >= 0) | (tq[0][2] >= 0) | (tq[0][3] >= 0);      // the B row is needed if ANY of the four offsets has a neighbour
+#pragma unroll
+        for (int f = 0; f + 1 < TF; ++f) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) tq[f][e] = tq[f + 1][e];
+        }
+        fetch_into(tq[TF - 1], loaded + TF);
         const int64_t q0 = (int64_t)c0 * p.lda + a_col, q1 = (int64_t)c1 * p.lda + a_col;
         v.h0 = ldrow(p.Ahi, q0, a_on && c0 >= 0); v.l0 = ldrow(p.Alo, q0, a_on && c0 >= 0);
         v.h1 = ldrow(p.Ahi, q1, a_on && c1 >= 0); v.l1 = ldrow(p.Alo, q1, a_on && c1 >= 0);
@@ -915,7 +924,8 @@ __global__ void __launch_bounds__(NTHR, 1) wgrad_tcgen05_kernel(const Args p) {
       if (++is == NS) { is = 0; ++iround; }
     };
     Regs v0, v1;
-    fetch();
+#pragma unroll
+    for (int f = 0; f < TF; ++f) fetch_into(tq[f], f);
     load(v0); load(v1);
     for (int i = 0; i < nsteps; i += PF) {
       store(v0); load(v0);
