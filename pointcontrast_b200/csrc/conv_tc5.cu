@@ -278,7 +278,7 @@ struct DSmem {
 // <DNS, DPROD, CTAS>: <6, 512, 1> = one CTA per SM with a 6-slot ring; <3, 256, 2> = two CTAs per SM with 3 slots each --
 // every hand-off (mbarrier wake-up ~260 cycles, smem store -> fence -> arrive, MMA issue) is a serial chain inside a CTA,
 // so two co-resident CTAs hide each other's chains.
-template <int BN, int DNS, int DPROD, int CTAS>
+template <int BN, int DNS, int DPROD, int CTAS, int PF = 3>
 __global__ void __launch_bounds__(DPROD + 32, CTAS) conv_tcgen05_split_kernel(const Args p) {
   using S = DSmem<BN, DNS>;
   constexpr int DTHR = DPROD + 32;
@@ -341,7 +341,6 @@ __global__ void __launch_bounds__(DPROD + 32, CTAS) conv_tcgen05_split_kernel(co
     // plane): 128-bit global loads into registers PF stages ahead, 128-bit shared stores when the slot is free.
     // The weight tile of a stage is ONE TMA bulk copy (the weights are pre-tiled as shared-memory images), issued by
     // thread 0 and completed on the same "full" barrier through its transaction count.
-    constexpr int PF = 3;
     constexpr int RP = BM * 4 / DPROD;                  // (row, chunk) pairs per thread: rows ar + j * (DPROD / 4)
     constexpr uint32_t BLOB = 2 * S::B_PLANE;
     const int ar = tid >> 2, ak8 = tid & 3;
@@ -406,12 +405,14 @@ __global__ void __launch_bounds__(DPROD + 32, CTAS) conv_tcgen05_split_kernel(co
       if (++is == DNS) { is = 0; ++iround; }
       if (++s_kc == nkc) { s_kc = 0; ++s_kq; }
     };
-    Regs v0, v1, v2;
+    Regs v0, v1, v2, v3;
     load(v0); load(v1); load(v2);
+    if (PF == 4) load(v3);
     for (int i = 0; i < n_it; i += PF) {
       store(v0); load(v0);
       if (i + 1 < n_it) { store(v1); load(v1); }
       if (i + 2 < n_it) { store(v2); load(v2); }
+      if (PF == 4 && i + 3 < n_it) { store(v3); load(v3); }
     }
   } else if (lane == 0) {
     // ===== MMA issuer =====
@@ -703,17 +704,17 @@ int launch_wide(const Args& a, cudaStream_t st) {
   return check_launch("conv_tcgen05_wide_kernel");
 }
 
-template <int BN, int DNS, int DPROD, int CTAS>
+template <int BN, int DNS, int DPROD, int CTAS, int PF = 3>
 int launch_split_cfg(const Args& a, int nsplit, cudaStream_t st) {
   using S = DSmem<BN, DNS>;
   static bool attr_set[64] = {};          // per device: the opt-in is a per-device function attribute
   const int dev_ = current_device();
   if (!attr_set[dev_]) {
-    PCB_CUDA(cudaFuncSetAttribute(conv_tcgen05_split_kernel<BN, DNS, DPROD, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    PCB_CUDA(cudaFuncSetAttribute(conv_tcgen05_split_kernel<BN, DNS, DPROD, CTAS, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     attr_set[dev_] = true;
   }
   dim3 grid((unsigned)((a.n_out + BM - 1) / BM), a.Cout / BN, nsplit);
-  launch_kernel(conv_tcgen05_split_kernel<BN, DNS, DPROD, CTAS>, grid, DPROD + 32, S::TOTAL, st, a);
+  launch_kernel(conv_tcgen05_split_kernel<BN, DNS, DPROD, CTAS, PF>, grid, DPROD + 32, S::TOTAL, st, a);
   return check_launch("conv_tcgen05_split_kernel");
 }
 
@@ -728,6 +729,7 @@ int launch_split(const Args& a, int nsplit, cudaStream_t st) {
   }
   if (cfg == 1) return launch_split_cfg<BN, 6, 512, 1>(a, nsplit, st);
   if (cfg == 3) return launch_split_cfg<BN, 2, 256, 3>(a, nsplit, st);
+  if (cfg == 5) return launch_split_cfg<BN, 3, 256, 2, 4>(a, nsplit, st);         // gathered rows loaded 4 (not 3) stages ahead
   return launch_split_cfg<BN, 3, 256, 2>(a, nsplit, st);
 }
 
