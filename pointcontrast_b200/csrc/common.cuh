@@ -48,7 +48,7 @@ struct ProfScope {
   ~ProfScope() { prof_end(st, kind); }
 };
 
-// Programmatic dependent launch (PCB_PDL=1): every kernel below starts with pdl_wait() -- it blocks until the preceding kernel of
+// Programmatic dependent launch (default; PCB_PDL=0 turns it off): every kernel below starts with pdl_wait() -- it blocks until the preceding kernel of
 // the stream has completed and its writes are visible -- followed by pdl_trigger(), which lets the NEXT kernel's CTAs be scheduled
 // as soon as all of this kernel's CTAs are running.  The launch latency and CTA ramp-up of a kernel then overlap the tail of its
 // predecessor; ordering is unchanged (nothing precedes the wait).  Launched without the attribute, both are no-ops.

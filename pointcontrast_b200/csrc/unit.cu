@@ -40,7 +40,7 @@ cudaEvent_t prof_event() {
 namespace pcb {
 bool pdl_enabled() {
   static int on = -1;
-  if (on < 0) { const char* e = getenv("PCB_PDL"); on = (e && atoi(e) != 0) ? 1 : 0; }
+  if (on < 0) { const char* e = getenv("PCB_PDL"); on = (e && atoi(e) == 0) ? 0 : 1; }      // on by default; PCB_PDL=0 disables
   return on == 1;
 }
 void prof_begin(cudaStream_t st) {
