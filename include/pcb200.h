@@ -108,19 +108,16 @@ int pcb_radius_pairs(const float* src, int64_t ns, const float* dst, int64_t nd,
 int pcb_weight_prep(const float* W, int K, int Cin, int Cout, uint16_t* w_hi, uint16_t* w_lo,
                     uint16_t* wt_hi, uint16_t* wt_lo, void* stream);
 
-/* Y[j, :] = bias + sum_k X[tbl[kmap[k]][j], :] . W[k]      (j < n_out)
+/* Y[j, :] = bias + sum_k X[tbl[kmap[k]][j], :] . W[k]      (j < n_out)      -- fp32 operands (the modular ME-style surface)
  *   X  : [*, Cin] row stride ldx (floats);  Y: [n_out, Cout] row stride ldy.
- *   w_hi/w_lo : bf16 split weights [K][Cin][Cout] for THIS call's (Cin, Cout) roles (use the wt_* planes and
- *               swapped channel counts for the data gradient).   w_f32: the fp32 weights in the same layout
- *               (used by the exact SIMT path; may be NULL when the tensor-core path applies).
- *   wk_hi/wk_lo : the same weights K-major, [K][Cout][Cin] (the transposed planes of pcb_weight_prep), used by the
- *               tcgen05 kernel (PCB_CONV_TCGEN05); may be NULL otherwise.
- *   kmap      : HOST int32 [K] table row used by weight k (NULL = identity).
- *   flags     : PCB_CONV_FORCE_SIMT forces the exact fp32 SIMT kernel.
- * Tensor-core path (bf16x3 split, fp32 accumulate) requires Cin % 32 == 0, Cout % 32 == 0, K <= 27. */
+ *   wk_hi/wk_lo : the weights of THIS call's roles as bf16 hi/lo planes, K-major = [K][Cout][Cin] (pcb_weight_prep: the wt_* planes for
+ *               the forward roles; the w_* planes with swapped channel counts for the data gradient).  Tensor-core path (tcgen05, fp32 rows
+ *               split to bf16 hi/lo in the producers' registers, fp32 accumulate in TMEM): Cin % 32 == 0, Cout % 32 == 0, K <= 27.
+ *   w_f32     : fp32 weights [K][Cin][Cout] for the exact SIMT path (other widths, the 3-channel stem, PCB_CONV_FORCE_SIMT); may be NULL
+ *               when the tensor-core path applies.
+ *   kmap      : HOST int32 [K] table row used by weight k (NULL = identity). */
 #define PCB_CONV_FORCE_SIMT 1
-#define PCB_CONV_TCGEN05 2     /* use the tcgen05/TMEM kernel (needs wk_hi/wk_lo = the K-major planes [K][Cout][Cin]) */
-#define PCB_CONV_ACCUMULATE 4  /* Y += result (pcb_conv_forward, tcgen05 path) / dW += result (pcb_conv_wgrad) */
+#define PCB_CONV_ACCUMULATE 4  /* Y += result (tensor-core paths) / dW += result (weight gradients) */
 #define PCB_PLANES_A_FP16 8    /* split-operand calls: the GATHERED operand's planes are fp16 hi/lo (default: bf16 hi/lo) */
 #define PCB_PLANES_B_FP16 16   /* pcb_conv_forward_split: the weight tiles are fp16 x 2^10 (pcb_weight_tile with this flag);
                                   pcb_conv_wgrad_split: the ROW-ALIGNED operand's planes are fp16.  Both operands of a call must
@@ -128,9 +125,8 @@ int pcb_weight_prep(const float* W, int K, int Cin, int Cout, uint16_t* w_hi, ui
 /* Small levels split the (offset, channel-chunk) loop over extra CTAs and reduce through `ws` (deterministic). */
 size_t pcb_conv_forward_ws_bytes(int K, int64_t n_out, int Cin, int Cout);
 int pcb_conv_forward(const float* X, int ldx, const int32_t* tbl, int64_t tbl_stride, const int32_t* kmap, int K,
-                     int64_t n_out, int Cin, int Cout, const uint16_t* w_hi, const uint16_t* w_lo,
-                     const uint16_t* wk_hi, const uint16_t* wk_lo, const float* w_f32, const float* bias, float* Y,
-                     int ldy, void* ws, size_t ws_bytes, int flags, void* stream);
+                     int64_t n_out, int Cin, int Cout, const uint16_t* wk_hi, const uint16_t* wk_lo, const float* w_f32,
+                     const float* bias, float* Y, int ldy, void* ws, size_t ws_bytes, int flags, void* stream);
 
 /* Y[j, :] = sum_k X[tbl[kmap[k]][j], :];  cnt[j] (optional) = number of neighbours present.  The sum / average pooling and unpooling
  * layers of the sibling models (MinkowskiSumPooling / AvgPooling / PoolingTranspose / AvgUnpooling, `model/modules/common.py:170-214`,
@@ -139,7 +135,9 @@ int pcb_gather_sum(const float* X, int ldx, const int32_t* tbl, int64_t tbl_stri
                    float* Y, int ldy, float* cnt, void* stream);
 
 /* dW[k] = sum_j A[tbl[k][j], :]^T . B[j, :]       A: gathered [*, Ca] (lda), B: contiguous rows [n_out, Cb] (ldb).
- *   transpose_out = 0: dW is [K][Ca][Cb];  1: dW is [K][Cb][Ca]. */
+ *   transpose_out = 0: dW is [K][Ca][Cb];  1: dW is [K][Cb][Ca].
+ * pcb_conv_wgrad: EXACT fp32 kernels on fp32 operands (the 3-channel stem layer, widths the tensor-core tiling does not cover, cross-checks);
+ * the tensor-core weight gradient is pcb_conv_wgrad_split on split operands. */
 size_t pcb_conv_wgrad_ws_bytes(int K, int64_t n_out, int Ca, int Cb);
 int pcb_conv_wgrad(const float* A, int lda, const float* B, int ldb, const int32_t* tbl, int64_t tbl_stride, int K,
                    int64_t n_out, int Ca, int Cb, float* dW, int transpose_out, void* ws, size_t ws_bytes,

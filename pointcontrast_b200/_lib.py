@@ -42,7 +42,7 @@ _SIGS = {
     "pcb_kernel_map_count": (_i, [_p, _i, _l, _p, _p]),
     "pcb_weight_prep": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _p]),
     "pcb_conv_forward_ws_bytes": (_sz, [_i, _l, _i, _i]),
-    "pcb_conv_forward": (_i, [_p, _i, _p, _l, _p, _i, _l, _i, _i, _p, _p, _p, _p, _p, _p, _p, _i, _p, _sz, _i, _p]),
+    "pcb_conv_forward": (_i, [_p, _i, _p, _l, _p, _i, _l, _i, _i, _p, _p, _p, _p, _p, _i, _p, _sz, _i, _p]),
     "pcb_gather_sum": (_i, [_p, _i, _p, _l, _p, _i, _l, _i, _p, _i, _p, _p]),
     "pcb_conv_wgrad_ws_bytes": (_sz, [_i, _l, _i, _i]),
     "pcb_conv_wgrad": (_i, [_p, _i, _p, _i, _p, _l, _i, _l, _i, _i, _p, _i, _p, _sz, _i, _p]),

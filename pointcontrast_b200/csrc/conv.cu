@@ -19,238 +19,11 @@ using namespace pcb;
 
 namespace {
 
-// --------------------------------------------------------------------------------------------- PTX helpers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::); }
-
-__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
-}
-__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
-}
-__device__ __forceinline__ void ldsm_x2_t(uint32_t (&r)[2], uint32_t addr) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];\n"
-               : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
-}
-__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
-               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-
-// fp32 x4 -> bf16 hi x4 (8 bytes) + bf16 lo x4 (8 bytes)
-__device__ __forceinline__ void split4(const float4& v, uint2& hi, uint2& lo) {
-  __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y);
-  __nv_bfloat162 h1 = __floats2bfloat162_rn(v.z, v.w);
-  float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
-  __nv_bfloat162 l0 = __floats2bfloat162_rn(v.x - f0.x, v.y - f0.y);
-  __nv_bfloat162 l1 = __floats2bfloat162_rn(v.z - f1.x, v.w - f1.y);
-  hi.x = *reinterpret_cast<uint32_t*>(&h0); hi.y = *reinterpret_cast<uint32_t*>(&h1);
-  lo.x = *reinterpret_cast<uint32_t*>(&l0); lo.y = *reinterpret_cast<uint32_t*>(&l1);
-}
-
 struct KMap { int v[PCB_MAX_KERNEL_VOLUME]; };
 
-// --------------------------------------------------------------------------------------------- forward (tensor cores)
-constexpr int BM = 128;        // output rows per CTA
-constexpr int BK = 32;         // input channels per pipeline step (one 128-byte line of every gathered row)
-constexpr int NTHR = 256;      // 8 warps: 4 (rows) x 2 (cols)
-constexpr int A_STRIDE = BK * 2 + 16;   // bytes per smem row, +16 keeps ldmatrix conflict-free
+constexpr int BM = 128;        // output rows per CTA tile of the tensor-core kernels (conv_tc5.cu)
+constexpr int BK = 32;         // input channels per pipeline step
 
-struct ConvArgs {
-  const float* X; int ldx;
-  const int32_t* tbl; int64_t tbl_stride;
-  KMap kmap; int K;
-  int64_t n_out; int Cin; int Cout;
-  const __nv_bfloat16* w_hi; const __nv_bfloat16* w_lo;
-  const float* bias;
-  float* Y; int ldy;
-  float* partial;     // non-NULL: gridDim.z CTAs split the (offset, channel-chunk) loop; tile sums go to partial[z][row][Cout]
-};
-
-template <int BN>
-struct ConvSmem {
-  static constexpr int B_STRIDE = BN * 2 + 16;
-  static constexpr int A_PLANE = BM * A_STRIDE;
-  static constexpr int B_PLANE = BK * B_STRIDE;
-  static constexpr int STAGE = 2 * A_PLANE + 2 * B_PLANE;
-  static constexpr int IDX_OFF = 2 * STAGE;
-  static constexpr int META_OFF = IDX_OFF + PCB_MAX_KERNEL_VOLUME * BM * 4;
-  static constexpr int TOTAL = META_OFF + 3 * 32 * 4;
-};
-
-template <int BN>
-__global__ void __launch_bounds__(NTHR, 2) conv_mma_kernel(const ConvArgs p) {
-  using S = ConvSmem<BN>;
-  constexpr int WN = BN / 2;       // columns per warp
-  constexpr int NT = WN / 8;       // n8 tiles per warp (even)
-  extern __shared__ __align__(128) unsigned char smem[];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = warp & 3, wn = warp >> 2;
-  const int64_t row0 = (int64_t)blockIdx.x * BM;
-  const int n0 = blockIdx.y * BN;
-  int* s_idx = reinterpret_cast<int*>(smem + S::IDX_OFF);
-  int* s_flag = reinterpret_cast<int*>(smem + S::META_OFF);
-  int* s_klist = s_flag + 32;
-  int* s_nk = s_klist + 32;
-
-  // ---- neighbour rows of this tile for every kernel offset
-  for (int e = tid; e < p.K * BM; e += NTHR) {
-    int k = e / BM, r = e - k * BM;
-    int64_t row = row0 + r;
-    int v = -1;
-    if (row < p.n_out) v = p.tbl[(int64_t)p.kmap.v[k] * p.tbl_stride + row];
-    s_idx[e] = v;
-  }
-  __syncthreads();
-  for (int k = warp; k < p.K; k += NTHR / 32) {      // which 32-row slabs have any neighbour for offset k
-    unsigned m = 0;
-#pragma unroll
-    for (int s = 0; s < 4; ++s) {
-      unsigned b = __ballot_sync(0xffffffffu, s_idx[k * BM + s * 32 + lane] >= 0);
-      if (b) m |= 1u << s;
-    }
-    if (lane == 0) s_flag[k] = (int)m;
-  }
-  __syncthreads();
-  if (tid == 0) {
-    int nk = 0;
-    for (int k = 0; k < p.K; ++k) if (s_flag[k]) s_klist[nk++] = k;
-    *s_nk = nk;
-  }
-  __syncthreads();
-  const int nk = *s_nk;
-  const int nkc = p.Cin / BK;
-  const int T = nk * nkc;
-
-  float acc[2][NT][4];
-#pragma unroll
-  for (int a = 0; a < 2; ++a)
-#pragma unroll
-    for (int b = 0; b < NT; ++b)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.f;
-
-  const uint32_t smem_base = smem_u32(smem);
-  const int a_chunk = tid & 7;      // which 16-byte piece of the 128-byte row segment
-  const int a_row = tid >> 3;       // + 32*i
-
-  auto load_B = [&](int stage, int it) {
-    const int k = s_klist[it / nkc], kc = it % nkc;
-    constexpr int CH = BN / 8;                       // 16-byte chunks per weight row
-    constexpr int PER_PLANE = BK * CH;
-    for (int c = tid; c < 2 * PER_PLANE; c += NTHR) {
-      int plane = c / PER_PLANE, rem = c - plane * PER_PLANE;
-      int r = rem / CH, ch = rem - r * CH;
-      const __nv_bfloat16* src = (plane ? p.w_lo : p.w_hi) + ((int64_t)k * p.Cin + kc * BK + r) * p.Cout + n0 + ch * 8;
-      uint32_t dst = smem_base + stage * S::STAGE + 2 * S::A_PLANE + plane * S::B_PLANE + r * S::B_STRIDE + ch * 16;
-      cp_async16(dst, src);
-    }
-    cp_async_commit();
-  };
-  auto load_A = [&](int it, float4 (&v)[4]) {
-    const int k = s_klist[it / nkc], kc = it % nkc;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      int idx = s_idx[k * BM + a_row + 32 * i];
-      if (idx >= 0) v[i] = __ldg(reinterpret_cast<const float4*>(p.X + (int64_t)idx * p.ldx + kc * BK) + a_chunk);
-      else v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-  };
-  auto store_A = [&](int stage, const float4 (&v)[4]) {
-    unsigned char* base = smem + stage * S::STAGE;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      uint2 hi, lo;
-      split4(v[i], hi, lo);
-      int off = (a_row + 32 * i) * A_STRIDE + a_chunk * 8;
-      *reinterpret_cast<uint2*>(base + off) = hi;
-      *reinterpret_cast<uint2*>(base + S::A_PLANE + off) = lo;
-    }
-  };
-  auto compute = [&](int stage, int it) {
-    const int k = s_klist[it / nkc];
-    if (!((s_flag[k] >> wm) & 1)) return;            // this warp's 32 rows have no neighbour at offset k
-    const uint32_t a_base = smem_base + stage * S::STAGE;
-    const uint32_t b_base = a_base + 2 * S::A_PLANE;
-#pragma unroll
-    for (int ks = 0; ks < BK / 16; ++ks) {
-      uint32_t ah[2][4], al[2][4];
-#pragma unroll
-      for (int mi = 0; mi < 2; ++mi) {
-        uint32_t addr = a_base + (wm * 32 + mi * 16 + (lane & 15)) * A_STRIDE + (ks * 16 + (lane >> 4) * 8) * 2;
-        ldsm_x4(ah[mi], addr);
-        ldsm_x4(al[mi], addr + S::A_PLANE);
-      }
-#pragma unroll
-      for (int np = 0; np < NT / 2; ++np) {
-        uint32_t bh[4], bl[4];
-        uint32_t addr = b_base + (ks * 16 + ((lane >> 3) & 1) * 8 + (lane & 7)) * S::B_STRIDE +
-                        (wn * WN + np * 16 + (lane >> 4) * 8) * 2;
-        ldsm_x4_t(bh, addr);
-        ldsm_x4_t(bl, addr + S::B_PLANE);
-#pragma unroll
-        for (int mi = 0; mi < 2; ++mi)
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            mma_bf16(acc[mi][2 * np + j], al[mi], bh[2 * j], bh[2 * j + 1]);
-            mma_bf16(acc[mi][2 * np + j], ah[mi], bl[2 * j], bl[2 * j + 1]);
-            mma_bf16(acc[mi][2 * np + j], ah[mi], bh[2 * j], bh[2 * j + 1]);
-          }
-      }
-    }
-  };
-
-  const int it0 = (int)((int64_t)T * blockIdx.z / gridDim.z);
-  const int it1 = (int)((int64_t)T * (blockIdx.z + 1) / gridDim.z);
-  if (it1 > it0) {
-    float4 v[4];
-    load_B(0, it0);
-    load_A(it0, v);
-    store_A(0, v);
-    cp_async_wait_all();
-    __syncthreads();
-    for (int it = it0; it < it1; ++it) {
-      const int s = (it - it0) & 1;
-      const bool more = (it + 1 < it1);
-      if (more) { load_B(s ^ 1, it + 1); load_A(it + 1, v); }
-      compute(s, it);
-      if (more) store_A(s ^ 1, v);
-      cp_async_wait_all();
-      __syncthreads();
-    }
-  }
-
-  // ---- epilogue: fp32 accumulators -> Y (each quad writes 32 contiguous bytes per row)
-  const int g = lane >> 2, t = lane & 3;
-  float* outp = p.partial ? p.partial + (int64_t)blockIdx.z * p.n_out * p.Cout : p.Y;
-  const int ldo = p.partial ? p.Cout : p.ldy;
-  const float* bias = p.partial ? nullptr : p.bias;
-#pragma unroll
-  for (int mi = 0; mi < 2; ++mi)
-#pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
-      int col = n0 + wn * WN + nt * 8 + 2 * t;
-      float b0 = 0.f, b1 = 0.f;
-      if (bias) { b0 = bias[col]; b1 = bias[col + 1]; }
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        int64_t row = row0 + wm * 32 + mi * 16 + g + h * 8;
-        if (row < p.n_out) {
-          float2 o = make_float2(acc[mi][nt][2 * h] + b0, acc[mi][nt][2 * h + 1] + b1);
-          *reinterpret_cast<float2*>(outp + row * ldo + col) = o;
-        }
-      }
-    }
-}
 
 // Y[row, c] = bias[c] + sum_z partial[z][row][c]   (fixed order: deterministic)
 __global__ void conv_split_reduce_kernel(const float* __restrict__ partial, int nsplit, int64_t n_out, int Cout,
@@ -354,185 +127,16 @@ __global__ void __launch_bounds__(128) conv_stem_kernel(const float* __restrict_
   for (int q = 0; q < 8; ++q) yo[q] = make_float4(acc[q * 4], acc[q * 4 + 1], acc[q * 4 + 2], acc[q * 4 + 3]);
 }
 
-// --------------------------------------------------------------------------------------------- weight gradient (tensor cores)
-constexpr int WK = 32;    // rows (reduction dim) per pipeline step
-
+// --------------------------------------------------------------------------------------------- weight gradient (exact fp32)
 struct WgradArgs {
-  const float* A; int lda;
-  const float* B; int ldb;
+  const float* A; int lda;      // gathered operand  [*, Ca]
+  const float* B; int ldb;      // row-aligned operand [n_out, Cb]
   const int32_t* tbl; int64_t tbl_stride;
-  int K; int64_t n_out;
-  int Ca; int Cb;
+  int K; int64_t n_out; int Ca; int Cb;
   int rows_per_split;
-  float* partial;       // [splits][K][Ca][Cb] (or transposed)
+  float* partial;               // [splits][K][Ca][Cb] (or transposed)
   int transpose_out;
 };
-
-template <int TM, int TN>
-struct WgradSmem {
-  static constexpr int AS = TM * 2 + 16;
-  static constexpr int BS = TN * 2 + 16;
-  static constexpr int A_PLANE = WK * AS;
-  static constexpr int B_PLANE = WK * BS;
-  static constexpr int STAGE = 2 * A_PLANE + 2 * B_PLANE;
-  static constexpr int TOTAL = 2 * STAGE;
-};
-
-// grid: x = K * mblocks * nblocks, y = splits.  8 warps as 2 (M) x 4 (N).
-template <int TM, int TN>
-__global__ void __launch_bounds__(NTHR, 2) wgrad_mma_kernel(const WgradArgs p) {
-  using S = WgradSmem<TM, TN>;
-  constexpr int MT = TM / 2 / 16;      // m16 tiles per warp
-  constexpr int NT = TN / 4 / 8;       // n8 tiles per warp
-  constexpr int ACH = TM / 4;          // float4 chunks per gathered A row
-  constexpr int BCH = TN / 4;
-  constexpr int AV = (WK * ACH + NTHR - 1) / NTHR;
-  constexpr int BV = (WK * BCH + NTHR - 1) / NTHR;
-  extern __shared__ __align__(128) unsigned char smem[];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = warp & 1, wn = warp >> 1;
-  const int mblocks = p.Ca / TM, nblocks = p.Cb / TN;
-  int bx = blockIdx.x;
-  const int nb = bx % nblocks; bx /= nblocks;
-  const int mb = bx % mblocks; bx /= mblocks;
-  const int k = bx;
-  const int split = blockIdx.y;
-  const int64_t r_begin = (int64_t)split * p.rows_per_split;
-  const int64_t r_end = min(p.n_out, r_begin + p.rows_per_split);
-  const int m0 = mb * TM, n0 = nb * TN;
-  const int32_t* trow = p.tbl + (int64_t)k * p.tbl_stride;
-
-  float acc[MT][NT][4];
-#pragma unroll
-  for (int a = 0; a < MT; ++a)
-#pragma unroll
-    for (int b = 0; b < NT; ++b)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.f;
-
-  const uint32_t smem_base = smem_u32(smem);
-  const int nsteps = (int)((r_end - r_begin + WK - 1) / WK);
-
-  auto load = [&](int step, float4 (&va)[AV], float4 (&vb)[BV], bool& any) {
-    const int64_t rbase = r_begin + (int64_t)step * WK;
-    int my = -1;
-    if (lane < WK) { int64_t r = rbase + lane; if (r < r_end) my = trow[r]; }
-    unsigned bal = __ballot_sync(0xffffffffu, my >= 0);
-    any = bal != 0;
-#pragma unroll
-    for (int i = 0; i < AV; ++i) {
-      int e = tid + i * NTHR;
-      const bool ok = e < WK * ACH;
-      int r = ok ? e / ACH : 0, c = e - r * ACH;
-      int idx = __shfl_sync(0xffffffffu, my, r);      // executed by the full warp
-      va[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (ok && idx >= 0) va[i] = __ldg(reinterpret_cast<const float4*>(p.A + (int64_t)idx * p.lda + m0) + c);
-    }
-#pragma unroll
-    for (int i = 0; i < BV; ++i) {
-      int e = tid + i * NTHR;
-      vb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (e < WK * BCH) {
-        int r = e / BCH, c = e - r * BCH;
-        int64_t row = rbase + r;
-        if (any && row < r_end && ((bal >> r) & 1))
-          vb[i] = __ldg(reinterpret_cast<const float4*>(p.B + row * p.ldb + n0) + c);
-      }
-    }
-  };
-  auto store = [&](int stage, const float4 (&va)[AV], const float4 (&vb)[BV]) {
-    unsigned char* base = smem + stage * S::STAGE;
-#pragma unroll
-    for (int i = 0; i < AV; ++i) {
-      int e = tid + i * NTHR;
-      if (e < WK * ACH) {
-        int r = e / ACH, c = e - r * ACH;
-        uint2 hi, lo; split4(va[i], hi, lo);
-        *reinterpret_cast<uint2*>(base + r * S::AS + c * 8) = hi;
-        *reinterpret_cast<uint2*>(base + S::A_PLANE + r * S::AS + c * 8) = lo;
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < BV; ++i) {
-      int e = tid + i * NTHR;
-      if (e < WK * BCH) {
-        int r = e / BCH, c = e - r * BCH;
-        uint2 hi, lo; split4(vb[i], hi, lo);
-        *reinterpret_cast<uint2*>(base + 2 * S::A_PLANE + r * S::BS + c * 8) = hi;
-        *reinterpret_cast<uint2*>(base + 2 * S::A_PLANE + S::B_PLANE + r * S::BS + c * 8) = lo;
-      }
-    }
-  };
-  auto compute = [&](int stage) {
-    const uint32_t a_base = smem_base + stage * S::STAGE;
-    const uint32_t b_base = a_base + 2 * S::A_PLANE;
-#pragma unroll
-    for (int ks = 0; ks < WK / 16; ++ks) {
-      uint32_t ah[MT][4], al[MT][4];
-#pragma unroll
-      for (int mi = 0; mi < MT; ++mi) {
-        // A operand = gathered rows transposed: smem is [row j (k-dim)][channel (m-dim)] -> ldmatrix.trans
-        uint32_t addr = a_base + (ks * 16 + (lane >> 4) * 8 + (lane & 7)) * S::AS +
-                        (wm * (TM / 2) + mi * 16 + ((lane >> 3) & 1) * 8) * 2;
-        ldsm_x4_t(ah[mi], addr);
-        ldsm_x4_t(al[mi], addr + S::A_PLANE);
-      }
-#pragma unroll
-      for (int ni = 0; ni < NT; ++ni) {
-        uint32_t bh[2], bl[2];
-        uint32_t addr = b_base + (ks * 16 + (lane & 15)) * S::BS + (wn * (TN / 4) + ni * 8) * 2;
-        ldsm_x2_t(bh, addr);
-        ldsm_x2_t(bl, addr + S::B_PLANE);
-#pragma unroll
-        for (int mi = 0; mi < MT; ++mi) {
-          mma_bf16(acc[mi][ni], al[mi], bh[0], bh[1]);
-          mma_bf16(acc[mi][ni], ah[mi], bl[0], bl[1]);
-          mma_bf16(acc[mi][ni], ah[mi], bh[0], bh[1]);
-        }
-      }
-    }
-  };
-
-  // software pipeline; steps whose 32 rows have no neighbour are skipped (block-uniform decision via smem flag)
-  __shared__ int s_any[2];
-  if (nsteps > 0) {
-    float4 va[AV], vb[BV];
-    bool any;
-    load(0, va, vb, any);
-    store(0, va, vb);
-    if (tid == 0) s_any[0] = any ? 1 : 0;
-    __syncthreads();
-    for (int step = 0; step < nsteps; ++step) {
-      const int s = step & 1;
-      const bool more = step + 1 < nsteps;
-      bool any_next = false;
-      if (more) load(step + 1, va, vb, any_next);
-      if (s_any[s]) compute(s);
-      if (more) { store(s ^ 1, va, vb); if (tid == 0) s_any[s ^ 1] = any_next ? 1 : 0; }
-      __syncthreads();
-    }
-  }
-
-  // ---- write the partial tile
-  const int g = lane >> 2, t = lane & 3;
-  float* out = p.partial + ((int64_t)split * p.K + k) * (int64_t)p.Ca * p.Cb;
-#pragma unroll
-  for (int mi = 0; mi < MT; ++mi)
-#pragma unroll
-    for (int ni = 0; ni < NT; ++ni)
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        int m = m0 + wm * (TM / 2) + mi * 16 + g + h * 8;
-        int n = n0 + wn * (TN / 4) + ni * 8 + 2 * t;
-        float v0 = acc[mi][ni][2 * h], v1 = acc[mi][ni][2 * h + 1];
-        if (!p.transpose_out) {
-          *reinterpret_cast<float2*>(out + (int64_t)m * p.Cb + n) = make_float2(v0, v1);
-        } else {
-          out[(int64_t)n * p.Ca + m] = v0;
-          out[(int64_t)(n + 1) * p.Ca + m] = v1;
-        }
-      }
-}
 
 // exact fp32 SIMT weight gradient: block = (k, split), threads stride over the Ca*Cb outputs
 __global__ void wgrad_simt_kernel(const WgradArgs p) {
@@ -656,41 +260,6 @@ int conv_splits(int K, int64_t n_out, int Cin, int Cout) {
   return s < 2 ? 1 : (int)s;
 }
 
-template <int BN>
-int launch_conv(ConvArgs a, int nsplit, float* ws, cudaStream_t st) {
-  using S = ConvSmem<BN>;
-  static bool attr_set[64] = {};          // per device: the opt-in is a per-device function attribute
-  const int dev_ = current_device();
-  if (!attr_set[dev_]) {
-    PCB_CUDA(cudaFuncSetAttribute(conv_mma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-    attr_set[dev_] = true;
-  }
-  a.partial = nsplit > 1 ? ws : nullptr;
-  dim3 grid((unsigned)((a.n_out + BM - 1) / BM), a.Cout / BN, nsplit);
-  conv_mma_kernel<BN><<<grid, NTHR, S::TOTAL, st>>>(a);
-  if (int e = check_launch("conv_mma_kernel")) return e;
-  if (nsplit > 1) {
-    int64_t n4 = a.n_out * (a.Cout / 4);
-    launch_kernel(conv_split_reduce_kernel, (unsigned)((n4 + 255) / 256), 256, 0, st, ws, nsplit, a.n_out, a.Cout, a.bias, a.Y, a.ldy, 0);
-    return check_launch("conv_split_reduce_kernel");
-  }
-  return PCB_OK;
-}
-
-template <int TM, int TN>
-int launch_wgrad(const WgradArgs& a, int splits, cudaStream_t st) {
-  using S = WgradSmem<TM, TN>;
-  static bool attr_set[64] = {};          // per device: the opt-in is a per-device function attribute
-  const int dev_ = current_device();
-  if (!attr_set[dev_]) {
-    PCB_CUDA(cudaFuncSetAttribute(wgrad_mma_kernel<TM, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-    attr_set[dev_] = true;
-  }
-  dim3 grid((unsigned)(a.K * (a.Ca / TM) * (a.Cb / TN)), splits);
-  wgrad_mma_kernel<TM, TN><<<grid, NTHR, S::TOTAL, st>>>(a);
-  return check_launch("wgrad_mma_kernel");
-}
-
 int wgrad_splits(int K, int64_t n_out, int Ca, int Cb, int tm, int tn) {
   int64_t base = (int64_t)K * (tm ? Ca / tm : 1) * (tn ? Cb / tn : 1);
   int64_t target = 4ll * num_sms();
@@ -730,7 +299,7 @@ extern "C" size_t pcb_conv_forward_ws_bytes(int K, int64_t n_out, int Cin, int C
 }
 
 extern "C" int pcb_conv_forward(const float* X, int ldx, const int32_t* tbl, int64_t tbl_stride, const int32_t* kmap, int K,
-                                int64_t n_out, int Cin, int Cout, const uint16_t* w_hi, const uint16_t* w_lo,
+                                int64_t n_out, int Cin, int Cout,
                                 const uint16_t* wk_hi, const uint16_t* wk_lo, const float* w_f32, const float* bias, float* Y,
                                 int ldy, void* ws, size_t ws_bytes, int flags, void* stream) {
   PCB_ARG(K >= 1 && K <= PCB_MAX_KERNEL_VOLUME && n_out >= 0 && Cin >= 1 && Cout >= 1 && ldx >= Cin && ldy >= Cout);
@@ -740,8 +309,7 @@ extern "C" int pcb_conv_forward(const float* X, int ldx, const int32_t* tbl, int
   ProfScope prof(st, 0);
   KMap km;
   for (int k = 0; k < K; ++k) { km.v[k] = kmap ? kmap[k] : k; PCB_ARG(km.v[k] >= 0 && km.v[k] < PCB_MAX_KERNEL_VOLUME); }
-  const bool tc_ok = (Cin % 32 == 0) && (Cout % 32 == 0) && (ldx % 4 == 0) && (ldy % 2 == 0) && w_hi && w_lo &&
-                     !(flags & PCB_CONV_FORCE_SIMT);
+  const bool tc_ok = (Cin % 32 == 0) && (Cout % 32 == 0) && (ldx % 4 == 0) && wk_hi && wk_lo && !(flags & PCB_CONV_FORCE_SIMT);
   if (!tc_ok) {
     if (flags & PCB_CONV_ACCUMULATE) { set_error("PCB_CONV_ACCUMULATE needs the tcgen05 path"); return PCB_ERR_ARG; }
     if (!w_f32) { set_error("pcb_conv_forward: SIMT path needs w_f32 (Cin=%d Cout=%d)", Cin, Cout); return PCB_ERR_ARG; }
@@ -754,34 +322,19 @@ extern "C" int pcb_conv_forward(const float* X, int ldx, const int32_t* tbl, int
                                                                       w_f32, bias, Y, ldy);
     return check_launch("conv_simt_kernel");
   }
-  ConvArgs a;
-  a.X = X; a.ldx = ldx; a.tbl = tbl; a.tbl_stride = tbl_stride; a.kmap = km; a.K = K; a.n_out = n_out; a.Cin = Cin;
-  a.Cout = Cout; a.w_hi = (const __nv_bfloat16*)w_hi; a.w_lo = (const __nv_bfloat16*)w_lo; a.bias = bias; a.Y = Y; a.ldy = ldy;
-  a.partial = nullptr;
-  int nsplit = conv_splits(K, n_out, Cin, Cout);
-  if (nsplit > 1) {
-    PCB_ARG(ws && ws_bytes >= (size_t)nsplit * n_out * Cout * sizeof(float));
-    PCB_ARG(ldy % 4 == 0);
-  }
+  // tensor-core path: the tcgen05 kernel on fp32 inputs (split to bf16 hi/lo in the producers' registers), K-major weight planes
+  if (!(wk_hi && wk_lo && ldy % 4 == 0)) { set_error("pcb_conv_forward: the tensor-core path needs the K-major planes wk_hi / wk_lo"); return PCB_ERR_ARG; }
+  const int nsplit = conv_splits(K, n_out, Cin, Cout);
+  if (nsplit > 1) PCB_ARG(ws && ws_bytes >= (size_t)nsplit * n_out * Cout * sizeof(float));
   const int accumulate = (flags & PCB_CONV_ACCUMULATE) ? 1 : 0;
-  if ((flags & PCB_CONV_TCGEN05) && wk_hi && wk_lo && ldy % 4 == 0) {
-    if (int e = launch_conv_tcgen05(X, ldx, nullptr, nullptr, 0, nullptr, tbl, tbl_stride, km.v, K, n_out, Cin, Cout, wk_hi, wk_lo, bias, Y, ldy,
-                                    nsplit > 1 ? (float*)ws : nullptr, nsplit, pick_tile(Cout), accumulate, st)) return e;
-    if (nsplit > 1) {
-      int64_t n4 = n_out * (Cout / 4);
-      launch_kernel(conv_split_reduce_kernel, (unsigned)((n4 + 255) / 256), 256, 0, st, (const float*)ws, nsplit, n_out, Cout, bias, Y, ldy,
-                                                                             accumulate);
-      return check_launch("conv_split_reduce_kernel");
-    }
-    return PCB_OK;
+  if (int e = launch_conv_tcgen05(X, ldx, nullptr, nullptr, 0, nullptr, tbl, tbl_stride, km.v, K, n_out, Cin, Cout, wk_hi, wk_lo, bias, Y, ldy,
+                                  nsplit > 1 ? (float*)ws : nullptr, nsplit, pick_tile(Cout), accumulate, st)) return e;
+  if (nsplit > 1) {
+    int64_t n4 = n_out * (Cout / 4);
+    launch_kernel(conv_split_reduce_kernel, (unsigned)((n4 + 255) / 256), 256, 0, st, (const float*)ws, nsplit, n_out, Cout, bias, Y, ldy, accumulate);
+    return check_launch("conv_split_reduce_kernel");
   }
-  if (accumulate) { set_error("PCB_CONV_ACCUMULATE needs the tcgen05 path"); return PCB_ERR_ARG; }
-  switch (pick_tile(Cout)) {
-    case 128: return launch_conv<128>(a, nsplit, (float*)ws, st);
-    case 96: return launch_conv<96>(a, nsplit, (float*)ws, st);
-    case 64: return launch_conv<64>(a, nsplit, (float*)ws, st);
-    default: return launch_conv<32>(a, nsplit, (float*)ws, st);
-  }
+  return PCB_OK;
 }
 
 extern "C" int pcb_gather_sum(const float* X, int ldx, const int32_t* tbl, int64_t tbl_stride, const int32_t* kmap, int K, int64_t n_out, int C,
@@ -799,14 +352,11 @@ extern "C" int pcb_gather_sum(const float* X, int ldx, const int32_t* tbl, int64
 
 extern "C" size_t pcb_conv_wgrad_ws_bytes(int K, int64_t n_out, int Ca, int Cb) {
   if (Ca == 3 && Cb == 32) return (size_t)2 * num_sms() * K * Ca * Cb * sizeof(float) + 256;
-  int tm = pick_tile(Ca), tn = pick_tile(Cb);
-  if (!tm || !tn) { tm = 0; tn = 0; }
-  int s = wgrad_splits(K, n_out, Ca, Cb, tm, tn);
-  return (size_t)s * K * Ca * Cb * sizeof(float) + 256;
+  return (size_t)wgrad_splits(K, n_out, Ca, Cb, 0, 0) * K * Ca * Cb * sizeof(float) + 256;
 }
 
-#define WG_CASE(TM_, TN_) if (tm == TM_ && tn == TN_) rc = launch_wgrad<TM_, TN_>(a, splits, st)
-
+// Exact fp32 weight gradient (the 3-channel stem layer, widths the tensor-core tiling does not cover, PCB_CONV_FORCE_SIMT cross-checks).
+// Tensor-core shapes go through pcb_conv_wgrad_split on split (hi/lo) operands.
 extern "C" int pcb_conv_wgrad(const float* A, int lda, const float* B, int ldb, const int32_t* tbl, int64_t tbl_stride, int K,
                               int64_t n_out, int Ca, int Cb, float* dW, int transpose_out, void* ws, size_t ws_bytes,
                               int flags, void* stream) {
@@ -831,32 +381,17 @@ extern "C" int pcb_conv_wgrad(const float* A, int lda, const float* B, int ldb, 
     launch_kernel(wgrad_reduce_kernel, (unsigned)((nW + 255) / 256), 256, 0, st, (const float*)ws, nb, nW, dW, (flags & PCB_CONV_ACCUMULATE) ? 1 : 0);
     return check_launch("wgrad_reduce_kernel");
   }
-  int tm = pick_tile(Ca), tn = pick_tile(Cb);
-  const bool tc_ok = tm && tn && (lda % 4 == 0) && (ldb % 4 == 0) && !(flags & PCB_CONV_FORCE_SIMT);
-  if (!tc_ok) { tm = 0; tn = 0; }
-  const int splits = wgrad_splits(K, n_out, Ca, Cb, tm, tn);
+  const int splits = wgrad_splits(K, n_out, Ca, Cb, 0, 0);
   PCB_ARG(ws_bytes >= (size_t)splits * nW * sizeof(float));
   WgradArgs a;
   a.A = A; a.lda = lda; a.B = B; a.ldb = ldb; a.tbl = tbl; a.tbl_stride = tbl_stride; a.K = K; a.n_out = n_out;
   a.Ca = Ca; a.Cb = Cb; a.partial = (float*)ws; a.transpose_out = transpose_out;
-  int64_t rps = (n_out + splits - 1) / splits;
-  rps = (rps + WK - 1) / WK * WK;
-  a.rows_per_split = (int)rps;
-  int rc = PCB_OK;
-  if (!tc_ok) {
-    dim3 grid(K, splits);
-    wgrad_simt_kernel<<<grid, 256, 0, st>>>(a);
-    rc = check_launch("wgrad_simt_kernel");
-  } else {
-    rc = PCB_ERR_ARG;
-    WG_CASE(128, 128); WG_CASE(128, 96); WG_CASE(128, 64); WG_CASE(128, 32);
-    WG_CASE(96, 128);  WG_CASE(96, 96);  WG_CASE(96, 64);  WG_CASE(96, 32);
-    WG_CASE(64, 128);  WG_CASE(64, 96);  WG_CASE(64, 64);  WG_CASE(64, 32);
-    WG_CASE(32, 128);  WG_CASE(32, 96);  WG_CASE(32, 64);  WG_CASE(32, 32);
-  }
-  if (rc) return rc;
+  a.rows_per_split = (int)((n_out + splits - 1) / splits);
+  dim3 grid(K, splits);
+  wgrad_simt_kernel<<<grid, 256, 0, st>>>(a);
+  if (int e = check_launch("wgrad_simt_kernel")) return e;
   launch_kernel(wgrad_reduce_kernel, (unsigned)((nW + 255) / 256), 256, 0, st, (const float*)ws, splits, nW, dW,
-                                                                    (flags & PCB_CONV_ACCUMULATE) ? 1 : 0);
+                (flags & PCB_CONV_ACCUMULATE) ? 1 : 0);
   return check_launch("wgrad_reduce_kernel");
 }
 

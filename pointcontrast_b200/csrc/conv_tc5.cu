@@ -871,7 +871,7 @@ __global__ void __launch_bounds__(NTHR, 1) wgrad_tcgen05_kernel(const Args p) {
     // st.shared, ~900 cycles each under load) sits on the per-step critical path.  (ncu, round 2: with the table only ONE step ahead
     // the producers spent 60 % of their samples in long-scoreboard stalls on exactly these two hops and a step took ~1800 cycles.)
     constexpr int TF = 3;
-    int tq[TF][4];             // [steps loaded .. loaded + TF - 1][own offset pair (2) + (B loaders) the other pair (2)]
+    int tq[TF][4] = {};        // [steps loaded .. loaded + TF - 1][own offset pair (2) + (B loaders) the other pair (2)]
     int loaded = 0;
     auto fetch_into = [&](int (&d)[4], int step) {          // independent loads only: nothing here waits on a previous load
       const int64_t row = r_begin + (int64_t)step * WK + r;

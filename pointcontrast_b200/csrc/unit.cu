@@ -121,7 +121,7 @@ extern "C" int pcb_unit_forward(const pcb_unit* u, void* stream) {
                                         st, fuse ? &bn : nullptr, &have_stats)) return e;
   } else {
     PCB_ARG(u->x_p && u->W);
-    if (int e = pcb_conv_forward(u->x_p, u->x_ld, u->fwd_tbl, u->fwd_stride, u->fwd_kmap, u->K, u->n_out, u->Cin, u->Cout, nullptr, nullptr,
+    if (int e = pcb_conv_forward(u->x_p, u->x_ld, u->fwd_tbl, u->fwd_stride, u->fwd_kmap, u->K, u->n_out, u->Cin, u->Cout,
                                  nullptr, nullptr, u->W, nullptr, u->z_p, u->z_ld, nullptr, 0, 0, stream)) return e;
   }
   if (u->flags & PCB_UNIT_EVAL) {            // eval-mode BatchNorm (`downstream/semseg/lib/test.py:95-117`): normalise with the running statistics

@@ -277,7 +277,7 @@ class Runner:
             # data gradient it runs on the per-offset transposed weights
             assert not accumulate and x.p, "the fp32 SIMT conv writes (never accumulates) and reads the fp32 plane"
             w = kern.detach().transpose(1, 2).contiguous() if transposed_roles else kern.detach()
-            check(lib.pcb_conv_forward(x.p, x.ld, ptr(tbl), tbl.shape[1], kmap, K, n_out, Cin, Cout, None, None, None, None,
+            check(lib.pcb_conv_forward(x.p, x.ld, ptr(tbl), tbl.shape[1], kmap, K, n_out, Cin, Cout, None, None,
                                        ptr(w), ptr(bias), out.p, out.ld, None, 0, 0, st))
 
     def _wgrad(self, conv, plan, a_in, dz):
@@ -594,7 +594,7 @@ def _matches(m):
 
 def applicable_on(model, device):
     return (ENABLED and model.training and torch.is_grad_enabled() and torch.device(device).type == "cuda"
-            and me.CONV_IMPL == "tcgen05" and not me.FORCE_SIMT and matches(model))
+            and not me.FORCE_SIMT and matches(model))
 
 
 def applicable(model, sinput):
@@ -603,8 +603,7 @@ def applicable(model, sinput):
 
 def applicable_eval(model, sinput):
     """Inference (`model.eval()` under `torch.no_grad()`, `downstream/semseg/lib/test.py:95-117`): the same units, forward only."""
-    return (ENABLED and not model.training and not torch.is_grad_enabled() and sinput.F.is_cuda and me.CONV_IMPL == "tcgen05"
-            and not me.FORCE_SIMT and matches(model))
+    return (ENABLED and not model.training and not torch.is_grad_enabled() and sinput.F.is_cuda and not me.FORCE_SIMT and matches(model))
 
 
 def run_eval(model, sinput):

@@ -386,7 +386,7 @@ import os as _os
 
 FORCE_SIMT = False      # tests flip this to run the exact fp32 kernels
 SIMT_OPS = set()        # diagnostics (profiles/grad_precision_ab.py): subset of {"fwd", "dgrad", "wgrad"} forced onto the exact fp32 kernels (modular path)
-CONV_IMPL = _os.environ.get("PCB_CONV_IMPL", "tcgen05")     # "mma" (mma.sync) | "tcgen05" (TMEM accumulators)
+CONV_IMPL = "tcgen05"   # the only tensor-core implementation (the round-1 mma.sync kernels are gone); kept as a name for callers
 # bench.py sets this to a list: every convolution / weight-gradient entry-point call then appends its description here, in
 # issue order -- the same order in which the library (pcb_profile_enable) brackets those calls with CUDA events.
 PROFILE = None
@@ -453,15 +453,16 @@ def _use_tc(Cin, Cout, op="fwd"):
     return (not _simt(op)) and Cin % 32 == 0 and Cout % 32 == 0
 
 
-def _conv_forward_raw(x, tbl, kmap, K, n_out, Cin, Cout, planes_hi, planes_lo, w_f32, bias, kmajor_hi=None, kmajor_lo=None, op="fwd"):
+def _conv_forward_raw(x, tbl, kmap, K, n_out, Cin, Cout, w_f32, bias, kmajor_hi=None, kmajor_lo=None, op="fwd"):
+    """Y = conv(x) on a neighbour table.  kmajor_*: the bf16 hi/lo weight planes laid out [K][Cout][Cin] for THIS call's roles (tensor-
+    core path); w_f32: fp32 [K][Cin][Cout] (exact SIMT path)."""
     y = torch.empty(n_out, Cout, dtype=torch.float32, device=x.device)
     km = _c_int_array(kmap) if kmap is not None else None
-    flags = (1 if _simt(op) else 0) | (2 if CONV_IMPL == "tcgen05" else 0)
+    flags = 1 if _simt(op) else 0
     wsb = lib.pcb_conv_forward_ws_bytes(K, n_out, Cin, Cout)
     ws = workspace(wsb, x.device, slot=2)
-    check(lib.pcb_conv_forward(ptr(x), x.stride(0), ptr(tbl), tbl.shape[1], km, K, n_out, Cin, Cout, ptr(planes_hi),
-                               ptr(planes_lo), ptr(kmajor_hi), ptr(kmajor_lo), ptr(w_f32), ptr(bias), ptr(y), Cout, ptr(ws), wsb,
-                               flags, stream()))
+    check(lib.pcb_conv_forward(ptr(x), x.stride(0), ptr(tbl), tbl.shape[1], km, K, n_out, Cin, Cout, ptr(kmajor_hi), ptr(kmajor_lo),
+                               ptr(w_f32), ptr(bias), ptr(y), Cout, ptr(ws), wsb, flags, stream()))
     return y
 
 
@@ -474,14 +475,14 @@ class _SparseConvFunction(torch.autograd.Function):
             raise _lib.PcbError("features must be float32")
         K, Cin, Cout = kernel.shape
         with torch.cuda.device(x.device):
-            hi = lo = khi = klo = None
+            khi = klo = None
             if _use_tc(Cin, Cout):
                 pl = prepared.get(kernel)
-                hi, lo, khi, klo = pl[0], pl[1], pl[2], pl[3]
+                khi, klo = pl[2], pl[3]                    # [K][Cout][Cin]: K-major for the forward roles
             ev = _prof_begin()
-            y = _conv_forward_raw(x, plan.fwd_tbl, plan.fwd_kmap, K, plan.n_out, Cin, Cout, hi, lo,
+            y = _conv_forward_raw(x, plan.fwd_tbl, plan.fwd_kmap, K, plan.n_out, Cin, Cout,
                                   kernel.detach().contiguous(), bias.detach().reshape(-1) if bias is not None else None, khi, klo)
-            _prof_end(ev, "fwd", plan, K, Cin, Cout, hi is not None)
+            _prof_end(ev, "fwd", plan, K, Cin, Cout, khi is not None)
         ctx.save_for_backward(x, kernel)
         ctx.plan, ctx.prepared, ctx.has_bias = plan, prepared, bias is not None
         return y
@@ -495,28 +496,39 @@ class _SparseConvFunction(torch.autograd.Function):
         dx = dw = db = None
         with torch.cuda.device(dy.device):
             if ctx.needs_input_grad[0]:
-                hi = lo = khi = klo = wt = None
+                khi = klo = wt = None
                 if _use_tc(Cout, Cin, "dgrad"):
                     pl = ctx.prepared.get(kernel)
-                    hi, lo, khi, klo = pl[2], pl[3], pl[0], pl[1]
+                    khi, klo = pl[0], pl[1]                # [K][Cin][Cout]: K-major for the data-gradient roles (N = Cin, contraction = Cout)
                 else:
                     wt = kernel.detach().transpose(1, 2).contiguous()
                 ev = _prof_begin()
-                dx = _conv_forward_raw(dy, plan.dg_tbl, plan.dg_kmap, K, plan.n_in, Cout, Cin, hi, lo, wt, None, khi, klo, op="dgrad")
-                _prof_end(ev, "dgrad", plan, K, Cin, Cout, hi is not None)
+                dx = _conv_forward_raw(dy, plan.dg_tbl, plan.dg_kmap, K, plan.n_in, Cout, Cin, wt, None, khi, klo, op="dgrad")
+                _prof_end(ev, "dgrad", plan, K, Cin, Cout, khi is not None)
             if ctx.needs_input_grad[1]:
                 dw = torch.empty_like(kernel)
-                flags = 1 if _simt("wgrad") else 0
                 if plan.wg_gather_x:
                     A, B, Ca, Cb, tr, rows = x, dy, Cin, Cout, 0, plan.n_out
                 else:
                     A, B, Ca, Cb, tr, rows = dy, x, Cout, Cin, 1, plan.n_in
-                wsb = lib.pcb_conv_wgrad_ws_bytes(K, rows, Ca, Cb)
-                ws = workspace(wsb, dy.device)
+                tc = Ca % 32 == 0 and Cb % 32 == 0 and not _simt("wgrad")
                 ev = _prof_begin()
-                check(lib.pcb_conv_wgrad(ptr(A), A.stride(0), ptr(B), B.stride(0), ptr(plan.wg_tbl), plan.wg_tbl.shape[1], K,
-                                         rows, Ca, Cb, ptr(dw), tr, ptr(ws), wsb, flags, stream()))
-                _prof_end(ev, "wgrad", plan, K, Cin, Cout, Ca % 32 == 0 and Cb % 32 == 0 and not _simt("wgrad"))
+                if tc:      # tensor-core weight gradient on split (bf16 hi/lo) operands
+                    def planes(t):
+                        pl = torch.empty(2, t.shape[0] * t.shape[1], dtype=torch.bfloat16, device=t.device)
+                        check(lib.pcb_split_rows(ptr(t), t.shape[1], t.shape[0], t.shape[1], pl[0].data_ptr(), pl[1].data_ptr(), t.shape[1], 0, stream()))
+                        return pl
+                    Ap, Bp = planes(A), planes(B)
+                    wsb = lib.pcb_conv_wgrad_split_ws_bytes(K, rows, Ca, Cb)
+                    ws = workspace(wsb, dy.device)
+                    check(lib.pcb_conv_wgrad_split(Ap[0].data_ptr(), Ap[1].data_ptr(), Ca, Bp[0].data_ptr(), Bp[1].data_ptr(), Cb, ptr(plan.wg_tbl),
+                                                   plan.wg_tbl.shape[1], K, rows, Ca, Cb, ptr(dw), tr, ptr(ws), wsb, 0, stream()))
+                else:       # exact fp32 (stem layer, odd widths, FORCE_SIMT)
+                    wsb = lib.pcb_conv_wgrad_ws_bytes(K, rows, Ca, Cb)
+                    ws = workspace(wsb, dy.device)
+                    check(lib.pcb_conv_wgrad(ptr(A), A.stride(0), ptr(B), B.stride(0), ptr(plan.wg_tbl), plan.wg_tbl.shape[1], K,
+                                             rows, Ca, Cb, ptr(dw), tr, ptr(ws), wsb, 1 if _simt("wgrad") else 0, stream()))
+                _prof_end(ev, "wgrad", plan, K, Cin, Cout, tc)
             if ctx.has_bias and ctx.needs_input_grad[2]:
                 db = dy.sum(0, keepdim=True)
         return dx, dw, db, None, None

@@ -1,4 +1,4 @@
-"""Per-operator parity on the GPU against the fp64 oracle (tolerance: 1e-3 relative, the north-star bar; the bf16x3
+"""Per-operator parity on the GPU against the fp64 oracle (tolerance: 1e-3 relative, the north-star bar; the split-operand
 tensor-core path is expected near 1e-5, the exact SIMT path near 1e-6)."""
 import numpy as np
 import pytest
@@ -80,48 +80,6 @@ def test_conv_forward_backward(kind, cin, cout, bias, simt):
     assert max_rel_err(conv.kernel.grad, oconv.kernel.grad) < TOL and rel_err(conv.kernel.grad, oconv.kernel.grad) < TOL / 10
     if bias:
         assert rel_err(conv.bias.grad, oconv.bias.grad) < TOL / 10
-
-
-@pytest.mark.parametrize("kind,cin,cout,bias", [c for c in CASES if c[1] % 32 == 0])
-def test_tcgen05_conv_forward_backward(kind, cin, cout, bias):
-    """The Blackwell-native (tcgen05 / TMEM) kernel: same parity bar, and near-exact agreement with the mma.sync kernel."""
-    from pointcontrast_b200 import me
-    rng = np.random.default_rng(cin * 7 + cout)
-    n = 3000 if cin * cout <= 128 * 128 else 1200
-    coords = surface_coords(rng, n)
-    g = torch.Generator().manual_seed(cin + cout + 1)
-    conv, oconv = _pair(kind, cin, cout, bias)
-    oconv = oconv.double()
-    with torch.no_grad():
-        oconv.kernel.copy_(conv.kernel.double())
-        if bias:
-            oconv.bias.copy_(conv.bias.double())
-    conv = conv.cuda()
-    st0 = me.SparseTensor(torch.zeros(len(coords), 1, device="cuda"), coords=torch.from_numpy(coords))
-    ost0 = OR.SparseTensor(torch.zeros(len(coords), 1, dtype=torch.float64), coords=torch.from_numpy(coords))
-    if kind == "up":
-        key = st0.coords_man.stride(st0.coords_key, [2, 2, 2]); okey = ost0.coords_man.stride(ost0.coords_key, [2, 2, 2])
-    else:
-        key, okey = st0.coords_key, ost0.coords_key
-    x = torch.randn(st0.coords_man.num_rows(key), cin, generator=g, dtype=torch.float64)
-    xo = x.clone().requires_grad_(True)
-    yo = oconv(OR.SparseTensor(xo, coords_key=okey, coords_manager=ost0.coords_man))
-    dy = torch.randn(yo.F.shape, generator=g, dtype=torch.float64)
-    yo.F.backward(dy)
-    res = {}
-    default_impl = me.CONV_IMPL
-    for impl in ("mma", "tcgen05"):
-        me.CONV_IMPL = impl
-        try:
-            xg = x.float().cuda().requires_grad_(True)
-            y = conv(me.SparseTensor(xg, coords_key=key, coords_manager=st0.coords_man))
-            y.F.backward(dy.float().cuda())
-            res[impl] = (y.F.detach().clone(), xg.grad.clone())
-        finally:
-            me.CONV_IMPL = default_impl
-    y5, dx5 = res["tcgen05"]
-    assert max_rel_err(y5, yo.F) < TOL and max_rel_err(dx5, xo.grad) < TOL
-    assert max_rel_err(y5, res["mma"][0]) < 2e-5 and max_rel_err(dx5, res["mma"][1]) < 2e-5
 
 
 def test_tensor_core_and_simt_paths_agree_tightly():
@@ -255,12 +213,12 @@ def _split(x, flags=0):
 
 @pytest.mark.parametrize("Ca,Cb,tr", [(96, 96, 0), (128, 96, 0), (32, 32, 0), (64, 64, 1), (256, 256, 0), (384, 256, 0),
                                        (192, 128, 1), (96, 32, 0), (256, 128, 1), (32, 96, 0)])
-def test_split_operand_wgrad_tcgen05_matches_fp32_input_kernels(Ca, Cb, tr):
-    """tcgen05 weight-gradient on bf16 hi/lo planes (MN-major UMMA operands) vs the mma.sync kernel on fp32 inputs."""
+def test_split_operand_wgrad_tcgen05_matches_exact_fp32_kernel(Ca, Cb, tr):
+    """tcgen05 weight-gradient on bf16 hi/lo planes (MN-major UMMA operands) vs the exact fp32 SIMT kernel of the library."""
     from pointcontrast_b200 import me
     from pointcontrast_b200._lib import check, lib, ptr, stream
     rng = np.random.default_rng(Ca + Cb)
-    coords = surface_coords(rng, 5000 if Ca * Cb <= 128 * 128 else 1500)
+    coords = surface_coords(rng, 3000 if Ca * Cb <= 128 * 128 else 900)
     st = me.SparseTensor(torch.zeros(len(coords), 1, device="cuda"), coords=torch.from_numpy(coords))
     kg = me.KernelGenerator(3, 1, 1, region_type=me.RegionType.HYBRID, axis_types=[me.RegionType.HYPERCUBE] * 3, dimension=3)
     plan = st.coords_man.conv_plan(st.coords_key, st.coords_key, kg, False)
@@ -270,13 +228,13 @@ def test_split_operand_wgrad_tcgen05_matches_fp32_input_kernels(Ca, Cb, tr):
     shape = (K, Cb, Ca) if tr else (K, Ca, Cb)
     ref = torch.empty(shape, device="cuda"); got = torch.full(shape, 0.5, device="cuda")
     wsb = lib.pcb_conv_wgrad_ws_bytes(K, n, Ca, Cb); ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
-    check(lib.pcb_conv_wgrad(ptr(A), Ca, ptr(B), Cb, ptr(plan.wg_tbl), plan.wg_tbl.shape[1], K, n, Ca, Cb, ptr(ref), tr, ptr(ws), wsb, 0, stream()))
+    check(lib.pcb_conv_wgrad(ptr(A), Ca, ptr(B), Cb, ptr(plan.wg_tbl), plan.wg_tbl.shape[1], K, n, Ca, Cb, ptr(ref), tr, ptr(ws), wsb, 1, stream()))
     As, Bs = _split(A), _split(B)
     wsb = lib.pcb_conv_wgrad_split_ws_bytes(K, n, Ca, Cb); ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
     check(lib.pcb_conv_wgrad_split(As[0].data_ptr(), As[1].data_ptr(), Ca, Bs[0].data_ptr(), Bs[1].data_ptr(), Cb, ptr(plan.wg_tbl),
                                    plan.wg_tbl.shape[1], K, n, Ca, Cb, ptr(got), tr, ptr(ws), wsb, 4, stream()))      # accumulate onto 0.5
     torch.cuda.synchronize()
-    assert max_rel_err(got - 0.5, ref) < 5e-5          # two kernels, different partial-sum partitions: fp32 rounding only
+    assert max_rel_err(got - 0.5, ref) < 1e-4          # bf16 hi/lo products (2^-17) vs exact fp32
     # and against fp64
     tbl = plan.wg_tbl.long()
     k = 5
@@ -299,7 +257,7 @@ def test_split_operand_conv_forward_matches_fp32_input_kernel(cin, cout):
     X = torch.randn(n, cin, device="cuda"); W = torch.randn(27, cin, cout, device="cuda") * 0.05
     planes = torch.empty(4, 27 * cin * cout, dtype=torch.int16, device="cuda")
     check(lib.pcb_weight_prep(ptr(W), 27, cin, cout, ptr(planes[0]), ptr(planes[1]), ptr(planes[2]), ptr(planes[3]), stream()))
-    ref = me._conv_forward_raw(X, plan.fwd_tbl, None, 27, n, cin, cout, planes[0], planes[1], W, None, planes[2], planes[3])
+    ref = me._conv_forward_raw(X, plan.fwd_tbl, None, 27, n, cin, cout, W, None, planes[2], planes[3])
     Xs = _split(X)
     got = torch.full((n, cout), 0.25, device="cuda")
     wsb = lib.pcb_conv_forward_ws_bytes(27, n, cin, cout); ws = torch.empty(max(wsb, 256), dtype=torch.uint8, device="cuda")
@@ -313,7 +271,7 @@ def test_split_operand_conv_forward_matches_fp32_input_kernel(cin, cout):
     # data-gradient roles: dX = sum_k dY[tbl[opp k]] W[k]^T through the dgrad tiles vs the fp32-input kernel
     dY = torch.randn(n, cout, device="cuda")
     opp = plan.dg_kmap
-    ref_dx = me._conv_forward_raw(dY, plan.dg_tbl, opp, 27, n, cout, cin, planes[2], planes[3], None, None, planes[0], planes[1])
+    ref_dx = me._conv_forward_raw(dY, plan.dg_tbl, opp, 27, n, cout, cin, None, None, planes[0], planes[1])
     dYs = _split(dY)
     got_dx = torch.empty(n, cin, device="cuda")
     wsb = lib.pcb_conv_forward_ws_bytes(27, n, cout, cin); ws = torch.empty(max(wsb, 256), dtype=torch.uint8, device="cuda")

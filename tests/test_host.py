@@ -36,7 +36,11 @@ def test_library_has_sm100a_code_and_tensor_core_instructions():
     out = subprocess.run(["cuobjdump", "-lelf", so], capture_output=True, text=True).stdout
     assert "sm_100a" in out
     sass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
-    assert "HMMA.16816.F32.BF16" in sass and "LDSM" in sass and "LDGSTS" in sass
+    # Blackwell-native evidence (B200_PROFILING.md): tcgen05.mma -> UTCHMMA, tcgen05.ld -> LDTM, TMA bulk copy -> UBLKCP, commit -> UTCBAR,
+    # programmatic dependent launch -> ACQBULK; and NO legacy mma.sync (" HMMA.") tensor-core path left in the library
+    for mnemonic in ("UTCHMMA", "LDTM", "UBLKCP", "UTCBAR", "ACQBULK"):
+        assert mnemonic in sass, mnemonic
+    assert " HMMA." not in sass and "HGMMA" not in sass
 
 
 def test_argument_errors_do_not_need_a_gpu():
