@@ -277,17 +277,26 @@ def run_ours(args):
         return float(t.item())
 
     # ---- device-resident timing: one event per step boundary (no host sync inside the timed region)
+    # (the nvidia-smi sampler is started BEFORE the warm-up: its start-up -- process spawn, NVML / driver initialisation -- stalls kernel
+    #  launches for tens of ms once, which used to land inside the timed region as a single 60-90 ms step)
+    clocks = Clocks(local) if rank == 0 else None
     for i in range(args.warmup):
         trainer.train_step(dev_batches[i % len(dev_batches)])
     sync_all()
-    clocks = Clocks(local) if rank == 0 else None
+    if clocks is not None:
+        time.sleep(0.3)
+    import gc
+    gc.collect()
     l0 = _lib.launch_count()
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     t_wall0 = time.time()
     evs[0].record()
+    host_enq = []
     for i in range(args.steps):
+        t_h = time.perf_counter()
         loss = trainer.train_step(dev_batches[i % len(dev_batches)])
         evs[i + 1].record()
+        host_enq.append((time.perf_counter() - t_h) * 1e3)
     sync_all()
     t_wall1 = time.time()
     launches = _lib.launch_count() - l0
@@ -389,6 +398,8 @@ def run_ours(args):
                             "final_loss": float(loss[0] if isinstance(loss, tuple) else loss),
                             "per_step_ms": {"median": float(np.median(per_step)), "min": float(np.min(per_step)), "max": float(np.max(per_step)),
                                             "p90": float(np.percentile(per_step, 90))},
+                            "per_step_ms_list": [round(t, 2) for t in per_step],
+                            "host_enqueue_ms_per_step": {"median": float(np.median(host_enq)), "max": float(np.max(host_enq))},
                             "host_ms_per_step": host_ms_per_step, "launches_per_step": launches / args.steps, "ranks": ranks},
                 "clocks": clk, "gpu_launches": int(launches),
                 "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},

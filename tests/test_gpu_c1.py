@@ -106,7 +106,7 @@ def test_direct_epilogue_conv_at_c1_rows(cin, cout):
                                      ptr(bias.cuda()), ptr(y16), cout, ptr(ws), 256, 8 | 16, stream()))
     e_bf16, e_fp16 = rel_err(y, yo), rel_err(y16, yo)
     # measured: 4.8e-6 (bf16 hi/lo) vs 2.1e-6 (fp16 hi/lo: what is left is the fp32 accumulation over 27 x Cin terms)
-    assert e_fp16 < 0.6 * e_bf16 and max_rel_err(y16, yo) < 2e-5, (e_bf16, e_fp16)
+    assert e_fp16 < 0.6 * e_bf16 and max_rel_err(y16, yo) < 1e-4, (e_bf16, e_fp16)
     # (tcgen05.mma rejects mixed fp16 x bf16 operands -- profiles/probes/mixed_fmt_probe.cu -- so the weight gradient keeps reading
     #  the bf16 planes of the activations, checked above)
 
