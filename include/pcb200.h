@@ -152,6 +152,15 @@ int pcb_conv_wgrad(const float* A, int lda, const float* B, int ldb, const int32
  * the FORWARD tiles hold fp16 hi/lo of W * 2^10 (|W| < 60; the kernel rescales its output), the data-gradient tiles stay bf16. */
 size_t pcb_weight_tile_bytes(int K, int Cin, int Cout, int dgrad_roles);
 int pcb_weight_tile(const float* W, int K, int Cin, int Cout, void* fwd_tiles, void* dgrad_tiles, int flags, void* stream);
+/* The same for every convolution of a network in ONE launch: fill a HOST array of descriptors with pcb_tile_desc_fill (start = running
+ * sum of K*Cin*Cout), copy it to the device, call pcb_weight_tile_batch(device array, n <= 256, total elements) after every optimiser step. */
+typedef struct pcb_tile_desc {
+  const float* W; void* fwd; void* dgrad;
+  int32_t K, Cin, Cout, flags, bn_f, bn_d;
+  int64_t start;
+} pcb_tile_desc;
+int pcb_tile_desc_fill(pcb_tile_desc* d, const float* W, int K, int Cin, int Cout, void* fwd_tiles, void* dgrad_tiles, int flags, int64_t start);
+int pcb_weight_tile_batch(const pcb_tile_desc* descs_dev, int n, int64_t total, void* stream);
 int pcb_conv_forward_split(const uint16_t* Xhi, const uint16_t* Xlo, int lds, const int32_t* tbl, int64_t tbl_stride,
                            const int32_t* kmap, int K, int64_t n_out, int Cin, int Cout, const void* w_tiles,
                            const float* bias, float* Y, int ldy, void* ws, size_t ws_bytes, int flags, void* stream);

@@ -48,6 +48,8 @@ _SIGS = {
     "pcb_conv_wgrad": (_i, [_p, _i, _p, _i, _p, _l, _i, _l, _i, _i, _p, _i, _p, _sz, _i, _p]),
     "pcb_weight_tile_bytes": (_sz, [_i, _i, _i, _i]),
     "pcb_weight_tile": (_i, [_p, _i, _i, _i, _p, _p, _i, _p]),
+    "pcb_tile_desc_fill": (_i, [_p, _p, _i, _i, _i, _p, _p, _i, _l]),
+    "pcb_weight_tile_batch": (_i, [_p, _i, _l, _p]),
     "pcb_conv_forward_split": (_i, [_p, _p, _i, _p, _l, _p, _i, _l, _i, _i, _p, _p, _p, _i, _p, _sz, _i, _p]),
     "pcb_conv_wgrad_split_ws_bytes": (_sz, [_i, _l, _i, _i]),
     "pcb_conv_wgrad_split": (_i, [_p, _p, _i, _p, _p, _i, _p, _l, _i, _l, _i, _i, _p, _i, _p, _sz, _i, _p]),
@@ -74,6 +76,12 @@ _SIGS = {
     "pcb_unit_forward": (_i, [_p, _p]),
     "pcb_unit_backward": (_i, [_p, _p]),
 }
+
+
+class PcbTileDesc(C.Structure):
+    """`struct pcb_tile_desc` of include/pcb200.h."""
+    _fields_ = [("W", _p), ("fwd", _p), ("dgrad", _p), ("K", C.c_int32), ("Cin", C.c_int32), ("Cout", C.c_int32), ("flags", C.c_int32),
+                ("bn_f", C.c_int32), ("bn_d", C.c_int32), ("start", _l)]
 
 
 class PcbUnit(C.Structure):

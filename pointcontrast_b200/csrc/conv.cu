@@ -442,6 +442,73 @@ __global__ void weight_tile_kernel(const float* __restrict__ W, int K, int Cin, 
 }
 }  // namespace
 
+// All convolutions of a network in ONE launch (the fused executor re-tiles every kernel after each SGD step: 62 small launches
+// otherwise).  descs: DEVICE array; `start` = prefix sum of K*Cin*Cout; a thread finds its convolution by binary search.
+namespace {
+__global__ void weight_tile_batch_kernel(const pcb_tile_desc* __restrict__ descs, int n, int64_t total) {
+  pdl_wait(); pdl_trigger();
+  __shared__ int64_t s_start[257];
+  for (int i = threadIdx.x; i <= n; i += blockDim.x) s_start[i] = i < n ? descs[i].start : total;
+  __syncthreads();
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  int lo = 0, hi = n - 1;
+  while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (s_start[mid] <= e) lo = mid; else hi = mid - 1; }
+  const pcb_tile_desc d = descs[lo];
+  const int64_t le = e - d.start;
+  const int K = d.K, Cin = d.Cin, Cout = d.Cout;
+  (void)K;
+  const float w = d.W[le];
+  const __nv_bfloat16 h = __float2bfloat16_rn(w);
+  const __nv_bfloat16 l = __float2bfloat16_rn(w - __bfloat162float(h));
+  const int co = (int)(le % Cout);
+  const int64_t r = le / Cout;
+  const int ci = (int)(r % Cin);
+  const int k = (int)(r / Cin);
+  const int bn_f = d.bn_f, bn_d = d.bn_d;
+  unsigned char* fwd = (unsigned char*)d.fwd;
+  unsigned char* dg = (unsigned char*)d.dgrad;
+  {
+    const int64_t plane = tile_plane_bytes(bn_f);
+    const int64_t blob = ((int64_t)(k * (Cin / 32) + ci / 32) * (Cout / bn_f) + co / bn_f) * 2 * plane;
+    const int nn = co % bn_f, c = ci % 32;
+    const int64_t off = blob + (c / 8) * (plane / 4) + (nn / 8) * 128 + (nn % 8) * 16 + (c % 8) * 2;
+    if (d.flags & PCB_PLANES_B_FP16) {
+      const float ws = fminf(fmaxf(w * 1024.0f, -65000.f), 65000.f);
+      const __half fh = __float2half_rn(ws);
+      const __half fl = __float2half_rn(ws - __half2float(fh));
+      *reinterpret_cast<__half*>(fwd + off) = fh;
+      *reinterpret_cast<__half*>(fwd + off + plane) = fl;
+    } else {
+      *reinterpret_cast<__nv_bfloat16*>(fwd + off) = h;
+      *reinterpret_cast<__nv_bfloat16*>(fwd + off + plane) = l;
+    }
+  }
+  {
+    const int64_t plane = tile_plane_bytes(bn_d);
+    const int64_t blob = ((int64_t)(k * (Cout / 32) + co / 32) * (Cin / bn_d) + ci / bn_d) * 2 * plane;
+    const int nn = ci % bn_d, c = co % 32;
+    const int64_t off = blob + (c / 8) * (plane / 4) + (nn / 8) * 128 + (nn % 8) * 16 + (c % 8) * 2;
+    *reinterpret_cast<__nv_bfloat16*>(dg + off) = h;
+    *reinterpret_cast<__nv_bfloat16*>(dg + off + plane) = l;
+  }
+}
+}  // namespace
+
+extern "C" int pcb_tile_desc_fill(pcb_tile_desc* d, const float* W, int K, int Cin, int Cout, void* fwd_tiles, void* dgrad_tiles, int flags,
+                                  int64_t start) {
+  PCB_ARG(d && W && fwd_tiles && dgrad_tiles && K >= 1 && Cin % 32 == 0 && Cout % 32 == 0 && Cin >= 32 && Cout >= 32);
+  d->W = W; d->fwd = fwd_tiles; d->dgrad = dgrad_tiles; d->K = K; d->Cin = Cin; d->Cout = Cout; d->flags = flags;
+  d->bn_f = pick_tile(Cout); d->bn_d = pick_tile(Cin); d->start = start;
+  return PCB_OK;
+}
+
+extern "C" int pcb_weight_tile_batch(const pcb_tile_desc* descs_dev, int n, int64_t total, void* stream) {
+  PCB_ARG(descs_dev && n >= 1 && n <= 256 && total >= 1);
+  launch_kernel(weight_tile_batch_kernel, (unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream, descs_dev, n, total);
+  return check_launch("weight_tile_batch_kernel");
+}
+
 extern "C" size_t pcb_weight_tile_bytes(int K, int Cin, int Cout, int dgrad_roles) {
   if (Cin % 32 || Cout % 32) return 0;
   const int N = dgrad_roles ? Cin : Cout, Kc = dgrad_roles ? Cout : Cin;

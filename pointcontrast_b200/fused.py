@@ -360,6 +360,39 @@ class Runner:
             self.units.append((u, conv, bn, a_in, out, plan, residual))
         return out
 
+    def _refresh_tiles(self):
+        """Re-tile the weights of every tensor-core convolution in ONE launch when the parameters changed (after each optimiser
+        step) and hand the results to the per-layer caches (`me._PreparedWeights`), instead of one small launch per layer."""
+        m = self.model
+        convs = [c for c in m.modules() if isinstance(c, me._ConvolutionBase) and c.in_channels % 32 == 0 and c.out_channels % 32 == 0]
+        tags = [(c.kernel.data_ptr(), c.kernel._version, tuple(c.kernel.shape), me._WEIGHTS_EPOCH[0], me.FWD_FP16) for c in convs]
+        if all(c._prepared.tile_tag == t for c, t in zip(convs, tags)):
+            return
+        cache = self.__dict__.get("_tile_batch")
+        key = tuple((c.kernel.data_ptr(), tuple(c.kernel.shape)) for c in convs) + (me.FWD_FP16,)
+        if cache is None or cache[0] != key:
+            dev = convs[0].kernel.device
+            sizes_f = [lib.pcb_weight_tile_bytes(*c.kernel.shape, 0) for c in convs]
+            sizes_d = [lib.pcb_weight_tile_bytes(*c.kernel.shape, 1) for c in convs]
+            al = lambda v: (v + 255) & ~255
+            buf = torch.zeros(sum(al(v) for v in sizes_f + sizes_d), dtype=torch.uint8, device=dev)
+            descs = (_lib.PcbTileDesc * len(convs))()
+            views, off, start = [], 0, 0
+            for i, c in enumerate(convs):
+                f = buf[off:off + sizes_f[i]]; off += al(sizes_f[i])
+                d = buf[off:off + sizes_d[i]]; off += al(sizes_d[i])
+                K, Cin, Cout = c.kernel.shape
+                check(lib.pcb_tile_desc_fill(ctypes.byref(descs[i]), c.kernel.data_ptr(), K, Cin, Cout, f.data_ptr(), d.data_ptr(),
+                                             me.PLANES_B_FP16 if me.FWD_FP16 else 0, start))
+                start += K * Cin * Cout
+                views.append((f, d))
+            host = torch.frombuffer(bytearray(bytes(descs)), dtype=torch.uint8)
+            cache = self._tile_batch = (key, host.to(dev), views, start, buf)
+        _, ddev, views, total, _ = cache
+        check(lib.pcb_weight_tile_batch(ddev.data_ptr(), len(convs), total, stream()))
+        for c, t, v in zip(convs, tags, views):
+            c._prepared._tiles, c._prepared.tile_tag = v, t
+
     def _stat(self, C):
         p = self.stats.data_ptr() + 4 * self.stat_off
         self.stat_off += C
@@ -431,6 +464,7 @@ class Runner:
                                      dtype=torch.float32, device=dev)
             self.stat_off = 0
             self.ws = me.workspace(self._ws_bytes(g), dev, slot=5)
+            self._refresh_tiles()
             self.arena = arena = Arena(dev, self._fwd_hint)
             P = m.PLANES
             x_in = feats.detach().contiguous().float()
