@@ -29,6 +29,7 @@ class FlatSGD(torch.optim.Optimizer):
         self.flat_param = torch.zeros(total, dtype=torch.float32, device=dev)
         self.flat_grad = torch.zeros_like(self.flat_param)
         self.flat_buf = torch.zeros_like(self.flat_param)
+        self._gviews = []
         with torch.no_grad():
             for p, off in zip(ps, self._offsets):
                 view = self.flat_param[off:off + p.numel()].view(p.shape)
@@ -38,6 +39,7 @@ class FlatSGD(torch.optim.Optimizer):
                 if p.grad is not None:
                     g.copy_(p.grad)
                 p.grad = g
+                self._gviews.append(g)
         self._first = True
         self.grad_scale = 1.0                            # e.g. 1/world_size after a sum all-reduce
         bump_weights_epoch()
@@ -45,18 +47,25 @@ class FlatSGD(torch.optim.Optimizer):
     def _views(self, flat):
         return [flat[off:off + p.numel()].view(p.shape) for p, off in zip(self.param_groups[0]["params"], self._offsets)]
 
+    def _grad_views(self):
+        """The per-parameter views into flat_grad, created once (187 tensor views per call would cost ~1 ms of host time per step)."""
+        v = self.__dict__.get("_gviews")
+        if v is None:
+            v = self._gviews = self._views(self.flat_grad)
+        return v
+
     def zero_grad(self, set_to_none=False):
         self.flat_grad.zero_()
-        for p, g in zip(self.param_groups[0]["params"], self._views(self.flat_grad)):
-            if p.grad is None or p.grad.data_ptr() != g.data_ptr():
+        for p, g in zip(self.param_groups[0]["params"], self._grad_views()):
+            if p.grad is not g and (p.grad is None or p.grad.data_ptr() != g.data_ptr()):
                 p.grad = g
 
     @torch.no_grad()
     def step(self, closure=None):
         grp = self.param_groups[0]
         ps = grp["params"]
-        for p, g in zip(ps, self._views(self.flat_grad)):     # a grad replaced behind our back is folded in
-            if p.grad is not None and p.grad.data_ptr() != g.data_ptr():
+        for p, g in zip(ps, self._grad_views()):              # a grad replaced behind our back is folded in
+            if p.grad is not g and p.grad is not None and p.grad.data_ptr() != g.data_ptr():
                 g.copy_(p.grad)
                 p.grad = g
         with torch.cuda.device(self.flat_param.device):
