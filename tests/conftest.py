@@ -12,6 +12,9 @@ REFERENCE = "/root/reference"
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on the B200 box)")
+    import torch
+    # the CPU oracle is many small torch ops: on a 100+-core host the default thread count is several times SLOWER than 16 threads
+    torch.set_num_threads(min(torch.get_num_threads(), 16))
 
 
 def pytest_collection_modifyitems(config, items):

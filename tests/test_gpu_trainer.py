@@ -59,68 +59,46 @@ def test_loss_curve_matches_cpu_oracle():
 
 def test_loss_curve_100_steps_against_fp64_and_fp32_oracles():
     """100 SGD steps (the reference's optimiser settings: lr 0.1, momentum 0.8, wd 1e-4, ExponentialLR 0.99 applied every step here,
-    PointInfoNCE T = 0.4) on two small scene pairs.  Three runs see identical batches and positive draws: the GPU path, the CPU oracle
-    in fp32 and the CPU oracle in fp64.  Training from scratch at this learning rate amplifies any rounding difference step by step
-    (the 6-step test above already shows 1e-7 -> 1e-3), so the yardstick for "matches the reference" is the fp32 CPU oracle's own
-    distance from fp64: the GPU curve must stay within 3x of it (and both curves must actually train).  Stated tolerance, per step:
-    |gpu - fp64| / fp64 <= 3 * max over steps so far of |fp32 - fp64| / fp64 + 1e-3."""
-    from pointcontrast_b200 import losses, optim, synth
+    PointInfoNCE T = 0.4) on two small scene-pair batches.  The GPU path replays exactly the steps of the committed golden curves
+    (tests/golden/loss_curve_100.npz, made by tests/golden/make_loss_curve.py on the CPU oracle in fp64 and in fp32: same batches,
+    same deterministic weights, same positive draws).  Training from scratch at this learning rate amplifies any rounding difference
+    step by step (the 6-step test above already shows 1e-7 -> 1e-3), so the yardstick for "matches the reference" is the fp32 CPU
+    oracle's own distance from fp64.  Stated tolerance, per step:
+        |gpu - fp64| / fp64  <=  3 * (max over the steps so far of |fp32 - fp64| / fp64) + 1e-3
+    and the mean loss of the last 10 steps within 3x the fp32 oracle's deviation + 5e-3."""
+    from pointcontrast_b200 import losses, optim
     from pointcontrast_b200.model import load_model
-    steps = 100
-    batches = [synth.collate_pairs([synth.synth_pair(60 + 2 * s, scale=0.12), synth.synth_pair(61 + 2 * s, scale=0.12)]) for s in range(2)]
-    cfg = refload.default_config()
-    net = load_model("Res16UNet34C")(3, 32, cfg, D=3)
-    det_init(net, 11)
-    state = {k: v.clone() for k, v in net.state_dict().items()}
-    rng = np.random.default_rng(5)
-    draws = []
-    for step in range(steps):
-        pairs = batches[step % 2]["correspondences"]
-        nq = len(np.unique(pairs[:, 0]))
-        draws.append(loss_cpu.select_positives(pairs, rng.random(nq).astype(np.float32), 4096, rng.choice(nq, 4096, replace=False) if nq > 4096 else None))
-
-    def run_oracle(dtype):
-        with model_backend(OR) as mod:
-            onet = mod.Res16UNet34C(3, 32, cfg, D=3).to(dtype)
-            onet.load_state_dict({k: (v.to(dtype) if v.dtype.is_floating_point else v) for k, v in state.items()})
-            onet.train()
-            oopt = torch.optim.SGD(onet.parameters(), lr=0.1, momentum=0.8, weight_decay=1e-4)
-            sch = torch.optim.lr_scheduler.ExponentialLR(oopt, 0.99)
-            curve = []
-            for step in range(steps):
-                b = batches[step % 2]
-                q, k = draws[step]
-                oopt.zero_grad()
-                Fo = [onet(OR.SparseTensor(torch.from_numpy(b[f"sinput{v}_F"]).to(dtype), coords=torch.from_numpy(b[f"sinput{v}_C"]))).F for v in "01"]
-                lo = loss_cpu.point_nce_loss(Fo[0], Fo[1], q, k, 0.4)
-                lo.backward(); oopt.step(); sch.step()
-                curve.append(float(lo.detach()))
-        return curve
-
+    from tests.golden import make_loss_curve as G
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "loss_curve_100.npz"))
+    assert int(gold["steps"]) == G.STEPS and tuple(gold["seeds"]) == G.SEEDS and float(gold["scale"]) == G.SCALE
+    c64, c32 = gold["oracle_fp64"], gold["oracle_fp32"]
+    batches, draws = G.setup()
+    net = load_model("Res16UNet34C")(3, 32, refload.default_config(), D=3)
+    det_init(net, G.INIT_SEED)
     net = net.cuda().train()
     opt = optim.FlatSGD(net.parameters(), lr=0.1, momentum=0.8, weight_decay=1e-4)
     sch = torch.optim.lr_scheduler.ExponentialLR(opt, 0.99)
+    dev = [{k: torch.from_numpy(b[k]).cuda() for k in ("sinput0_F", "sinput0_C", "sinput1_F", "sinput1_C")} for b in batches]
     gpu = []
-    for step in range(steps):
-        b = batches[step % 2]
+    for step in range(G.STEPS):
+        b = dev[step % 2]
         q, k = draws[step]
         opt.zero_grad()
-        F0, F1 = net.forward_pair(torch.from_numpy(b["sinput0_F"]), torch.from_numpy(b["sinput0_C"]), torch.from_numpy(b["sinput1_F"]),
-                                  torch.from_numpy(b["sinput1_C"]), torch.device("cuda"))
+        F0, F1 = net.forward_pair(b["sinput0_F"], b["sinput0_C"], b["sinput1_F"], b["sinput1_C"], torch.device("cuda"))
         loss = losses.point_nce_loss(F0, F1, q.cuda(), k.cuda(), 0.4)
         loss.backward(); opt.step(); sch.step()
-        gpu.append(float(loss.detach()))
-    c64, c32 = run_oracle(torch.float64), run_oracle(torch.float32)
-    d_gpu = np.abs(np.array(gpu) - np.array(c64)) / np.array(c64)
-    d_f32 = np.abs(np.array(c32) - np.array(c64)) / np.array(c64)
+        gpu.append(loss.detach())
+    gpu = torch.stack(gpu).cpu().numpy().astype(np.float64)
+    d_gpu = np.abs(gpu - c64) / c64
+    d_f32 = np.abs(c32 - c64) / c64
     if os.environ.get("PCB_REPORT_DIR"):
-        json.dump({"gpu": gpu, "oracle_fp64": c64, "oracle_fp32": c32, "gpu_vs_fp64": d_gpu.tolist(), "fp32_vs_fp64": d_f32.tolist()},
-                  open(os.path.join(os.environ["PCB_REPORT_DIR"], "loss_curve_100.json"), "w"), indent=1)
+        json.dump({"gpu": gpu.tolist(), "oracle_fp64": c64.tolist(), "oracle_fp32": c32.tolist(), "gpu_vs_fp64": d_gpu.tolist(),
+                   "fp32_vs_fp64": d_f32.tolist()}, open(os.path.join(os.environ["PCB_REPORT_DIR"], "loss_curve_100.json"), "w"), indent=1)
     assert c64[-1] < 0.8 * c64[0] and gpu[-1] < 0.8 * gpu[0]                        # the curves train
     bound = 3 * np.maximum.accumulate(d_f32) + 1e-3
     worst = int(np.argmax(d_gpu - bound))
     assert (d_gpu <= bound).all(), (worst, float(d_gpu[worst]), float(bound[worst]))
-    assert abs(np.mean(gpu[-10:]) - np.mean(c64[-10:])) / np.mean(c64[-10:]) < 3 * abs(np.mean(c32[-10:]) - np.mean(c64[-10:])) / np.mean(c64[-10:]) + 5e-3
+    assert abs(gpu[-10:].mean() - c64[-10:].mean()) / c64[-10:].mean() < 3 * abs(c32[-10:].mean() - c64[-10:].mean()) / c64[-10:].mean() + 5e-3
 
 
 def test_trainers_step_and_checkpoint_roundtrip(tmp_path, monkeypatch):
