@@ -277,14 +277,12 @@ def run_ours(args):
         return float(t.item())
 
     # ---- device-resident timing: one event per step boundary (no host sync inside the timed region)
-    # (the nvidia-smi sampler is started BEFORE the warm-up: its start-up -- process spawn, NVML / driver initialisation -- stalls kernel
-    #  launches for tens of ms once, which used to land inside the timed region as a single 60-90 ms step)
+    # (the nvidia-smi sampler is started BEFORE the warm-up: its start-up -- process spawn, NVML / driver initialisation -- otherwise opens
+    #  an idle gap right before the timed region, the SM clocks drop, and the first timed steps take 60-90 ms while they ramp up again)
     clocks = Clocks(local) if rank == 0 else None
     for i in range(args.warmup):
         trainer.train_step(dev_batches[i % len(dev_batches)])
     sync_all()
-    if clocks is not None:
-        time.sleep(0.3)
     import gc
     gc.collect()
     l0 = _lib.launch_count()

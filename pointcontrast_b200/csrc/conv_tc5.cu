@@ -33,7 +33,10 @@ __device__ __forceinline__ void split4(const float4& v, uint2& hi, uint2& lo) {
 
 constexpr int BM = 128, BK = 32, NTHR = 256, NS = 3;
 constexpr int A_SBO = 128;
-constexpr int A_LBO = (BM / 8) * 128 + 64;          // +64: the 4 k-chunks of a row land in different bank groups
+// k8-chunk stride of the A tile: +32 bytes, so that the four 16-byte chunks (t & 3) x two rows (t >> 2) written by a quarter-warp of a
+// 128-bit st.shared cover eight DIFFERENT 16-byte slots of a 128-byte bank line.  (Round 1 used +64: chunks 0/2 and 1/3 collided --
+// ncu counted 23.1 M of 39.8 M shared wavefronts as bank conflicts on the block8 shape.)
+constexpr int A_LBO = (BM / 8) * 128 + 32;
 constexpr int A_PLANE = (BK / 8) * A_LBO;
 
 struct Args {
