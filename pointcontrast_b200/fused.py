@@ -36,6 +36,11 @@ VIEW1_BATCH_OFFSET = 1 << 14      # batch indices of view 1 in a stacked tensor 
 SIDE_STREAM = os.environ.get("PCB_COORDS_STREAM", "1") == "1"
 # Cross-check switch: BatchNorm statistics by a separate pass over z instead of the convolution epilogue.
 SEPARATE_STATS = os.environ.get("PCB_SEPARATE_STATS", "0") == "1"
+# Test hook: a list to which every ReLU unit of a training forward pass appends (rows of view 0, bool [n, C] = the ReLU decision
+# its backward pass will use), in the order the model file calls its ReLUs.  tests/test_gpu_model.py replays these decisions in
+# the fp64 oracle: a pre-activation within rounding distance of zero is a coin flip in ANY finite precision, and one flipped
+# entry on a deep level moves every upstream gradient by ~1/sqrt(rows x channels) of its norm.
+CAPTURE_RELU = None
 
 
 # ------------------------------------------------------------------------------------------------ side-stream preparation
@@ -232,6 +237,17 @@ class Buf:
         return self._grad
 
 
+class _Plane:
+    def __init__(self, p, n, C, ld):
+        self.__cuda_array_interface__ = {"shape": (n, C), "strides": (2 * ld, 2), "typestr": "<i2", "data": (p, False), "version": 2}
+
+
+def _plane_i16(p, n, C, ld, device):
+    """A 16-bit plane of a Buf as an int16 tensor view (positive fp16 / bf16 values are positive int16 bit patterns)."""
+    with torch.cuda.device(device):
+        return torch.as_tensor(_Plane(p, n, C, ld), device=device)
+
+
 def _kmap(plan, which):
     """HOST int32 array of a plan's kernel-offset permutation (cached on the plan) or None."""
     cache = plan._c_kmaps
@@ -355,6 +371,8 @@ class Runner:
         if me.PROFILE is not None:
             me.PROFILE.append(dict(kind="fwd", K=K, Cin=Cin, Cout=Cout, n_in=plan.n_in, n_out=plan.n_out, plan=plan, tc=tc))
         check(lib.pcb_unit_forward(ctypes.byref(u), self.st))
+        if CAPTURE_RELU is not None and relu:
+            CAPTURE_RELU.append((n0, _plane_i16(out.hi, n, Cout, out.ld, self.device) > 0))
         if not self.eval_mode:
             self.bns.append(bn)
             self.units.append((u, conv, bn, a_in, out, plan, residual))

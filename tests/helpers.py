@@ -59,6 +59,30 @@ def model_backend(me_module):
         res16unet.ME = old
 
 
+@contextlib.contextmanager
+def pinned_relu(me_module, masks, flips):
+    """Run the oracle with the ReLU decisions of another run: the i-th MinkowskiReLU call multiplies by masks[i] (bool [n, C]) instead of
+    testing the sign itself; flips[i] = number of entries where the oracle's own sign test disagrees.  ReLU is the one discontinuous
+    operator of the network: a pre-activation that is zero to within rounding falls on either side in any finite precision (the fp32
+    CPU oracle against the fp64 one: 2 entries of 3 million at C0 size), and a single flipped entry on a deep level changes every upstream
+    gradient by ~1/sqrt(rows x channels) of its norm.  Pinning the decisions separates that coin from the arithmetic being tested."""
+    cls = me_module.MinkowskiReLU
+    old = cls.forward
+    it = iter(masks)
+
+    def forward(self, x):
+        m = next(it)
+        assert m.shape == x.F.shape, (m.shape, x.F.shape)
+        flips.append(int(((x.F > 0) != m).sum()))
+        return me_module.SparseTensor(x.F * m.to(x.F.dtype), coords_key=x.coords_key, coords_manager=x.coords_man)
+
+    cls.forward = forward
+    try:
+        yield
+    finally:
+        cls.forward = old
+
+
 def rel_err(a, b):
     a = a.detach().double().cpu(); b = b.detach().double().cpu()
     return float((a - b).norm() / (b.norm() + 1e-300))

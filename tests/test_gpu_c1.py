@@ -111,8 +111,10 @@ def test_direct_epilogue_conv_at_c1_rows(cin, cout):
     #  the bf16 planes of the activations, checked above)
 
 # ----------------------------------------------------------------------------------------------- one full C1 pair
-def _oracle(state, batch, dtype):
-    with model_backend(OR) as mod:
+def _oracle(state, batch, dtype, masks=None, flips=None):
+    import contextlib
+    from tests.helpers import pinned_relu
+    with (pinned_relu(OR, masks, flips) if masks is not None else contextlib.nullcontext()), model_backend(OR) as mod:
         onet = mod.Res16UNet34C(3, 32, refload.default_config(), D=3).to(dtype)
         onet.load_state_dict({k: (v.to(dtype) if v.dtype.is_floating_point else v) for k, v in state.items()})
         onet.train()
@@ -123,7 +125,8 @@ def _oracle(state, batch, dtype):
 
 @pytest.fixture(scope="module")
 def c1():
-    """One full-size pair on the GPU (stacked pass + PointInfoNCE + backward) and on the fp64 / fp32 oracle."""
+    """One full-size pair on the GPU (stacked pass + PointInfoNCE + backward) and on the fp64 oracle, twice: taking its own ReLU
+    decisions, and replaying the GPU pass's (tests/test_gpu_model.py::test_small_scene_all_gradients_with_pinned_relu_decisions)."""
     from pointcontrast_b200 import fused, losses, synth
     from pointcontrast_b200.model import load_model
     assert fused.PAIR
@@ -137,19 +140,26 @@ def c1():
     pairs = batch["correspondences"]
     nq = len(np.unique(pairs[:, 0]))
     q, k = loss_cpu.select_positives(pairs, rng.random(nq).astype(np.float32), 4096, rng.choice(nq, 4096, replace=False))
-    F0, F1 = net.forward_pair(torch.from_numpy(batch["sinput0_F"]), torch.from_numpy(batch["sinput0_C"]),
-                              torch.from_numpy(batch["sinput1_F"]), torch.from_numpy(batch["sinput1_C"]), torch.device("cuda"))
-    assert "_fused_runner" in net.__dict__
+    fused.CAPTURE_RELU = cap = []
+    try:
+        F0, F1 = net.forward_pair(torch.from_numpy(batch["sinput0_F"]), torch.from_numpy(batch["sinput0_C"]),
+                                  torch.from_numpy(batch["sinput1_F"]), torch.from_numpy(batch["sinput1_C"]), torch.device("cuda"))
+    finally:
+        fused.CAPTURE_RELU = None
+    assert "_fused_runner" in net.__dict__ and len(cap) == 55
+    masks = [m[:n0].cpu() for n0, m in cap] + [m[n0:].cpu() for n0, m in cap]
     loss = losses.point_nce_loss(F0, F1, q.cuda(), k.cuda(), 0.4)
     loss.backward()
     torch.cuda.synchronize()
     onet, Fo = _oracle(state, batch, torch.float64)
     lo = loss_cpu.point_nce_loss(Fo[0], Fo[1], q, k, 0.4)
     lo.backward()
-    onet32, Fo32 = _oracle(state, batch, torch.float32)
-    loss_cpu.point_nce_loss(Fo32[0], Fo32[1], q, k, 0.4).backward()
+    flips = []
+    pnet, Fp = _oracle(state, batch, torch.float64, masks, flips)
+    loss_cpu.point_nce_loss(Fp[0], Fp[1], q, k, 0.4).backward()
     return dict(batch=batch, net=net, F=(F0.detach(), F1.detach()), loss=float(loss.detach()), onet=onet, Fo=[f.detach() for f in Fo],
-                lo=float(lo.detach()), onet32=onet32, rng=rng)
+                lo=float(lo.detach()), pnet=pnet, flips=flips, relu_entries=sum(m.numel() for m in masks),
+                flip_sizes=[int(m.numel()) for m in masks], rng=rng)
 
 
 def test_c1_pair_features_and_loss(c1):
@@ -158,19 +168,26 @@ def test_c1_pair_features_and_loss(c1):
 
 
 def test_c1_pair_every_parameter_gradient(c1):
+    """All 187 parameter gradients of the full-size pair at the north-star tolerance, the fp64 oracle replaying the GPU pass's ReLU
+    decisions; those decisions may differ from the oracle's own on < 1e-4 of the entries (pre-activations within rounding of zero)."""
     import json
     import os
-    net, onet, onet32 = c1["net"], c1["onet"], c1["onet32"]
+    net, onet, pnet = c1["net"], c1["onet"], c1["pnet"]
     names = [n for n, _ in net.named_parameters()]
-    floor = np.array([rel_err(p32.grad, po.grad) for (_, po), (_, p32) in zip(onet.named_parameters(), onet32.named_parameters())])
-    err = np.array([rel_err(p.grad, po.grad) for (_, p), (_, po) in zip(net.named_parameters(), onet.named_parameters())])
-    tol = max(1e-3, 10 * float(floor.max()))
+    err = np.array([rel_err(p.grad, po.grad) for (_, p), (_, po) in zip(net.named_parameters(), pnet.named_parameters())])
+    err_nat = np.array([rel_err(p.grad, po.grad) for (_, p), (_, po) in zip(net.named_parameters(), onet.named_parameters())])
     order = np.argsort(-err)
-    report = {"floor_max": float(floor.max()), "floor_median": float(np.median(floor)), "err_max": float(err.max()),
-              "err_median": float(np.median(err)), "tol": tol, "worst": [(names[i], float(err[i]), float(floor[i])) for i in order[:8]]}
+    flips = c1["flips"]
+    report = {"relu_entries": c1["relu_entries"], "relu_flips_vs_fp64": int(sum(flips)),
+              "flips_by_call": [(i, f, c1["flip_sizes"][i]) for i, f in enumerate(flips) if f],
+              "pinned_err_max": float(err.max()), "pinned_err_median": float(np.median(err)),
+              "unpinned_err_max": float(err_nat.max()), "unpinned_err_median": float(np.median(err_nat)),
+              "worst_pinned": [(names[i], float(err[i])) for i in order[:8]]}
     if os.environ.get("PCB_REPORT_DIR"):
         json.dump(report, open(os.path.join(os.environ["PCB_REPORT_DIR"], "c1_grad_report.json"), "w"), indent=1)
-    assert (err <= tol).all(), report
+    assert sum(flips) <= 1e-4 * c1["relu_entries"], report
+    assert (err <= 1e-3).all(), report
+    assert err_nat.max() < 5e-2, report
     for (n, b), (_, bo) in zip(net.named_buffers(), onet.named_buffers()):        # BatchNorm running statistics after view 0, view 1
         if b.dtype.is_floating_point:
             assert rel_err(b, bo) < 1e-3, n

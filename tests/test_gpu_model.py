@@ -2,10 +2,11 @@
   * against the committed golden vectors, produced by the REFERENCE's model file running on the fp64 oracle
     (tests/golden/make_golden.py);
   * against the oracle run live with this repo's own model wiring (needs no reference tree).
-Tolerance: 1e-3 relative (north star) on per-point features and the loss.  Whole-network parameter gradients are
-ill-conditioned on this problem (BatchNorm backward cancels the common-mode gradient): the SAME graph in plain fp32 on
-the CPU is already 2e-3..5e-3 away from fp64 (stored in the golden file as `grad_relerr_f32`).  Gradients are therefore
-held to max(1e-3, 10 x that fp32 floor); the individual backward kernels are held to 1e-3 in tests/test_gpu_ops.py."""
+Tolerance: 1e-3 relative (north star) on per-point features, the loss and -- with the ReLU decisions pinned, see
+test_small_scene_all_gradients_with_pinned_relu_decisions -- every parameter gradient.  Against an oracle taking its own ReLU
+decisions the gradients of ANY finite-precision evaluation sit a few coin flips away (the same graph in plain fp32 on the CPU:
+2e-5 .. 7e-3 from fp64 depending on the thread count; stored in the golden file as `grad_relerr_f32`), so the golden-file test
+holds them to max(1e-3, 10 x that fp32 figure); the individual backward kernels are held to 1e-3 in tests/test_gpu_ops.py."""
 import os
 
 import numpy as np
@@ -66,56 +67,112 @@ def test_c0_against_reference_graph_golden():
     assert (np.abs(rm - g["bn_running_mean_l1"]) / (g["bn_running_mean_l1"] + 1e-30)).max() < 1e-3
 
 
-@pytest.mark.parametrize("simt", [False, True])
-def test_small_scene_against_live_oracle_all_gradients(simt):
-    """Own wiring on both sides; every one of the 187 parameter gradients is compared tensor by tensor, for the
-    tensor-core path and for the exact-fp32 SIMT path (which must sit at the CPU fp32 floor)."""
-    from pointcontrast_b200 import losses, me, synth
-    batch = synth.collate_pairs([synth.synth_pair(3, scale=0.12), synth.synth_pair(4, scale=0.1)])
-    net = _gpu_net(1)
+_SMALL = {}
 
-    def oracle(dtype):
+
+def _small_problem():
+    """Two small scene pairs, the deterministic weights, the positive draw and the fp64 oracle's own (unpinned) result."""
+    if _SMALL:
+        return _SMALL
+    from pointcontrast_b200 import synth
+    batch = synth.collate_pairs([synth.synth_pair(3, scale=0.12), synth.synth_pair(4, scale=0.1)])
+    rng = np.random.default_rng(0)
+    pairs = batch["correspondences"]
+    nq = len(np.unique(pairs[:, 0]))
+    q, k = loss_cpu.select_positives(pairs, rng.random(nq).astype(np.float32), 4096,
+                                     rng.choice(nq, 4096, replace=False) if nq > 4096 else None)
+    _SMALL.update(batch=batch, q=q, k=k)
+    return _SMALL
+
+
+def _oracle_run(state, batch, q, k, dtype, masks=None):
+    """Forward + PointInfoNCE + backward of the oracle; with `masks` (one bool [n, C] per ReLU call: view 0's calls, then view 1's)
+    the ReLU decisions are replayed instead of taken (tests/helpers.py pinned_relu)."""
+    import contextlib
+    from tests.helpers import pinned_relu
+    flips = []
+    with (pinned_relu(OR, masks, flips) if masks is not None else contextlib.nullcontext()):
         with model_backend(OR) as mod:
             onet = mod.Res16UNet34C(3, 32, refload.default_config(), D=3).to(dtype)
-            onet.load_state_dict({k: v.to(dtype).cpu() if v.dtype.is_floating_point else v.cpu() for k, v in net.state_dict().items()})
+            onet.load_state_dict({n: v.to(dtype).cpu() if v.dtype.is_floating_point else v.cpu() for n, v in state.items()})
             onet.train()
             Fo = [onet(OR.SparseTensor(torch.from_numpy(batch[f"sinput{v}_F"]).to(dtype),
                                        coords=torch.from_numpy(batch[f"sinput{v}_C"]))).F for v in "01"]
-        return onet, Fo
+    lo = loss_cpu.point_nce_loss(Fo[0], Fo[1], q, k, 0.4)
+    lo.backward()
+    return onet, Fo, lo, flips
 
-    init_state = {k: v.clone() for k, v in net.state_dict().items()}
-    onet, Fo = oracle(torch.float64)
-    onet32, Fo32 = oracle(torch.float32)
-    me.FORCE_SIMT = simt
+
+@pytest.mark.parametrize("path", ["fused_pair", "fused_views", "modular_simt"])
+def test_small_scene_all_gradients_with_pinned_relu_decisions(path):
+    """Every one of the 187 parameter gradients, tensor by tensor, against the fp64 oracle -- at the north-star tolerance (1e-3).
+
+    ReLU is the network's one discontinuous operator.  A pre-activation that is zero to within rounding falls on either side in ANY
+    finite precision: the oracle itself in fp32 disagrees with its fp64 run on 2 of the 3.0 million ReLU entries of this problem, and
+    those two entries alone put its gradients 5e-3 (median) .. 7e-3 (max) away from fp64 -- or 2e-5 away when a different thread count
+    happens to round them the other way (one flipped entry on a stride-16 level moves every upstream gradient by
+    ~1/sqrt(rows x channels) of its norm).  So the gradient comparison replays, in the fp64 oracle, the ReLU decisions the GPU pass
+    took (the sign of each unit's stored output, which is what its backward pass masks with); everything else -- convolutions,
+    BatchNorm statistics and backward, weight / data gradients, normalisation, loss -- is then held to 1e-3.  The decisions themselves
+    are checked separately: they may differ from the fp64 oracle's only on a handful of entries (< 1e-4 of them).
+
+    paths: the stacked-pair fused executor (what `forward_pair` / the trainer / bench.py run), the fused executor one view at a time
+    (`net(sparse_tensor)`), and the modular per-operator surface on the exact-fp32 SIMT kernels."""
+    from pointcontrast_b200 import fused, losses, me
+    P = _small_problem()
+    batch, q, k = P["batch"], P["q"], P["k"]
+    net = _gpu_net(1)
+    state = {n: v.clone() for n, v in net.state_dict().items()}
+    if "natural" not in P:
+        P["natural"] = _oracle_run(state, batch, q, k, torch.float64)
+    onet, Fo, lo, _ = P["natural"]
+    dev = torch.device("cuda")
+    T = {n: torch.from_numpy(batch[n]) for n in ("sinput0_F", "sinput0_C", "sinput1_F", "sinput1_C")}
+    cap, hooks = [], []
     try:
-        F = [net(me.SparseTensor(torch.from_numpy(batch[f"sinput{v}_F"]), coords=torch.from_numpy(batch[f"sinput{v}_C"])).to("cuda")).F
-             for v in "01"]
-        assert max_rel_err(F[0], Fo[0]) < 1e-3 and max_rel_err(F[1], Fo[1]) < 1e-3
-        rng = np.random.default_rng(0)
-        pairs = batch["correspondences"]
-        nq = len(np.unique(pairs[:, 0]))
-        q, k = loss_cpu.select_positives(pairs, rng.random(nq).astype(np.float32), 4096,
-                                         rng.choice(nq, 4096, replace=False) if nq > 4096 else None)
-        lo = loss_cpu.point_nce_loss(Fo[0], Fo[1], q, k, 0.4)
-        lo.backward()
-        loss_cpu.point_nce_loss(Fo32[0], Fo32[1], q, k, 0.4).backward()
+        if path == "modular_simt":
+            me.FORCE_SIMT = True
+            for mod in net.modules():
+                if isinstance(mod, me.MinkowskiReLU):
+                    hooks.append(mod.register_forward_hook(lambda m, i, o: cap.append((o.F.shape[0], o.F.detach() > 0))))
+        else:
+            fused.CAPTURE_RELU = cap
+        if path == "fused_pair":
+            F = list(net.forward_pair(T["sinput0_F"], T["sinput0_C"], T["sinput1_F"], T["sinput1_C"], dev))
+        else:
+            F = [net(me.SparseTensor(T[f"sinput{v}_F"], coords=T[f"sinput{v}_C"]).to("cuda")).F for v in "01"]
         l = losses.point_nce_loss(F[0], F[1], q.cuda(), k.cuda(), 0.4)
         l.backward()
     finally:
         me.FORCE_SIMT = False
+        fused.CAPTURE_RELU = None
+        for h in hooks:
+            h.remove()
+    assert len(cap) in (55, 110)
+    if len(cap) == 55:                     # stacked: rows of view 0, then rows of view 1, in every unit
+        masks = [m[:n0].cpu() for n0, m in cap] + [m[n0:].cpu() for n0, m in cap]
+    else:
+        masks = [m.cpu() for _, m in cap]
+    pnet, Fp, lp, flips = _oracle_run(state, batch, q, k, torch.float64, masks)
+    entries = sum(m.numel() for m in masks)
+    assert max_rel_err(F[0], Fo[0]) < 1e-3 and max_rel_err(F[1], Fo[1]) < 1e-3          # features: against the oracle's own decisions
     assert abs(float(l.detach()) - float(lo.detach())) / abs(float(lo.detach())) < 1e-3
+    assert abs(float(l.detach()) - float(lp.detach())) / abs(float(lp.detach())) < 1e-3
     names = [n for n, _ in net.named_parameters()]
-    floor = np.array([rel_err(p32.grad, po.grad) for (_, po), (_, p32) in zip(onet.named_parameters(), onet32.named_parameters())])
-    err = np.array([rel_err(p.grad, po.grad) for (_, p), (_, po) in zip(net.named_parameters(), onet.named_parameters())])
-    tol = _grad_tol(floor, 4 if simt else 10)
-    order = np.argsort(-err / tol)
-    report = [(names[i], float(err[i]), float(floor[i]), float(tol[i])) for i in order[:8]]
+    err = np.array([rel_err(p.grad, po.grad) for (_, p), (_, po) in zip(net.named_parameters(), pnet.named_parameters())])
+    err_nat = np.array([rel_err(p.grad, po.grad) for (_, p), (_, po) in zip(net.named_parameters(), onet.named_parameters())])
+    order = np.argsort(-err)
+    report = [(names[i], float(err[i])) for i in order[:8]]
     if os.environ.get("PCB_REPORT_DIR"):
         import json
-        json.dump({"simt": simt, "floor_max": float(floor.max()), "err_max": float(err.max()), "err_median": float(np.median(err)),
-                   "floor_median": float(np.median(floor)), "worst": report},
-                  open(os.path.join(os.environ["PCB_REPORT_DIR"], f"grad_report_simt{int(simt)}.json"), "w"), indent=1)
-    assert (err <= tol).all(), report
+        json.dump({"path": path, "relu_entries": entries, "relu_flips_vs_fp64": int(sum(flips)),
+                   "flips_by_call": [(i, f, int(masks[i].numel())) for i, f in enumerate(flips) if f],
+                   "pinned_err_max": float(err.max()), "pinned_err_median": float(np.median(err)),
+                   "unpinned_err_max": float(err_nat.max()), "unpinned_err_median": float(np.median(err_nat)), "worst_pinned": report},
+                  open(os.path.join(os.environ["PCB_REPORT_DIR"], f"grad_pinned_{path}.json"), "w"), indent=1)
+    assert sum(flips) <= 1e-4 * entries, (sum(flips), entries)
+    assert (err <= 1e-3).all(), report
+    assert err_nat.max() < 5e-2               # unpinned: a few coin flips; bounded, not meaningful beyond that
     for (n, b), (_, bo) in zip(net.named_buffers(), onet.named_buffers()):
         if b.dtype.is_floating_point:
             assert rel_err(b, bo) < 1e-3, n
