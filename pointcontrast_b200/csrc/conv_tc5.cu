@@ -12,6 +12,7 @@
 // Same arguments, kernel-offset skipping and split-reduce mode as conv_mma_kernel; results agree with it to fp32
 // rounding (same 3-term bf16 split, fp32 accumulation).
 #include <stdlib.h>
+#include <string.h>
 #include "common.cuh"
 #include "tc5_ptx.cuh"
 
@@ -55,7 +56,20 @@ struct Args {
   // and the factor applied to the accumulators on the way out (2^-10 when the weight tiles hold fp16(W * 2^10))
   uint32_t fmt_bits; float out_scale;
   int debug;            // timing experiments only (PCB_TC5_DEBUG): 1 skip A copies, 2 skip B copies, 4 skip MMAs, 8 skip proxy fence
+  int consumer_fence;   // generic -> async proxy fence issued by the MMA thread after the "full" wait instead of by every producer (see consumer_fence())
 };
+
+// Where the generic-proxy -> async-proxy fence of a stage sits.  `fence.proxy.async` compiles to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC, and
+// the membar waits for EVERY outstanding memory operation of the issuing thread -- for a producer that is the gather loads it has just
+// put in flight for the next stages, so each stage costs one full L2 round trip no matter how far ahead the loads are issued (ncu, round
+// 2: 25 % of all warp samples of the kernel sat on these two instructions with long-scoreboard stalls; an iteration took ~1900 cycles at
+// any occupancy).  The MMA-issuing thread has no loads in flight: producers st.shared -> mbarrier.arrive (release.cta), the issuer
+// mbarrier.try_wait (acquire.cta) -> fence.proxy.async -> tcgen05.mma.  PCB_TC5_FENCE=producer restores the writer-side fence.
+inline int consumer_fence() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("PCB_TC5_FENCE"); v = (e && !strcmp(e, "consumer")) ? 1 : 0; }
+  return v;
+}
 
 template <int BN>
 struct Smem {
@@ -402,7 +416,7 @@ __global__ void __launch_bounds__(DPROD + 32, CTAS) conv_tcgen05_split_kernel(co
         asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};\n" ::"r"(sb + a_dst[j]), "r"(v.h[j].x), "r"(v.h[j].y), "r"(v.h[j].z), "r"(v.h[j].w) : "memory");
         asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};\n" ::"r"(sb + A_PLANE + a_dst[j]), "r"(v.l[j].x), "r"(v.l[j].y), "r"(v.l[j].z), "r"(v.l[j].w) : "memory");
       }
-      if (!(p.debug & 8)) fence_proxy_async();
+      if (!(p.debug & 8) && !p.consumer_fence) fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(full_bar + 8 * is);
       if (++is == DNS) { is = 0; ++iround; }
@@ -422,6 +436,7 @@ __global__ void __launch_bounds__(DPROD + 32, CTAS) conv_tcgen05_split_kernel(co
     int s = 0, par = 0;
     for (int i = 0; i < n_it; ++i) {
       mbar_wait(full_bar + 8 * s, par);
+      if (p.consumer_fence) fence_proxy_async();
       tc_fence_after();
       const uint32_t a_hi = smem_base + s * S::STAGE, a_lo = a_hi + A_PLANE;
       const uint32_t b_hi = a_hi + 2 * A_PLANE, b_lo = b_hi + S::B_PLANE;
@@ -769,6 +784,7 @@ int launch_conv_tcgen05(const float* X, int ldx, const uint16_t* Xhi, const uint
   static int dbg = -1;
   if (dbg < 0) { const char* e = getenv("PCB_TC5_DEBUG"); dbg = e ? atoi(e) : 0; }
   a.debug = dbg;
+  a.consumer_fence = tc5::consumer_fence();
   a.Xhi = (const __nv_bfloat16*)Xhi; a.Xlo = (const __nv_bfloat16*)Xlo; a.lds = lds;
   a.wt = (const unsigned char*)wt;
   a.X = X; a.ldx = ldx; a.tbl = tbl; a.tbl_stride = tbl_stride; a.K = K; a.n_out = n_out; a.Cin = Cin; a.Cout = Cout;
@@ -805,6 +821,7 @@ struct Args {
   float* partial; int transpose_out;
   int ns;               // ring depth (host-chosen to fill shared memory)
   uint32_t fmt_bits;    // instruction-descriptor formats: bits 7-9 gathered operand, bits 10-12 row-aligned operand (0 fp16, 1 bf16)
+  int consumer_fence;   // tc5::consumer_fence()
 };
 
 // channel-chunk (core-matrix) stride 144 B, not 128: a producer warp writes the 16 chunks of ONE row, and a 128-byte stride
@@ -923,7 +940,7 @@ __global__ void __launch_bounds__(NTHR, 1) wgrad_tcgen05_kernel(const Args p) {
         sts(ab, v.h0); sts(ab + 2 * A_LBO, v.l0);
         sts(ab + 4 * A_LBO, v.h1); sts(ab + 6 * A_LBO, v.l1);
       }
-      fence_proxy_async();
+      if (!p.consumer_fence) fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(full_bar + 8 * is);
       if (++is == NS) { is = 0; ++iround; }
@@ -940,6 +957,7 @@ __global__ void __launch_bounds__(NTHR, 1) wgrad_tcgen05_kernel(const Args p) {
     int s = 0, par = 0;
     for (int i = 0; i < nsteps; ++i) {
       mbar_wait(full_bar + 8 * s, par);
+      if (p.consumer_fence) fence_proxy_async();
       tc_fence_after();
       const uint32_t sb = smem_base + s * STAGE;
       const uint64_t dbh = make_desc(sb, B_LBO, SBO), dbl = make_desc(sb + 2 * B_LBO, B_LBO, SBO);
@@ -1032,6 +1050,7 @@ int launch_wgrad_tcgen05(const uint16_t* Ahi, const uint16_t* Alo, int lda, cons
   a.Bhi = (const __nv_bfloat16*)Bhi; a.Blo = (const __nv_bfloat16*)Blo; a.ldb = ldb;
   a.tbl = tbl; a.tbl_stride = tbl_stride; a.K = K; a.n_out = n_out; a.Ca = Ca; a.Cb = Cb; a.rows_per_split = rows_per_split;
   a.partial = partial; a.transpose_out = transpose_out;
+  a.consumer_fence = tc5::consumer_fence();
   switch (tn) {
     case 128: return wg::launch<128>(a, splits, st);
     case 96: return wg::launch<96>(a, splits, st);
