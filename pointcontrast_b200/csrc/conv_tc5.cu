@@ -64,10 +64,17 @@ struct Args {
 // put in flight for the next stages, so each stage costs one full L2 round trip no matter how far ahead the loads are issued (ncu, round
 // 2: 25 % of all warp samples of the kernel sat on these two instructions with long-scoreboard stalls; an iteration took ~1900 cycles at
 // any occupancy).  The MMA-issuing thread has no loads in flight: producers st.shared -> mbarrier.arrive (release.cta), the issuer
-// mbarrier.try_wait (acquire.cta) -> fence.proxy.async -> tcgen05.mma.  PCB_TC5_FENCE=producer restores the writer-side fence.
+// mbarrier.try_wait (acquire.cta) -> fence.proxy.async -> tcgen05.mma.  Measured (profiles/r2_results.md): forward / data-gradient kernel
+// 339 -> 318 us on the block8 shape, 12.66 -> 12.08 ms per step; the weight-gradient kernel (12 MMAs per step on the issuing thread)
+// is 5 % SLOWER with it and keeps the writer-side fence.  PCB_TC5_FENCE=producer / PCB_WG_FENCE=consumer flip the defaults.
 inline int consumer_fence() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("PCB_TC5_FENCE"); v = (e && !strcmp(e, "consumer")) ? 1 : 0; }
+  if (v < 0) { const char* e = getenv("PCB_TC5_FENCE"); v = (e && !strcmp(e, "producer")) ? 0 : 1; }
+  return v;
+}
+inline int wgrad_consumer_fence() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("PCB_WG_FENCE"); v = (e && !strcmp(e, "consumer")) ? 1 : 0; }
   return v;
 }
 
@@ -295,10 +302,12 @@ struct DSmem {
 // <DNS, DPROD, CTAS>: <6, 512, 1> = one CTA per SM with a 6-slot ring; <3, 256, 2> = two CTAs per SM with 3 slots each --
 // every hand-off (mbarrier wake-up ~260 cycles, smem store -> fence -> arrive, MMA issue) is a serial chain inside a CTA,
 // so two co-resident CTAs hide each other's chains.
-template <int BN, int DNS, int DPROD, int CTAS, int PF = 3>
-__global__ void __launch_bounds__(DPROD + 32, CTAS) conv_tcgen05_split_kernel(const Args p) {
+// BW = 1: the weight tiles are launched by their own warp (one thread) as soon as a slot is free, instead of by producer thread 0 in
+// between its own gather loads and stores.
+template <int BN, int DNS, int DPROD, int CTAS, int PF = 3, int BW = 0>
+__global__ void __launch_bounds__(DPROD + 32 + 32 * BW, CTAS) conv_tcgen05_split_kernel(const Args p) {
   using S = DSmem<BN, DNS>;
-  constexpr int DTHR = DPROD + 32;
+  constexpr int DTHR = DPROD + 32 + 32 * BW;
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t row0 = (int64_t)blockIdx.x * BM;
@@ -405,7 +414,7 @@ __global__ void __launch_bounds__(DPROD + 32, CTAS) conv_tcgen05_split_kernel(co
         __syncwarp();
       }
       const uint32_t sb = smem_base + is * S::STAGE;
-      if (tid == 0) {
+      if (!BW && tid == 0) {
         const int k = s_klist[s_kq];
         mbar_arrive_expect_tx(full_bar + 8 * is, (p.debug & 2) ? 0u : BLOB);
         if (!(p.debug & 2))
@@ -431,7 +440,23 @@ __global__ void __launch_bounds__(DPROD + 32, CTAS) conv_tcgen05_split_kernel(co
       if (i + 2 < n_it) { store(v2); load(v2); }
       if (PF == 4 && i + 3 < n_it) { store(v3); load(v3); }
     }
-  } else if (lane == 0) {
+  } else if (BW && warp == DPROD / 32 + 1) {
+    // ===== weight-tile loader: one TMA bulk copy per stage, as soon as the slot's previous MMAs have committed =====
+    if (lane == 0) {
+      constexpr uint32_t BLOB = 2 * S::B_PLANE;
+      const int nblk = p.Cout / BN;
+      int s = 0, round = 0, kq = it0 / nkc, kc = it0 - kq * nkc;
+      for (int i = 0; i < n_it; ++i) {
+        if (round >= 1) mbar_wait(empty_bar + 8 * s, (round - 1) & 1);
+        const int k = s_klist[kq];
+        mbar_arrive_expect_tx(full_bar + 8 * s, (p.debug & 2) ? 0u : BLOB);
+        if (!(p.debug & 2))
+          tma_bulk_load(smem_base + s * S::STAGE + 2 * A_PLANE, p.wt + ((int64_t)(k * nkc + kc) * nblk + blockIdx.y) * BLOB, BLOB, full_bar + 8 * s);
+        if (++s == DNS) { s = 0; ++round; }
+        if (++kc == nkc) { kc = 0; ++kq; }
+      }
+    }
+  } else if (warp == DPROD / 32 && lane == 0) {
     // ===== MMA issuer =====
     int s = 0, par = 0;
     for (int i = 0; i < n_it; ++i) {
@@ -628,7 +653,7 @@ __global__ void __launch_bounds__(544, 1) conv_tcgen05_wide_kernel(const Args p)
         asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};\n" ::"r"(d), "r"(v.h[j].x), "r"(v.h[j].y), "r"(v.h[j].z), "r"(v.h[j].w) : "memory");
         asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};\n" ::"r"(d + A_PLANE), "r"(v.l[j].x), "r"(v.l[j].y), "r"(v.l[j].z), "r"(v.l[j].w) : "memory");
       }
-      fence_proxy_async();
+      if (!p.consumer_fence) fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(full_bar + 8 * is);
       if (++is == DNS) { is = 0; ++iround; }
@@ -644,6 +669,7 @@ __global__ void __launch_bounds__(544, 1) conv_tcgen05_wide_kernel(const Args p)
     int s = 0, par = 0;
     for (int i = 0; i < n_it; ++i) {
       mbar_wait(full_bar + 8 * s, par);
+      if (p.consumer_fence) fence_proxy_async();
       tc_fence_after();
       const uint32_t sb = smem_base + s * S::STAGE;
       const uint32_t b_hi = sb + 4 * A_PLANE, b_lo = b_hi + S::B_PLANE;
@@ -722,17 +748,17 @@ int launch_wide(const Args& a, cudaStream_t st) {
   return check_launch("conv_tcgen05_wide_kernel");
 }
 
-template <int BN, int DNS, int DPROD, int CTAS, int PF = 3>
+template <int BN, int DNS, int DPROD, int CTAS, int PF = 3, int BW = 0>
 int launch_split_cfg(const Args& a, int nsplit, cudaStream_t st) {
   using S = DSmem<BN, DNS>;
   static bool attr_set[64] = {};          // per device: the opt-in is a per-device function attribute
   const int dev_ = current_device();
   if (!attr_set[dev_]) {
-    PCB_CUDA(cudaFuncSetAttribute(conv_tcgen05_split_kernel<BN, DNS, DPROD, CTAS, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    PCB_CUDA(cudaFuncSetAttribute(conv_tcgen05_split_kernel<BN, DNS, DPROD, CTAS, PF, BW>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     attr_set[dev_] = true;
   }
   dim3 grid((unsigned)((a.n_out + BM - 1) / BM), a.Cout / BN, nsplit);
-  launch_kernel(conv_tcgen05_split_kernel<BN, DNS, DPROD, CTAS, PF>, grid, DPROD + 32, S::TOTAL, st, a);
+  launch_kernel(conv_tcgen05_split_kernel<BN, DNS, DPROD, CTAS, PF, BW>, grid, DPROD + 32 + 32 * BW, S::TOTAL, st, a);
   return check_launch("conv_tcgen05_split_kernel");
 }
 
@@ -748,6 +774,7 @@ int launch_split(const Args& a, int nsplit, cudaStream_t st) {
   if (cfg == 1) return launch_split_cfg<BN, 6, 512, 1>(a, nsplit, st);
   if (cfg == 3) return launch_split_cfg<BN, 2, 256, 3>(a, nsplit, st);
   if (cfg == 5) return launch_split_cfg<BN, 3, 256, 2, 4>(a, nsplit, st);         // gathered rows loaded 4 (not 3) stages ahead
+  if (cfg == 6) return launch_split_cfg<BN, 3, 256, 2, 3, 1>(a, nsplit, st);      // weight tiles launched by their own warp
   return launch_split_cfg<BN, 3, 256, 2>(a, nsplit, st);
 }
 
@@ -821,7 +848,7 @@ struct Args {
   float* partial; int transpose_out;
   int ns;               // ring depth (host-chosen to fill shared memory)
   uint32_t fmt_bits;    // instruction-descriptor formats: bits 7-9 gathered operand, bits 10-12 row-aligned operand (0 fp16, 1 bf16)
-  int consumer_fence;   // tc5::consumer_fence()
+  int consumer_fence;   // tc5::wgrad_consumer_fence()
 };
 
 // channel-chunk (core-matrix) stride 144 B, not 128: a producer warp writes the 16 chunks of ONE row, and a 128-byte stride
@@ -1050,7 +1077,7 @@ int launch_wgrad_tcgen05(const uint16_t* Ahi, const uint16_t* Alo, int lda, cons
   a.Bhi = (const __nv_bfloat16*)Bhi; a.Blo = (const __nv_bfloat16*)Blo; a.ldb = ldb;
   a.tbl = tbl; a.tbl_stride = tbl_stride; a.K = K; a.n_out = n_out; a.Ca = Ca; a.Cb = Cb; a.rows_per_split = rows_per_split;
   a.partial = partial; a.transpose_out = transpose_out;
-  a.consumer_fence = tc5::consumer_fence();
+  a.consumer_fence = tc5::wgrad_consumer_fence();
   switch (tn) {
     case 128: return wg::launch<128>(a, splits, st);
     case 96: return wg::launch<96>(a, splits, st);

@@ -1,6 +1,7 @@
 """Data-parallel step of the trainer (`pretrain/pointcontrast/lib/ddp_trainer.py:96-102`: DistributedDataParallel) with
 world_size 2.  Two processes share ONE GPU over the gloo backend (NCCL refuses two ranks on one device; gloo all-reduces CUDA
-tensors through the host), so this runs on the single-GPU test box; `bench.py --gpus N` exercises the same code over NCCL.
+tensors through the host), so this runs on the single-GPU test box; with two devices visible the same test also runs over NCCL,
+one rank per device (`profiles/scripts/r2_run10.sh`), which is the path `bench.py --gpus N` takes.
 
 Checked after one `train_step` on different per-rank batches:
   * parameters (and SGD momentum buffers) are bit-identical on the two ranks;
@@ -40,11 +41,11 @@ def _make_trainer(rank, world):
     return tr, loader.batches[0]
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, backend):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
-    torch.cuda.set_device(0)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.cuda.set_device(rank if backend == "nccl" else 0)
+    dist.init_process_group(backend, rank=rank, world_size=world)
     try:
         tr, batch = _make_trainer(rank, world)
         assert tr.world == 2 and tr.optimizer.grad_scale == 0.5
@@ -61,10 +62,14 @@ def _worker(rank, world, port, out_dir):
         dist.destroy_process_group()
 
 
-def test_two_rank_step_equals_mean_of_single_rank_gradients(tmp_path):
+@pytest.mark.parametrize("backend", ["gloo", "nccl"])
+def test_two_rank_step_equals_mean_of_single_rank_gradients(tmp_path, backend):
+    """gloo: both ranks on device 0 (the single-GPU test box); nccl: one rank per device (needs two, `gpurun --gpus 2`)."""
     import torch.multiprocessing as mp
+    if backend == "nccl" and torch.cuda.device_count() < 2:
+        pytest.skip("NCCL needs one device per rank")
     port = _free_port()
-    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, str(tmp_path), backend), nprocs=2, join=True)
     r0 = torch.load(tmp_path / "rank0.pt")
     r1 = torch.load(tmp_path / "rank1.pt")
     assert r0["chunks"] == 3 and r1["chunks"] == 3
