@@ -388,7 +388,7 @@ def run_ours(args):
         n0 = int(np.mean([len(b["sinput0_C"]) for b in host_batches])); n1 = int(np.mean([len(b["sinput1_C"]) for b in host_batches]))
         line = {"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32 (bf16x3-split tensor-core products, fp32 accumulate)", "data": "synthetic",
+                "dtype": "f32 (hi+lo split 16-bit operands: 3 tensor-core products per fp32 product; fp16 planes forward, bf16 planes for gradients; fp32 accumulate)", "data": "synthetic",
                 "config": static_config(args, world),
                 "details": {"voxels_per_view_per_rank": [n0, n1],
                             "schedule": "both views stacked in one pass (per-view BatchNorm statistics)" if fused.PAIR else "two forward calls",
@@ -444,7 +444,7 @@ def run_c4(args):
     h2d = int(np.mean([f.numel() * 4 + c.numel() * 4 for f, c in host]))
     print(json.dumps({"metric": METRIC_C4, "value": 1e3 / ms, "unit": "scenes/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
                       "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                      "dtype": "f32 (bf16x3-split tensor-core products, fp32 accumulate)", "data": "synthetic",
+                      "dtype": "f32 (hi+lo split 16-bit operands: 3 tensor-core products per fp32 product; fp16 planes forward, bf16 planes for gradients; fp32 accumulate)", "data": "synthetic",
                       "config": static_config(args, 1), "details": {"voxels_per_scene": nvox, "voxels_per_s": nvox * 1e3 / ms},
                       "clocks": clk, "gpu_launches": int(launches),
                       "e2e": {"value": 1e3 / ms_e2e, "unit": "scenes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(nvox * 8)}}), flush=True)

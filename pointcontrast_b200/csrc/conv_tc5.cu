@@ -304,7 +304,11 @@ struct DSmem {
 // so two co-resident CTAs hide each other's chains.
 // BW = 1: the weight tiles are launched by their own warp (one thread) as soon as a slot is free, instead of by producer thread 0 in
 // between its own gather loads and stores.
-template <int BN, int DNS, int DPROD, int CTAS, int PF = 3, int BW = 0>
+// CPA = 1: the gathered rows go global -> shared by cp.async (LDGSTS, zero-fill for absent neighbours) and every producer thread hands its
+// copies to the stage's "full" barrier with cp.async.mbarrier.arrive.noinc: no data registers, no st.shared, no wait inside the producer
+// -- ~40 instructions per thread and stage instead of ~180 (the register-staged loop is bound by its own instruction stream: with the
+// loads, the weight tiles or the MMAs switched off the kernel still takes 260-280 of its 320 us, profiles/r2_results.md).
+template <int BN, int DNS, int DPROD, int CTAS, int PF = 3, int BW = 0, int CPA = 0>
 __global__ void __launch_bounds__(DPROD + 32 + 32 * BW, CTAS) conv_tcgen05_split_kernel(const Args p) {
   using S = DSmem<BN, DNS>;
   constexpr int DTHR = DPROD + 32 + 32 * BW;
@@ -321,7 +325,7 @@ __global__ void __launch_bounds__(DPROD + 32 + 32 * BW, CTAS) conv_tcgen05_split
   const uint32_t full_bar = smem_base + S::BAR_OFF, empty_bar = full_bar + 8 * DNS, done_bar = empty_bar + 8 * DNS;
 
   if (tid == 0) {
-    for (int i = 0; i < DNS; ++i) { mbar_init(full_bar + 8 * i, DPROD / 32 + 1); mbar_init(empty_bar + 8 * i, 1); }
+    for (int i = 0; i < DNS; ++i) { mbar_init(full_bar + 8 * i, (CPA ? DPROD : DPROD / 32) + 1); mbar_init(empty_bar + 8 * i, 1); }
     mbar_init(done_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
@@ -362,7 +366,44 @@ __global__ void __launch_bounds__(DPROD + 32 + 32 * BW, CTAS) conv_tcgen05_split
   const int n_it = (p.debug & 16) ? 0 : it1 - it0;
   const uint32_t IDESC = (1u << 4) | p.fmt_bits | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
-  if (warp < DPROD / 32) {
+  if (CPA && warp < DPROD / 32) {
+    // ===== producers, cp.async flavour: thread t owns the 16-byte chunk t&3 of rows t>>2 and 64 + (t>>2), hi and lo plane
+    static_assert(!CPA || BW, "the cp.async producers leave the weight tiles to the loader warp");
+    constexpr int RP = BM * 4 / DPROD;
+    const int ar = tid >> 2, ak8 = tid & 3;
+    uint32_t a_dst[RP];
+#pragma unroll
+    for (int j = 0; j < RP; ++j) { const int r = ar + j * (DPROD / 4); a_dst[j] = ak8 * A_LBO + (r >> 3) * A_SBO + (r & 7) * 16; }
+    int kq = it0 / nkc, kc = it0 - kq * nkc;
+    const __nv_bfloat16* src_hi[RP]; const __nv_bfloat16* src_lo[RP]; uint32_t nbytes[RP];
+    auto set_k = [&]() {
+      const int kb = s_klist[kq] * BM;
+#pragma unroll
+      for (int j = 0; j < RP; ++j) {
+        const int idx = s_idx[kb + ar + j * (DPROD / 4)];
+        nbytes[j] = idx >= 0 ? 16u : 0u;                                 // absent neighbour: zero-fill, nothing read
+        const int64_t off = (int64_t)(idx >= 0 ? idx : 0) * p.lds + ak8 * 8;
+        src_hi[j] = p.Xhi + off; src_lo[j] = p.Xlo + off;
+      }
+    };
+    if (n_it > 0) set_k();
+    int is = 0, iround = 0;
+    for (int i = 0; i < n_it; ++i) {
+      if (iround >= 1) {
+        if (lane == 0) mbar_wait(empty_bar + 8 * is, (iround - 1) & 1);
+        __syncwarp();
+      }
+      const uint32_t sb = smem_base + is * S::STAGE;
+#pragma unroll
+      for (int j = 0; j < RP; ++j) {
+        cp_async16_zfill(sb + a_dst[j], src_hi[j] + kc * BK, (p.debug & 1) ? 0u : nbytes[j]);
+        cp_async16_zfill(sb + A_PLANE + a_dst[j], src_lo[j] + kc * BK, (p.debug & 1) ? 0u : nbytes[j]);
+      }
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(full_bar + 8 * is) : "memory");
+      if (++is == DNS) { is = 0; ++iround; }
+      if (++kc == nkc) { kc = 0; ++kq; if (i + 1 < n_it) set_k(); }
+    }
+  } else if (warp < DPROD / 32) {
     // ===== producers.  Thread t always owns the same two 16-byte chunks of the A tile (row t>>2, chunk t&3, hi + lo
     // plane): 128-bit global loads into registers PF stages ahead, 128-bit shared stores when the slot is free.
     // The weight tile of a stage is ONE TMA bulk copy (the weights are pre-tiled as shared-memory images), issued by
@@ -461,7 +502,7 @@ __global__ void __launch_bounds__(DPROD + 32 + 32 * BW, CTAS) conv_tcgen05_split
     int s = 0, par = 0;
     for (int i = 0; i < n_it; ++i) {
       mbar_wait(full_bar + 8 * s, par);
-      if (p.consumer_fence) fence_proxy_async();
+      if (p.consumer_fence || CPA) fence_proxy_async();
       tc_fence_after();
       const uint32_t a_hi = smem_base + s * S::STAGE, a_lo = a_hi + A_PLANE;
       const uint32_t b_hi = a_hi + 2 * A_PLANE, b_lo = b_hi + S::B_PLANE;
@@ -748,17 +789,17 @@ int launch_wide(const Args& a, cudaStream_t st) {
   return check_launch("conv_tcgen05_wide_kernel");
 }
 
-template <int BN, int DNS, int DPROD, int CTAS, int PF = 3, int BW = 0>
+template <int BN, int DNS, int DPROD, int CTAS, int PF = 3, int BW = 0, int CPA = 0>
 int launch_split_cfg(const Args& a, int nsplit, cudaStream_t st) {
   using S = DSmem<BN, DNS>;
   static bool attr_set[64] = {};          // per device: the opt-in is a per-device function attribute
   const int dev_ = current_device();
   if (!attr_set[dev_]) {
-    PCB_CUDA(cudaFuncSetAttribute(conv_tcgen05_split_kernel<BN, DNS, DPROD, CTAS, PF, BW>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    PCB_CUDA(cudaFuncSetAttribute(conv_tcgen05_split_kernel<BN, DNS, DPROD, CTAS, PF, BW, CPA>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     attr_set[dev_] = true;
   }
   dim3 grid((unsigned)((a.n_out + BM - 1) / BM), a.Cout / BN, nsplit);
-  launch_kernel(conv_tcgen05_split_kernel<BN, DNS, DPROD, CTAS, PF, BW>, grid, DPROD + 32 + 32 * BW, S::TOTAL, st, a);
+  launch_kernel(conv_tcgen05_split_kernel<BN, DNS, DPROD, CTAS, PF, BW, CPA>, grid, DPROD + 32 + 32 * BW, S::TOTAL, st, a);
   return check_launch("conv_tcgen05_split_kernel");
 }
 
@@ -775,6 +816,8 @@ int launch_split(const Args& a, int nsplit, cudaStream_t st) {
   if (cfg == 3) return launch_split_cfg<BN, 2, 256, 3>(a, nsplit, st);
   if (cfg == 5) return launch_split_cfg<BN, 3, 256, 2, 4>(a, nsplit, st);         // gathered rows loaded 4 (not 3) stages ahead
   if (cfg == 6) return launch_split_cfg<BN, 3, 256, 2, 3, 1>(a, nsplit, st);      // weight tiles launched by their own warp
+  if (cfg == 7) return launch_split_cfg<BN, 3, 256, 2, 3, 1, 1>(a, nsplit, st);   // + cp.async producers
+  if (cfg == 8) return launch_split_cfg<BN, 2, 256, 3, 3, 1, 1>(a, nsplit, st);   // cp.async producers, three CTAs per SM with 2-slot rings
   return launch_split_cfg<BN, 3, 256, 2>(a, nsplit, st);
 }
 
