@@ -334,12 +334,27 @@ __global__ void __launch_bounds__(DPROD + 32 + 32 * BW, CTAS) conv_tcgen05_split
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
   }
   pdl_wait(); pdl_trigger();        // barriers + TMEM are set up while the preceding kernel drains; no global memory touched before this
-  for (int e = tid; e < p.K * BM; e += DTHR) {
-    int k = e / BM, r = e - k * BM;
-    int64_t row = row0 + r;
-    int v = -1;
-    if (row < p.n_out) v = p.tbl[(int64_t)p.kmap[k] * p.tbl_stride + row];
-    s_idx[e] = v;
+  {
+    // this tile's slice of the neighbour table -> shared memory.  All loads of a thread are issued before the first store: the
+    // table is read once per tile straight from DRAM / L2, and a load-store loop would pay that latency FILL times in a row.
+    constexpr int FILL = (PCB_MAX_KERNEL_VOLUME * BM + DTHR - 1) / DTHR;
+    int vals[FILL];
+#pragma unroll
+    for (int f = 0; f < FILL; ++f) {
+      const int e = tid + f * DTHR;
+      int v = -1;
+      if (e < p.K * BM) {
+        const int k = e / BM, r = e - k * BM;
+        const int64_t row = row0 + r;
+        if (row < p.n_out) v = __ldg(p.tbl + (int64_t)p.kmap[k] * p.tbl_stride + row);
+      }
+      vals[f] = v;
+    }
+#pragma unroll
+    for (int f = 0; f < FILL; ++f) {
+      const int e = tid + f * DTHR;
+      if (e < p.K * BM) s_idx[e] = vals[f];
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -352,10 +367,12 @@ __global__ void __launch_bounds__(DPROD + 32 + 32 * BW, CTAS) conv_tcgen05_split
     if (lane == 0) s_flag[k] = any ? 1 : 0;
   }
   __syncthreads();
-  if (tid == 0) {
-    int nk = 0;
-    for (int k = 0; k < p.K; ++k) if (s_flag[k]) s_klist[nk++] = k;
-    *s_nk = nk;
+  if (warp == 0) {                  // offsets with at least one neighbour in this tile, in order (K <= 27 < 32: one ballot)
+    static_assert(PCB_MAX_KERNEL_VOLUME <= 32, "one ballot per tile");
+    const int f = lane < p.K ? s_flag[lane] : 0;
+    const unsigned m = __ballot_sync(0xffffffffu, f != 0);
+    if (f) s_klist[__popc(m & ((1u << lane) - 1u))] = lane;
+    if (lane == 0) *s_nk = __popc(m);
   }
   __syncthreads();
   const int nk = *s_nk;
