@@ -283,6 +283,7 @@ extern "C" int pcb_weight_prep(const float* W, int K, int Cin, int Cout, uint16_
 }
 
 namespace pcb {
+int wgrad_group();
 int launch_wgrad_tcgen05(const uint16_t* Ahi, const uint16_t* Alo, int lda, const uint16_t* Bhi, const uint16_t* Blo, int ldb,
                          const int32_t* tbl, int64_t tbl_stride, int K, int64_t n_out, int Ca, int Cb, int rows_per_split, int splits,
                          float* partial, int transpose_out, int tn, cudaStream_t st, int a_fp16 = 0, int b_fp16 = 0);
@@ -576,10 +577,11 @@ extern "C" int pcb_conv_forward_split(const uint16_t* Xhi, const uint16_t* Xlo, 
 namespace {
 int wgrad_split_splits(int K, int64_t n_out, int Ca, int Cb) {
   int tn = pick_tile(Cb);
-  int64_t base = (int64_t)((K + 3) / 4) * ((Ca + 127) / 128) * (Cb / tn);      // CTAs per split: offset groups x channel blocks
+  const int gk = pcb::wgrad_group();          // 4 offsets per CTA, one CTA per SM -- or 2 and two CTAs per SM
+  int64_t base = (int64_t)((K + gk - 1) / gk) * ((Ca + 127) / 128) * (Cb / tn);      // CTAs per split: offset groups x channel blocks
   static double wwaves = 0.0;
   if (wwaves == 0.0) { const char* e = getenv("PCB_WGRAD_SPLIT_WAVES"); wwaves = e ? atof(e) : 1.0; if (wwaves < 0.05) wwaves = 0.05; }      // measured on C1: 1 wave best (0.5 under-fills, 2-3 add reduce traffic)
-  int64_t s = (int64_t)(wwaves * num_sms()) / base;       // one CTA per SM: whole waves, never a nearly-empty extra one
+  int64_t s = (int64_t)(wwaves * num_sms() * (gk == 2 ? 2 : 1)) / base;       // whole waves of resident CTAs, never a nearly-empty extra one
   int64_t max_s = (n_out + 63) / 64;          // small levels: rather many short CTAs than a few long serial ones
   if (s > max_s) s = max_s;
   if (s < 1) s = 1;

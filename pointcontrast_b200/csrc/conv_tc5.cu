@@ -886,6 +886,13 @@ int launch_conv_tcgen05(const float* X, int ldx, const uint16_t* Xhi, const uint
   }
 }
 
+// Offsets per weight-gradient CTA (PCB_WG_GROUP = 4 | 2); conv.cu sizes the row splits and the partial buffer with it.
+int wgrad_group() {
+  static int v = 0;
+  if (!v) { const char* e = getenv("PCB_WG_GROUP"); v = (e && atoi(e) == 2) ? 2 : 4; }
+  return v;
+}
+
 // ------------------------------------------------------------------------------------------------ weight gradient
 // dW[k] (Ca x Cb) = sum_j A[tbl[k][j], :]^T . B[j, :] on split (bf16 hi/lo) operands.
 // UMMA view: D_k[M = Ca-block (padded to 128)][N = Cb-block] += A_k[M x 16 rows] . B[16 rows x N]; both operands MN-major
@@ -898,7 +905,10 @@ int launch_conv_tcgen05(const float* X, int ldx, const uint16_t* Xhi, const uint
 // grid: x = groups * mblocks * nblocks, y = row splits; partial tiles are reduced by wgrad_reduce_kernel (conv.cu).
 namespace wg {
 
-constexpr int WM = 128, WK = 16, WPROD = 512, NTHR = WPROD + 32, GK = 4;
+constexpr int WM = 128, WK = 16;
+// <GK, WPROD, CTAS>: <4, 512, 1> = one CTA per SM, 4 offsets share every staged row-aligned tile (all 512 TMEM columns);
+// <2, 256, 2> = two CTAs per SM with 2 offsets each: the per-step chain (table -> row loads -> st.shared -> fence -> arrive -> MMA ->
+// commit) is serial inside a CTA, and two co-resident CTAs hide each other's (the same trade the forward kernel makes).
 
 struct Args {
   const __nv_bfloat16* Ahi; const __nv_bfloat16* Alo; int lda;      // gathered operand (elements)
@@ -916,11 +926,12 @@ struct Args {
 constexpr int SBO = 144;
 __host__ __device__ inline int a_lbo(int mrows) { return (mrows / 8) * SBO + 16; }
 __host__ __device__ inline int b_lbo(int tn) { return (tn / 8) * SBO + 16; }
-__host__ __device__ inline int stage_bytes(int mrows, int tn) { return 4 * b_lbo(tn) + GK * 4 * a_lbo(mrows); }
+__host__ __device__ inline int stage_bytes(int mrows, int tn, int gk) { return 4 * b_lbo(tn) + gk * 4 * a_lbo(mrows); }
 
-template <int TN>
-__global__ void __launch_bounds__(NTHR, 1) wgrad_tcgen05_kernel(const Args p) {
+template <int TN, int GK, int WPROD, int CTAS>
+__global__ void __launch_bounds__(WPROD + 32, CTAS) wgrad_tcgen05_kernel(const Args p) {
   using namespace tc5;
+  static_assert((GK == 4 && WPROD == 512) || (GK == 2 && WPROD == 256), "thread = (row, 16-byte chunk) of two offsets");
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int mblocks = (p.Ca + WM - 1) / WM, nblocks = p.Cb / TN;
@@ -934,7 +945,7 @@ __global__ void __launch_bounds__(NTHR, 1) wgrad_tcgen05_kernel(const Args p) {
   const int ach = mrows / 8;
   constexpr int BCH = TN / 8;
   const int A_LBO = a_lbo(mrows), B_LBO = b_lbo(TN);
-  const int STAGE = stage_bytes(mrows, TN);
+  const int STAGE = stage_bytes(mrows, TN, GK);
   const int NS = p.ns;
   const int64_t r_begin = (int64_t)blockIdx.y * p.rows_per_split;
   const int64_t r_end = min(p.n_out, r_begin + p.rows_per_split);
@@ -965,14 +976,15 @@ __global__ void __launch_bounds__(NTHR, 1) wgrad_tcgen05_kernel(const Args p) {
 
   if (warp < WPROD / 32) {
     constexpr int PF = 2;
-    const int r = tid >> 5, kh = (tid >> 4) & 1, ch = tid & 15;   // row of the step, offset pair (2kh, 2kh+1), 16-byte channel chunk
+    // row of the step, offset pair (2kh, 2kh+1), 16-byte channel chunk
+    const int r = GK == 4 ? tid >> 5 : tid >> 4, kh = GK == 4 ? (tid >> 4) & 1 : 0, ch = tid & 15;
     const bool a_on = ch < ach, b_on = (ch < BCH) && kh == 0;
     const uint32_t a_dst = kh * 8 * A_LBO + (r >> 3) * A_LBO + ch * SBO + (r & 7) * 16;   // A block of offset 2kh, hi plane
     const uint32_t b_dst = (r >> 3) * B_LBO + ch * SBO + (r & 7) * 16;
     const int64_t a_col = m0 + ch * 8, b_col = n0 + ch * 8;
     const int32_t* trow = p.tbl + (int64_t)(k0 + 2 * kh) * p.tbl_stride;
     const int32_t* trow_other = p.tbl + (int64_t)(k0 + 2 * (1 - kh)) * p.tbl_stride;
-    const bool g0 = 2 * kh < nk, g1 = 2 * kh + 1 < nk, o0 = 2 * (1 - kh) < nk, o1 = 2 * (1 - kh) + 1 < nk;
+    const bool g0 = 2 * kh < nk, g1 = 2 * kh + 1 < nk, o0 = GK == 4 && 2 * (1 - kh) < nk, o1 = GK == 4 && 2 * (1 - kh) + 1 < nk;
     // Table entries are fetched TF steps ahead of the data loads that depend on them (a register ring, shifted once per step),
     // the data loads PF steps ahead of the shared-memory stores: neither dependent global-load latency (table -> row segment ->
     // st.shared, ~900 cycles each under load) sits on the per-step critical path.  (ncu, round 2: with the table only ONE step ahead
@@ -1104,17 +1116,17 @@ __global__ void __launch_bounds__(NTHR, 1) wgrad_tcgen05_kernel(const Args p) {
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_acc), "r"(TMEM_COLS));
 }
 
-template <int TN>
-int launch(Args a, int splits, cudaStream_t st) {
+template <int TN, int GK, int WPROD, int CTAS>
+int launch_cfg(Args a, int splits, cudaStream_t st) {
   static bool attr_set[64] = {};          // per device: the opt-in is a per-device function attribute
-  constexpr int MAX_SMEM = 220 * 1024;
+  constexpr int MAX_SMEM = CTAS == 1 ? 220 * 1024 : 112 * 1024;
   const int dev_ = current_device();
   if (!attr_set[dev_]) {
-    PCB_CUDA(cudaFuncSetAttribute(wgrad_tcgen05_kernel<TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
+    PCB_CUDA(cudaFuncSetAttribute(wgrad_tcgen05_kernel<TN, GK, WPROD, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
     attr_set[dev_] = true;
   }
   const int mrows_max = a.Ca < WM ? a.Ca : WM;
-  const int stage = stage_bytes(mrows_max, TN);
+  const int stage = stage_bytes(mrows_max, TN, GK);
   int ns = (MAX_SMEM - 6144) / stage;
   if (ns > 8) ns = 8;
   if (ns < 2) { set_error("wgrad_tcgen05: stage does not fit"); return PCB_ERR_ARG; }
@@ -1122,8 +1134,13 @@ int launch(Args a, int splits, cudaStream_t st) {
   const int groups = (a.K + GK - 1) / GK;
   dim3 grid((unsigned)(groups * ((a.Ca + WM - 1) / WM) * (a.Cb / TN)), splits);
   // + 4 KB: the M = 128 descriptor of a 96-channel block reads (and ignores) a few hundred bytes past the last staged chunk
-  launch_kernel(wgrad_tcgen05_kernel<TN>, grid, NTHR, (size_t)(ns * stage + (2 * ns + 1) * 8 + 64 + 4096), st, a);
+  launch_kernel(wgrad_tcgen05_kernel<TN, GK, WPROD, CTAS>, grid, WPROD + 32, (size_t)(ns * stage + (2 * ns + 1) * 8 + 64 + 4096), st, a);
   return check_launch("wgrad_tcgen05_kernel");
+}
+
+template <int TN>
+int launch(Args a, int splits, cudaStream_t st) {
+  return wgrad_group() == 2 ? launch_cfg<TN, 2, 256, 2>(a, splits, st) : launch_cfg<TN, 4, 512, 1>(a, splits, st);
 }
 
 }  // namespace wg
