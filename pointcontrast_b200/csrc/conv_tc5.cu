@@ -65,8 +65,9 @@ struct Args {
 // 2: 25 % of all warp samples of the kernel sat on these two instructions with long-scoreboard stalls; an iteration took ~1900 cycles at
 // any occupancy).  The MMA-issuing thread has no loads in flight: producers st.shared -> mbarrier.arrive (release.cta), the issuer
 // mbarrier.try_wait (acquire.cta) -> fence.proxy.async -> tcgen05.mma.  Measured (profiles/r2_results.md): forward / data-gradient kernel
-// 339 -> 318 us on the block8 shape, 12.66 -> 12.08 ms per step; the weight-gradient kernel (12 MMAs per step on the issuing thread)
-// is 5 % SLOWER with it and keeps the writer-side fence.  PCB_TC5_FENCE=producer / PCB_WG_FENCE=consumer flip the defaults.
+// 339 -> 318 us on the block8 shape, 12.66 -> 12.08 ms per step.  The weight-gradient kernel with 4 offsets per CTA (12 MMAs per step on
+// the issuing thread) was 5 % slower with it; in its two-CTAs-per-SM form (2 offsets per CTA) it gains 9-12 % (458 -> 415 us on the block8
+// shape, 435 -> 382 us at 128 channels).  PCB_TC5_FENCE=producer / PCB_WG_FENCE=producer restore the writer-side fence.
 inline int consumer_fence() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("PCB_TC5_FENCE"); v = (e && !strcmp(e, "producer")) ? 0 : 1; }
@@ -74,7 +75,7 @@ inline int consumer_fence() {
 }
 inline int wgrad_consumer_fence() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("PCB_WG_FENCE"); v = (e && !strcmp(e, "consumer")) ? 1 : 0; }
+  if (v < 0) { const char* e = getenv("PCB_WG_FENCE"); v = (e && !strcmp(e, "producer")) ? 0 : 1; }
   return v;
 }
 
@@ -302,16 +303,10 @@ struct DSmem {
 // <DNS, DPROD, CTAS>: <6, 512, 1> = one CTA per SM with a 6-slot ring; <3, 256, 2> = two CTAs per SM with 3 slots each --
 // every hand-off (mbarrier wake-up ~260 cycles, smem store -> fence -> arrive, MMA issue) is a serial chain inside a CTA,
 // so two co-resident CTAs hide each other's chains.
-// BW = 1: the weight tiles are launched by their own warp (one thread) as soon as a slot is free, instead of by producer thread 0 in
-// between its own gather loads and stores.
-// CPA = 1: the gathered rows go global -> shared by cp.async (LDGSTS, zero-fill for absent neighbours) and every producer thread hands its
-// copies to the stage's "full" barrier with cp.async.mbarrier.arrive.noinc: no data registers, no st.shared, no wait inside the producer
-// -- ~40 instructions per thread and stage instead of ~180 (the register-staged loop is bound by its own instruction stream: with the
-// loads, the weight tiles or the MMAs switched off the kernel still takes 260-280 of its 320 us, profiles/r2_results.md).
-template <int BN, int DNS, int DPROD, int CTAS, int PF = 3, int BW = 0, int CPA = 0>
-__global__ void __launch_bounds__(DPROD + 32 + 32 * BW, CTAS) conv_tcgen05_split_kernel(const Args p) {
+template <int BN, int DNS, int DPROD, int CTAS, int PF = 3>
+__global__ void __launch_bounds__(DPROD + 32, CTAS) conv_tcgen05_split_kernel(const Args p) {
   using S = DSmem<BN, DNS>;
-  constexpr int DTHR = DPROD + 32 + 32 * BW;
+  constexpr int DTHR = DPROD + 32;
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t row0 = (int64_t)blockIdx.x * BM;
@@ -325,7 +320,7 @@ __global__ void __launch_bounds__(DPROD + 32 + 32 * BW, CTAS) conv_tcgen05_split
   const uint32_t full_bar = smem_base + S::BAR_OFF, empty_bar = full_bar + 8 * DNS, done_bar = empty_bar + 8 * DNS;
 
   if (tid == 0) {
-    for (int i = 0; i < DNS; ++i) { mbar_init(full_bar + 8 * i, (CPA ? DPROD : DPROD / 32) + 1); mbar_init(empty_bar + 8 * i, 1); }
+    for (int i = 0; i < DNS; ++i) { mbar_init(full_bar + 8 * i, DPROD / 32 + 1); mbar_init(empty_bar + 8 * i, 1); }
     mbar_init(done_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
@@ -383,44 +378,7 @@ __global__ void __launch_bounds__(DPROD + 32 + 32 * BW, CTAS) conv_tcgen05_split
   const int n_it = (p.debug & 16) ? 0 : it1 - it0;
   const uint32_t IDESC = (1u << 4) | p.fmt_bits | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
-  if (CPA && warp < DPROD / 32) {
-    // ===== producers, cp.async flavour: thread t owns the 16-byte chunk t&3 of rows t>>2 and 64 + (t>>2), hi and lo plane
-    static_assert(!CPA || BW, "the cp.async producers leave the weight tiles to the loader warp");
-    constexpr int RP = BM * 4 / DPROD;
-    const int ar = tid >> 2, ak8 = tid & 3;
-    uint32_t a_dst[RP];
-#pragma unroll
-    for (int j = 0; j < RP; ++j) { const int r = ar + j * (DPROD / 4); a_dst[j] = ak8 * A_LBO + (r >> 3) * A_SBO + (r & 7) * 16; }
-    int kq = it0 / nkc, kc = it0 - kq * nkc;
-    const __nv_bfloat16* src_hi[RP]; const __nv_bfloat16* src_lo[RP]; uint32_t nbytes[RP];
-    auto set_k = [&]() {
-      const int kb = s_klist[kq] * BM;
-#pragma unroll
-      for (int j = 0; j < RP; ++j) {
-        const int idx = s_idx[kb + ar + j * (DPROD / 4)];
-        nbytes[j] = idx >= 0 ? 16u : 0u;                                 // absent neighbour: zero-fill, nothing read
-        const int64_t off = (int64_t)(idx >= 0 ? idx : 0) * p.lds + ak8 * 8;
-        src_hi[j] = p.Xhi + off; src_lo[j] = p.Xlo + off;
-      }
-    };
-    if (n_it > 0) set_k();
-    int is = 0, iround = 0;
-    for (int i = 0; i < n_it; ++i) {
-      if (iround >= 1) {
-        if (lane == 0) mbar_wait(empty_bar + 8 * is, (iround - 1) & 1);
-        __syncwarp();
-      }
-      const uint32_t sb = smem_base + is * S::STAGE;
-#pragma unroll
-      for (int j = 0; j < RP; ++j) {
-        cp_async16_zfill(sb + a_dst[j], src_hi[j] + kc * BK, (p.debug & 1) ? 0u : nbytes[j]);
-        cp_async16_zfill(sb + A_PLANE + a_dst[j], src_lo[j] + kc * BK, (p.debug & 1) ? 0u : nbytes[j]);
-      }
-      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(full_bar + 8 * is) : "memory");
-      if (++is == DNS) { is = 0; ++iround; }
-      if (++kc == nkc) { kc = 0; ++kq; if (i + 1 < n_it) set_k(); }
-    }
-  } else if (warp < DPROD / 32) {
+  if (warp < DPROD / 32) {
     // ===== producers.  Thread t always owns the same two 16-byte chunks of the A tile (row t>>2, chunk t&3, hi + lo
     // plane): 128-bit global loads into registers PF stages ahead, 128-bit shared stores when the slot is free.
     // The weight tile of a stage is ONE TMA bulk copy (the weights are pre-tiled as shared-memory images), issued by
@@ -472,7 +430,7 @@ __global__ void __launch_bounds__(DPROD + 32 + 32 * BW, CTAS) conv_tcgen05_split
         __syncwarp();
       }
       const uint32_t sb = smem_base + is * S::STAGE;
-      if (!BW && tid == 0) {
+      if (tid == 0) {
         const int k = s_klist[s_kq];
         mbar_arrive_expect_tx(full_bar + 8 * is, (p.debug & 2) ? 0u : BLOB);
         if (!(p.debug & 2))
@@ -489,37 +447,20 @@ __global__ void __launch_bounds__(DPROD + 32 + 32 * BW, CTAS) conv_tcgen05_split
       if (++is == DNS) { is = 0; ++iround; }
       if (++s_kc == nkc) { s_kc = 0; ++s_kq; }
     };
-    Regs v0, v1, v2, v3;
+    static_assert(PF == 3, "three register stages");
+    Regs v0, v1, v2;
     load(v0); load(v1); load(v2);
-    if (PF == 4) load(v3);
     for (int i = 0; i < n_it; i += PF) {
       store(v0); load(v0);
       if (i + 1 < n_it) { store(v1); load(v1); }
       if (i + 2 < n_it) { store(v2); load(v2); }
-      if (PF == 4 && i + 3 < n_it) { store(v3); load(v3); }
-    }
-  } else if (BW && warp == DPROD / 32 + 1) {
-    // ===== weight-tile loader: one TMA bulk copy per stage, as soon as the slot's previous MMAs have committed =====
-    if (lane == 0) {
-      constexpr uint32_t BLOB = 2 * S::B_PLANE;
-      const int nblk = p.Cout / BN;
-      int s = 0, round = 0, kq = it0 / nkc, kc = it0 - kq * nkc;
-      for (int i = 0; i < n_it; ++i) {
-        if (round >= 1) mbar_wait(empty_bar + 8 * s, (round - 1) & 1);
-        const int k = s_klist[kq];
-        mbar_arrive_expect_tx(full_bar + 8 * s, (p.debug & 2) ? 0u : BLOB);
-        if (!(p.debug & 2))
-          tma_bulk_load(smem_base + s * S::STAGE + 2 * A_PLANE, p.wt + ((int64_t)(k * nkc + kc) * nblk + blockIdx.y) * BLOB, BLOB, full_bar + 8 * s);
-        if (++s == DNS) { s = 0; ++round; }
-        if (++kc == nkc) { kc = 0; ++kq; }
-      }
     }
   } else if (warp == DPROD / 32 && lane == 0) {
     // ===== MMA issuer =====
     int s = 0, par = 0;
     for (int i = 0; i < n_it; ++i) {
       mbar_wait(full_bar + 8 * s, par);
-      if (p.consumer_fence || CPA) fence_proxy_async();
+      if (p.consumer_fence) fence_proxy_async();
       tc_fence_after();
       const uint32_t a_hi = smem_base + s * S::STAGE, a_lo = a_hi + A_PLANE;
       const uint32_t b_hi = a_hi + 2 * A_PLANE, b_lo = b_hi + S::B_PLANE;
@@ -584,257 +525,25 @@ __global__ void __launch_bounds__(DPROD + 32 + 32 * BW, CTAS) conv_tcgen05_split
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_acc), "r"(S::TMEM_COLS));
 }
 
-// ------------------------------------------------------------------------------------------------ 256-row tiles (direct mode, large levels)
-// Same pipeline with TWO 128-row sub-tiles per CTA sharing every weight tile: one TMA weight copy and one full/empty barrier round trip
-// now feed 12 MMAs (two M128 accumulators in TMEM) instead of 6 -- the weight tiles are more than half of the L2 -> SM traffic of a
-// 128-row tile (81 stages x 12.4 KB = 1.0 MB against 0.74 MB of gathered rows at 96 channels).  16 producer warps (thread = one
-// 16-byte chunk of a row in each sub-tile), one CTA per SM, DNS-slot ring; no offset-split mode (large levels only).
-template <int BN, int DNS>
-struct WSmem {
-  static constexpr int B_LBO = (BN / 8) * 128 + 16;
-  static constexpr int B_PLANE = (BK / 8) * B_LBO;
-  static constexpr int STAGE = 4 * A_PLANE + 2 * B_PLANE;
-  static constexpr int IDX_OFF = DNS * STAGE;
-  static constexpr int META_OFF = IDX_OFF + PCB_MAX_KERNEL_VOLUME * 2 * BM * 4;
-  static constexpr int BAR_OFF = META_OFF + 72 * 4;
-  static constexpr int TOTAL = BAR_OFF + (2 * DNS + 1) * 8 + 16;
-  static constexpr int ACC_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : 128);
-  static constexpr int TMEM_COLS = 2 * ACC_COLS;
-};
-
-template <int BN, int DNS>
-__global__ void __launch_bounds__(544, 1) conv_tcgen05_wide_kernel(const Args p) {
-  using S = WSmem<BN, DNS>;
-  constexpr int DPROD = 512, DTHR = 544, BMT = 2 * BM;
-  extern __shared__ __align__(128) unsigned char smem[];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t row0 = (int64_t)blockIdx.x * BMT;
-  const int n0 = blockIdx.y * BN;
-  int* s_idx = reinterpret_cast<int*>(smem + S::IDX_OFF);
-  int* s_flag = reinterpret_cast<int*>(smem + S::META_OFF);
-  int* s_klist = s_flag + 32;
-  int* s_nk = s_klist + 32;
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_nk + 1);
-  const uint32_t smem_base = smem_u32(smem);
-  const uint32_t full_bar = smem_base + S::BAR_OFF, empty_bar = full_bar + 8 * DNS, done_bar = empty_bar + 8 * DNS;
-
-  if (tid == 0) {
-    for (int i = 0; i < DNS; ++i) { mbar_init(full_bar + 8 * i, DPROD / 32 + 1); mbar_init(empty_bar + 8 * i, 1); }
-    mbar_init(done_bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-  }
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(s_tmem)), "r"(S::TMEM_COLS));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
-  }
-  pdl_wait(); pdl_trigger();
-  for (int e = tid; e < p.K * BMT; e += DTHR) {
-    const int k = e / BMT, r = e - k * BMT;
-    const int64_t row = row0 + r;
-    s_idx[e] = row < p.n_out ? p.tbl[(int64_t)p.kmap[k] * p.tbl_stride + row] : -1;
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_acc = *s_tmem;
-  for (int k = warp; k < p.K; k += DTHR / 32) {
-    unsigned any = 0;
-#pragma unroll
-    for (int s = 0; s < 8; ++s) any |= __ballot_sync(0xffffffffu, s_idx[k * BMT + s * 32 + lane] >= 0);
-    if (lane == 0) s_flag[k] = any ? 1 : 0;
-  }
-  __syncthreads();
-  if (tid == 0) {
-    int nk = 0;
-    for (int k = 0; k < p.K; ++k) if (s_flag[k]) s_klist[nk++] = k;
-    *s_nk = nk;
-  }
-  __syncthreads();
-  const int nk = *s_nk;
-  const int nkc = p.Cin / BK;
-  const int n_it = nk * nkc;
-  const uint32_t IDESC = (1u << 4) | p.fmt_bits | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-
-  if (warp < DPROD / 32) {
-    // thread t owns chunk (t & 3) of row (t >> 2) in BOTH sub-tiles (rows r and r + 128 of the tile); loads run PF stages ahead
-    constexpr int PF = 2;
-    constexpr uint32_t BLOB = 2 * S::B_PLANE;
-    const int ar = tid >> 2, ak8 = tid & 3;
-    const uint32_t a_dst = ak8 * A_LBO + (ar >> 3) * A_SBO + (ar & 7) * 16;
-    const int nblk = p.Cout / BN;
-    int l_kq = 0, l_kc = 0, loaded = 0;
-    const __nv_bfloat16* l_hi[2]; const __nv_bfloat16* l_lo[2]; bool l_on[2];
-    auto set_k = [&]() {
-      const int kb = s_klist[l_kq] * BMT;
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int idx = s_idx[kb + ar + j * BM];
-        l_on[j] = idx >= 0;
-        const int64_t off = (int64_t)(l_on[j] ? idx : 0) * p.lds + ak8 * 8;
-        l_hi[j] = p.Xhi + off; l_lo[j] = p.Xlo + off;
-      }
-    };
-#pragma unroll
-    for (int j = 0; j < 2; ++j) { l_hi[j] = p.Xhi; l_lo[j] = p.Xlo; l_on[j] = false; }
-    if (n_it > 0) set_k();
-    struct Regs { uint4 h[2]; uint4 l[2]; };
-    auto load = [&](Regs& v) {
-      if (loaded < n_it) {
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          if (l_on[j]) {
-            v.h[j] = __ldg(reinterpret_cast<const uint4*>(l_hi[j] + l_kc * BK));
-            v.l[j] = __ldg(reinterpret_cast<const uint4*>(l_lo[j] + l_kc * BK));
-          } else {
-            v.h[j] = make_uint4(0, 0, 0, 0); v.l[j] = make_uint4(0, 0, 0, 0);
-          }
-        }
-        ++loaded;
-        if (++l_kc == nkc) { l_kc = 0; ++l_kq; if (loaded < n_it) set_k(); }
-      }
-    };
-    int is = 0, iround = 0, s_kq = 0, s_kc = 0;
-    auto store = [&](const Regs& v) {
-      if (iround >= 1) {
-        if (lane == 0) mbar_wait(empty_bar + 8 * is, (iround - 1) & 1);
-        __syncwarp();
-      }
-      const uint32_t sb = smem_base + is * S::STAGE;
-      if (tid == 0) {
-        const int k = s_klist[s_kq];
-        mbar_arrive_expect_tx(full_bar + 8 * is, BLOB);
-        tma_bulk_load(sb + 4 * A_PLANE, p.wt + ((int64_t)(k * nkc + s_kc) * nblk + blockIdx.y) * BLOB, BLOB, full_bar + 8 * is);
-      }
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const uint32_t d = sb + j * 2 * A_PLANE + a_dst;
-        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};\n" ::"r"(d), "r"(v.h[j].x), "r"(v.h[j].y), "r"(v.h[j].z), "r"(v.h[j].w) : "memory");
-        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};\n" ::"r"(d + A_PLANE), "r"(v.l[j].x), "r"(v.l[j].y), "r"(v.l[j].z), "r"(v.l[j].w) : "memory");
-      }
-      if (!p.consumer_fence) fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(full_bar + 8 * is);
-      if (++is == DNS) { is = 0; ++iround; }
-      if (++s_kc == nkc) { s_kc = 0; ++s_kq; }
-    };
-    Regs v0, v1;
-    load(v0); load(v1);
-    for (int i = 0; i < n_it; i += PF) {
-      store(v0); load(v0);
-      if (i + 1 < n_it) { store(v1); load(v1); }
-    }
-  } else if (lane == 0) {
-    int s = 0, par = 0;
-    for (int i = 0; i < n_it; ++i) {
-      mbar_wait(full_bar + 8 * s, par);
-      if (p.consumer_fence) fence_proxy_async();
-      tc_fence_after();
-      const uint32_t sb = smem_base + s * S::STAGE;
-      const uint32_t b_hi = sb + 4 * A_PLANE, b_lo = b_hi + S::B_PLANE;
-#pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        const uint32_t a_hi = sb + t * 2 * A_PLANE, a_lo = a_hi + A_PLANE;
-        const uint32_t acc = tmem_acc + t * S::ACC_COLS;
-#pragma unroll
-        for (int j = 0; j < BK / 16; ++j) {
-          const uint64_t dah = make_desc(a_hi + j * 2 * A_LBO, A_LBO, A_SBO), dal = make_desc(a_lo + j * 2 * A_LBO, A_LBO, A_SBO);
-          const uint64_t dbh = make_desc(b_hi + j * 2 * S::B_LBO, S::B_LBO, 128), dbl = make_desc(b_lo + j * 2 * S::B_LBO, S::B_LBO, 128);
-          tc_mma(acc, dal, dbh, IDESC, (i > 0 || j > 0) ? 1u : 0u);
-          tc_mma(acc, dah, dbl, IDESC, 1u);
-          tc_mma(acc, dah, dbh, IDESC, 1u);
-        }
-      }
-      tc_commit(empty_bar + 8 * s);
-      if (i == n_it - 1) tc_commit(done_bar);
-      if (++s == DNS) { s = 0; par ^= 1; }
-    }
-  }
-  if (n_it > 0) {
-    mbar_wait(done_bar, 0);
-    tc_fence_after();
-  }
-  if (warp < 16) {       // warp w: sub-tile w / 8, TMEM lane quarter w & 3, column half (w >> 2) & 1
-    const int t = warp >> 3, q = warp & 3, half = (warp >> 2) & 1;
-    const int64_t row = row0 + t * BM + q * 32 + lane;
-    constexpr int HALF = BN / 2;
-#pragma unroll
-    for (int c0 = 0; c0 < HALF; c0 += 16) {
-      const int col = half * HALF + c0;
-      uint32_t r[16];
-      if (n_it > 0) {
-        tc_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * S::ACC_COLS + col), r);
-        tc_ld_wait();
-      } else {
-#pragma unroll
-        for (int e = 0; e < 16; ++e) r[e] = 0u;
-      }
-      if (p.out_scale != 1.0f) {
-#pragma unroll
-        for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) * p.out_scale);
-      }
-      if (row < p.n_out) {
-        float* dst = p.Y + row * p.ldy + n0 + col;
-#pragma unroll
-        for (int e = 0; e < 16; e += 4) {
-          float4 o = make_float4(__uint_as_float(r[e]), __uint_as_float(r[e + 1]), __uint_as_float(r[e + 2]), __uint_as_float(r[e + 3]));
-          if (p.bias) { o.x += p.bias[n0 + col + e]; o.y += p.bias[n0 + col + e + 1]; o.z += p.bias[n0 + col + e + 2]; o.w += p.bias[n0 + col + e + 3]; }
-          if (p.accumulate) {
-            const float4 old = *reinterpret_cast<const float4*>(dst + e);
-            o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-          }
-          *reinterpret_cast<float4*>(dst + e) = o;
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_acc), "r"(S::TMEM_COLS));
-}
-
-template <int BN, int DNS>
-int launch_wide(const Args& a, cudaStream_t st) {
-  using S = WSmem<BN, DNS>;
-  static bool attr_set[64] = {};
-  const int dev_ = current_device();
-  if (!attr_set[dev_]) {
-    PCB_CUDA(cudaFuncSetAttribute(conv_tcgen05_wide_kernel<BN, DNS>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-    attr_set[dev_] = true;
-  }
-  dim3 grid((unsigned)((a.n_out + 2 * BM - 1) / (2 * BM)), a.Cout / BN, 1);
-  launch_kernel(conv_tcgen05_wide_kernel<BN, DNS>, grid, 544, S::TOTAL, st, a);
-  return check_launch("conv_tcgen05_wide_kernel");
-}
-
-template <int BN, int DNS, int DPROD, int CTAS, int PF = 3, int BW = 0, int CPA = 0>
+template <int BN, int DNS, int DPROD, int CTAS, int PF = 3>
 int launch_split_cfg(const Args& a, int nsplit, cudaStream_t st) {
   using S = DSmem<BN, DNS>;
   static bool attr_set[64] = {};          // per device: the opt-in is a per-device function attribute
   const int dev_ = current_device();
   if (!attr_set[dev_]) {
-    PCB_CUDA(cudaFuncSetAttribute(conv_tcgen05_split_kernel<BN, DNS, DPROD, CTAS, PF, BW, CPA>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    PCB_CUDA(cudaFuncSetAttribute(conv_tcgen05_split_kernel<BN, DNS, DPROD, CTAS, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     attr_set[dev_] = true;
   }
   dim3 grid((unsigned)((a.n_out + BM - 1) / BM), a.Cout / BN, nsplit);
-  launch_kernel(conv_tcgen05_split_kernel<BN, DNS, DPROD, CTAS, PF, BW, CPA>, grid, DPROD + 32 + 32 * BW, S::TOTAL, st, a);
+  launch_kernel(conv_tcgen05_split_kernel<BN, DNS, DPROD, CTAS, PF>, grid, DPROD + 32, S::TOTAL, st, a);
   return check_launch("conv_tcgen05_split_kernel");
 }
 
+// One configuration is built: 3-slot ring, 8 producer warps, two CTAs per SM, gathers three stages ahead.  Measured and dropped in round 2
+// (profiles/r2_results.md): one CTA per SM with a 6-slot ring and 16 producer warps, three CTAs per SM with 2-slot rings, gathers four
+// stages ahead, 256-row tiles sharing each weight tile, a dedicated weight-loader warp, cp.async (LDGSTS) producers.
 template <int BN>
 int launch_split(const Args& a, int nsplit, cudaStream_t st) {
-  static int cfg = -1;
-  if (cfg < 0) { const char* e = getenv("PCB_TC5_CFG"); cfg = e ? atoi(e) : 2; }
-  // cfg 4: 256-row tiles (one CTA per SM, shared weight tiles) for the direct mode of levels with at least ~2 waves of such tiles
-  if (cfg == 4 && nsplit == 1 && !a.partial && (a.n_out + 255) / 256 * (a.Cout / BN) >= (int64_t)num_sms()) {
-    if (BN == 128) return launch_wide<BN, 3>(a, st);
-    return launch_wide<BN, 4>(a, st);
-  }
-  if (cfg == 1) return launch_split_cfg<BN, 6, 512, 1>(a, nsplit, st);
-  if (cfg == 3) return launch_split_cfg<BN, 2, 256, 3>(a, nsplit, st);
-  if (cfg == 5) return launch_split_cfg<BN, 3, 256, 2, 4>(a, nsplit, st);         // gathered rows loaded 4 (not 3) stages ahead
-  if (cfg == 6) return launch_split_cfg<BN, 3, 256, 2, 3, 1>(a, nsplit, st);      // weight tiles launched by their own warp
-  if (cfg == 7) return launch_split_cfg<BN, 3, 256, 2, 3, 1, 1>(a, nsplit, st);   // + cp.async producers
-  if (cfg == 8) return launch_split_cfg<BN, 2, 256, 3, 3, 1, 1>(a, nsplit, st);   // cp.async producers, three CTAs per SM with 2-slot rings
   return launch_split_cfg<BN, 3, 256, 2>(a, nsplit, st);
 }
 
@@ -886,10 +595,12 @@ int launch_conv_tcgen05(const float* X, int ldx, const uint16_t* Xhi, const uint
   }
 }
 
-// Offsets per weight-gradient CTA (PCB_WG_GROUP = 4 | 2); conv.cu sizes the row splits and the partial buffer with it.
+// Offsets per weight-gradient CTA: 2 (two CTAs per SM; default) or 4 (PCB_WG_GROUP=4: one CTA per SM, the row-aligned tile staged once
+// per 4 offsets).  Measured (profiles/r2_results.md): 464 -> 415 us on the block8 shape, 478 -> 382 us at 128 channels, 8.05 -> 7.0 ms per
+// step.  conv.cu sizes the row splits and the partial buffer with it.
 int wgrad_group() {
   static int v = 0;
-  if (!v) { const char* e = getenv("PCB_WG_GROUP"); v = (e && atoi(e) == 2) ? 2 : 4; }
+  if (!v) { const char* e = getenv("PCB_WG_GROUP"); v = (e && atoi(e) == 4) ? 4 : 2; }
   return v;
 }
 
