@@ -41,7 +41,9 @@ __device__ __forceinline__ int hash_lookup(const uint64_t* __restrict__ tk, cons
 
 // Optional per-launch timing (pcb_profile_*, unit.cu): CUDA events around every convolution / weight-gradient entry point.
 void prof_begin(cudaStream_t st);
-void prof_end(cudaStream_t st, int kind);      // kind: 0 conv forward / data gradient, 1 weight gradient
+// kind: 0 conv forward / data gradient, 1 weight gradient, 2 BatchNorm forward pass(es) of a unit, 3 BatchNorm backward of a unit,
+// 4 PointInfoNCE forward + backward, 5 SGD step, 6 weight re-tiling
+void prof_end(cudaStream_t st, int kind);
 struct ProfScope {
   cudaStream_t st; int kind;
   ProfScope(cudaStream_t s, int k) : st(s), kind(k) { prof_begin(st); }

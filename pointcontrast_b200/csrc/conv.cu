@@ -506,6 +506,7 @@ extern "C" int pcb_tile_desc_fill(pcb_tile_desc* d, const float* W, int K, int C
 
 extern "C" int pcb_weight_tile_batch(const pcb_tile_desc* descs_dev, int n, int64_t total, void* stream) {
   PCB_ARG(descs_dev && n >= 1 && n <= 256 && total >= 1);
+  ProfScope prof((cudaStream_t)stream, 6);
   launch_kernel(weight_tile_batch_kernel, (unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream, descs_dev, n, total);
   return check_launch("weight_tile_batch_kernel");
 }

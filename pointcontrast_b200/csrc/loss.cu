@@ -207,6 +207,7 @@ extern "C" int pcb_nce_forward_backward(const float* q, const float* k, int64_t 
   cudaStream_t st = (cudaStream_t)stream;
   static int force_simt = -1;
   if (force_simt < 0) { const char* e = getenv("PCB_NCE_SIMT"); force_simt = (e && atoi(e)) ? 1 : 0; }
+  ProfScope prof(st, 4);
   if (!force_simt && nce_tc_supported(n, D)) return nce_tc_forward_backward(q, k, n, D, inv_T, loss, dq, dk, ws, st);
   float* L = (float*)ws;
   float* rowloss = L + n * n;
@@ -369,6 +370,7 @@ extern "C" int pcb_sgd_step(float* p, const float* g, float* buf, int64_t n, flo
   PCB_ARG(n >= 0);
   if (n == 0) return PCB_OK;
   PCB_ARG(p && g && buf);
+  ProfScope prof((cudaStream_t)stream, 5);
   int64_t threads = (n >> 2) + (n & 3);
   launch_kernel(sgd_kernel, (unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream, p, g, buf, n, lr, momentum, weight_decay,
                 grad_scale, first, 1.0f - dampening);

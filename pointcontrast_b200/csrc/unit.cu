@@ -124,6 +124,7 @@ extern "C" int pcb_unit_forward(const pcb_unit* u, void* stream) {
     if (int e = pcb_conv_forward(u->x_p, u->x_ld, u->fwd_tbl, u->fwd_stride, u->fwd_kmap, u->K, u->n_out, u->Cin, u->Cout,
                                  nullptr, nullptr, u->W, nullptr, u->z_p, u->z_ld, nullptr, 0, 0, stream)) return e;
   }
+  ProfScope prof(st, 2);                     // BatchNorm forward: statistics (unless fused into the split reduction) + normalise / residual / ReLU / planes
   if (u->flags & PCB_UNIT_EVAL) {            // eval-mode BatchNorm (`downstream/semseg/lib/test.py:95-117`): normalise with the running statistics
     PCB_ARG(u->n0 == u->n_out && u->running_mean && u->running_var);
     if (int e = bn_eval_stats_launch(u->running_mean, u->running_var, u->Cout, u->eps, u->mean, u->invstd, st)) return e;
@@ -148,9 +149,11 @@ extern "C" int pcb_unit_backward(const pcb_unit* u, void* stream) {
   const size_t conv_bytes = conv_part_bytes(u->K, u->n_in, u->n_out, u->Cin, u->Cout);
   unsigned char* bn_ws = (unsigned char*)u->ws + conv_bytes;
   // 1. g * (out > 0) -> BatchNorm backward -> dz (split planes), residual-gradient fan-out, dgamma / dbeta accumulated
+  prof_begin(st);
   if (int e = bn_backward_impl(u->g_p, u->g_ld, u->z_p, u->z_ld, nullptr, 0, u->relu ? u->out_hi : nullptr, u->out_lds, u->n_out, u->n0, u->Cout,
                                u->mean, u->invstd, u->gamma, u->dz_p, u->dz_ld, u->dgamma, u->dbeta, 1, u->gres_p, u->gres_ld, u->gres_mode,
                                u->dz_hi, u->dz_lo, u->dz_ld, bn_ws, u->ws_bytes - conv_bytes, st)) return e;
+  prof_end(st, 3);
   // 2. weight gradient, accumulated into dW (the flat parameter-gradient buffer)
   if (tc) {
     // the activation operand as bf16 hi/lo planes (its fp16 planes serve the forward pass only): both MMA operands share one format

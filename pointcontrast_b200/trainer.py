@@ -221,9 +221,12 @@ class ContrastiveLossTrainer:
     def train(self):
         curr_iter = self.curr_iter
         it = iter(self.data_loader)
+        first = curr_iter + 1
         while curr_iter < self.config.opt.max_iter:
             curr_iter += 1
             out = self._train_iter(it, None)
+            if curr_iter == first:
+                quiesce_gc()
             batch_loss = out[0] if isinstance(out, tuple) else out
             if curr_iter % self.lr_update_freq == 0 or curr_iter == 1:
                 lr = self.scheduler.get_last_lr()
@@ -234,6 +237,15 @@ class ContrastiveLossTrainer:
             if curr_iter % self.stat_freq == 0 and self.is_master:
                 logging.info("Train iter %d, Current Loss: %.3e, LR: %s", curr_iter, batch_loss, self.scheduler.get_last_lr())
         self.curr_iter = curr_iter
+
+
+def quiesce_gc():
+    """After the first iteration everything long-lived exists (model, optimiser state, plans, ctypes signatures, arenas): move it to the
+    collector's permanent generation.  A full collection otherwise walks that whole heap every few dozen steps -- a 15-60 ms host pause
+    during which the GPU runs dry (bench.py: one 40-95 ms step per 30-50 otherwise 25 ms steps)."""
+    import gc
+    gc.collect()
+    gc.freeze()
 
 
 class HardestContrastiveLossTrainer(ContrastiveLossTrainer):
