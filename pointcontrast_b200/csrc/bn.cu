@@ -151,18 +151,13 @@ __global__ void __launch_bounds__(256) colstat_kernel(const float* __restrict__ 
   }
 }
 
-// one warp per channel: lanes stride over the row chunks, fp64 shuffle reduction (fixed order: deterministic)
-__device__ __forceinline__ void warp_sum2(const float* __restrict__ partial, int chunks, int C, int c, double& s1, double& s2) {
-  const int lane = threadIdx.x & 31;
-  s1 = 0.0; s2 = 0.0;
-#pragma unroll 4
-  for (int k = lane; k < chunks; k += 32) { s1 += partial[(int64_t)k * 2 * C + c]; s2 += partial[(int64_t)k * 2 * C + C + c]; }
-  for (int o = 16; o; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
-}
-
 // Forward statistics from the per-chunk { sum, M2 } partials (Chan et al. pairwise merge, fp64).  Segment s has chunks
 // [s ? chunks0 : 0, ...) of R rows (the last one shorter) and n0 / n - n0 rows.  The running statistics see the segments one after
 // the other, as two forward calls would (`ddp_trainer.py:290-297`: the model runs on view 0, then on view 1).
+// One warp per channel.  A lane's share of the partials (both segments) is loaded into registers with independent loads BEFORE anything
+// is reduced: the kernel is a single memory round trip plus shuffles instead of four dependent passes over the partial rows (it runs 62
+// times per step on a few hundred KB: pure latency).
+constexpr int FIN_PER_LANE = 12;          // 32 x 12 = 384 chunks per segment held in registers; beyond that a plain loop
 __global__ void bn_finalize_kernel(const float* __restrict__ partial, int chunks, int chunks0, int R, int64_t n, int64_t n0, int C, float eps,
                                    float momentum, float* __restrict__ mean, float* __restrict__ invstd, float* running_mean,
                                    float* running_var) {
@@ -171,22 +166,44 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, int chunks
   if (c >= C) return;
   const int lane = threadIdx.x & 31;
   const int nseg = n0 < n ? 2 : 1;
-  for (int seg = 0; seg < nseg; ++seg) {
+  float v1[2][FIN_PER_LANE], v2[2][FIN_PER_LANE];
+#pragma unroll
+  for (int seg = 0; seg < 2; ++seg) {
+    const float* p = partial + (seg ? (int64_t)chunks0 * 2 * C : 0);
+    const int ch = seg < nseg ? (seg ? chunks - chunks0 : chunks0) : 0;
+#pragma unroll
+    for (int j = 0; j < FIN_PER_LANE; ++j) {
+      const int k = lane + 32 * j;
+      v1[seg][j] = k < ch ? __ldg(p + (int64_t)k * 2 * C + c) : 0.f;
+      v2[seg][j] = k < ch ? __ldg(p + (int64_t)k * 2 * C + C + c) : 0.f;
+    }
+  }
+#pragma unroll
+  for (int seg = 0; seg < 2; ++seg) {
+    if (seg >= nseg) break;
     const float* p = partial + (seg ? (int64_t)chunks0 * 2 * C : 0);
     const int ch = seg ? chunks - chunks0 : chunks0;
     const int64_t rows = seg ? n - n0 : n0;
     double s1 = 0.0;
-#pragma unroll 4
-    for (int k = lane; k < ch; k += 32) s1 += p[(int64_t)k * 2 * C + c];
+#pragma unroll
+    for (int j = 0; j < FIN_PER_LANE; ++j) s1 += (double)v1[seg][j];
+    for (int k = lane + 32 * FIN_PER_LANE; k < ch; k += 32) s1 += p[(int64_t)k * 2 * C + c];
     for (int o = 16; o; o >>= 1) s1 += __shfl_xor_sync(0xffffffffu, s1, o);
     const double m = s1 / (double)rows;
+    const double invR = 1.0 / (double)R;
     double M2 = 0.0;
-#pragma unroll 4
-    for (int k = lane; k < ch; k += 32) {
-      const double mk = (double)min((int64_t)R, rows - (int64_t)k * R);
-      const double d = (double)p[(int64_t)k * 2 * C + c] / mk - m;
-      M2 += (double)p[(int64_t)k * 2 * C + C + c] + mk * d * d;
+    auto term = [&](int k, float a1, float a2) {
+      const int64_t left = rows - (int64_t)k * R;
+      const double mk = (double)(left < R ? left : R);
+      const double d = (left < R ? (double)a1 / mk : (double)a1 * invR) - m;
+      return (double)a2 + mk * d * d;
+    };
+#pragma unroll
+    for (int j = 0; j < FIN_PER_LANE; ++j) {
+      const int k = lane + 32 * j;
+      if (k < ch) M2 += term(k, v1[seg][j], v2[seg][j]);
     }
+    for (int k = lane + 32 * FIN_PER_LANE; k < ch; k += 32) M2 += term(k, p[(int64_t)k * 2 * C + c], p[(int64_t)k * 2 * C + C + c]);
     for (int o = 16; o; o >>= 1) M2 += __shfl_xor_sync(0xffffffffu, M2, o);
     if (lane == 0) {
       double var = M2 / (double)rows;
@@ -239,20 +256,39 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int ch
   pdl_wait(); pdl_trigger();
   int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (c >= C) return;
+  const int lane = threadIdx.x & 31;
+  // both segments' partials of this lane in registers first (independent loads, one round trip), then the fp64 shuffle reductions
+  float v1[2][FIN_PER_LANE], v2[2][FIN_PER_LANE];
+#pragma unroll
+  for (int seg = 0; seg < 2; ++seg) {
+    const float* p = partial + (seg ? (int64_t)chunks0 * 2 * C : 0);
+    const int ch = seg < nseg ? (seg ? chunks - chunks0 : chunks0) : 0;
+#pragma unroll
+    for (int j = 0; j < FIN_PER_LANE; ++j) {
+      const int k = lane + 32 * j;
+      v1[seg][j] = k < ch ? __ldg(p + (int64_t)k * 2 * C + c) : 0.f;
+      v2[seg][j] = k < ch ? __ldg(p + (int64_t)k * 2 * C + C + c) : 0.f;
+    }
+  }
   float tb = 0.f, tg = 0.f;
-  for (int seg = 0; seg < nseg; ++seg) {
+#pragma unroll
+  for (int seg = 0; seg < 2; ++seg) {
+    if (seg >= nseg) break;
     const float* p = partial + (seg ? (int64_t)chunks0 * 2 * C : 0);
     const int ch = seg ? chunks - chunks0 : chunks0;
-    double s1, s2;
-    warp_sum2(p, ch, C, c, s1, s2);
-    if ((threadIdx.x & 31) == 0) {
+    double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+    for (int j = 0; j < FIN_PER_LANE; ++j) { s1 += (double)v1[seg][j]; s2 += (double)v2[seg][j]; }
+    for (int k = lane + 32 * FIN_PER_LANE; k < ch; k += 32) { s1 += p[(int64_t)k * 2 * C + c]; s2 += p[(int64_t)k * 2 * C + C + c]; }
+    for (int o = 16; o; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+    if (lane == 0) {
       sums[seg * 2 * C + c] = (float)s1;
       sums[seg * 2 * C + C + c] = (float)s2;
     }
     if (seg == 0) { tb = (float)s1; tg = (float)s2; }
     else { tb = (float)((double)tb + s1); tg = (float)((double)tg + s2); }
   }
-  if ((threadIdx.x & 31) != 0) return;
+  if (lane != 0) return;
   if (accumulate) { dbeta[c] += tb; dgamma[c] += tg; }
   else { dbeta[c] = tb; dgamma[c] = tg; }
 }

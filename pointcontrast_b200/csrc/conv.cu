@@ -445,53 +445,85 @@ __global__ void weight_tile_kernel(const float* __restrict__ W, int K, int Cin, 
 
 // All convolutions of a network in ONE launch (the fused executor re-tiles every kernel after each SGD step: 62 small launches
 // otherwise).  descs: DEVICE array; `start` = prefix sum of K*Cin*Cout; a thread finds its convolution by binary search.
+// A thread produces one 16-byte chunk (8 contraction-direction elements of one tile row) of BOTH planes for each role, so the tile
+// images are written with 128-bit stores that line up across a warp (the element-per-thread version, `weight_tile_kernel`, scatters
+// 2-byte stores: 0.53 ms per step for the 38 M parameters).  Forward roles: 8 consecutive input channels of one output channel
+// (threads along Cout: 8 coalesced 4-byte loads); data-gradient roles: 8 consecutive output channels of one input channel (threads along
+// Cin: two 128-bit loads).
 namespace {
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b, float& ra, float& rb) {
+  const __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
+  ra = a - __bfloat162float(ha); rb = b - __bfloat162float(hb);
+  return (uint32_t)__bfloat16_as_ushort(ha) | ((uint32_t)__bfloat16_as_ushort(hb) << 16);
+}
+__device__ __forceinline__ uint32_t pack_f16(float a, float b, float& ra, float& rb) {
+  const __half ha = __float2half_rn(a), hb = __float2half_rn(b);
+  ra = a - __half2float(ha); rb = b - __half2float(hb);
+  return (uint32_t)__half_as_ushort(ha) | ((uint32_t)__half_as_ushort(hb) << 16);
+}
+template <bool F16>
+__device__ __forceinline__ void split8(const float (&w)[8], uint4& hi, uint4& lo) {
+  float v[8], r[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = F16 ? fminf(fmaxf(w[j] * 1024.0f, -65000.f), 65000.f) : w[j];
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float d0, d1;
+    h[j] = F16 ? pack_f16(v[2 * j], v[2 * j + 1], r[2 * j], r[2 * j + 1]) : pack_bf16(v[2 * j], v[2 * j + 1], r[2 * j], r[2 * j + 1]);
+    l[j] = F16 ? pack_f16(r[2 * j], r[2 * j + 1], d0, d1) : pack_bf16(r[2 * j], r[2 * j + 1], d0, d1);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]); lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
 __global__ void weight_tile_batch_kernel(const pcb_tile_desc* __restrict__ descs, int n, int64_t total) {
   pdl_wait(); pdl_trigger();
   __shared__ int64_t s_start[257];
   for (int i = threadIdx.x; i <= n; i += blockDim.x) s_start[i] = i < n ? descs[i].start : total;
   __syncthreads();
-  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (e >= total) return;
-  int lo = 0, hi = n - 1;
-  while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (s_start[mid] <= e) lo = mid; else hi = mid - 1; }
-  const pcb_tile_desc d = descs[lo];
-  const int64_t le = e - d.start;
-  const int K = d.K, Cin = d.Cin, Cout = d.Cout;
-  (void)K;
-  const float w = d.W[le];
-  const __nv_bfloat16 h = __float2bfloat16_rn(w);
-  const __nv_bfloat16 l = __float2bfloat16_rn(w - __bfloat162float(h));
-  const int co = (int)(le % Cout);
-  const int64_t r = le / Cout;
-  const int ci = (int)(r % Cin);
-  const int k = (int)(r / Cin);
-  const int bn_f = d.bn_f, bn_d = d.bn_d;
-  unsigned char* fwd = (unsigned char*)d.fwd;
-  unsigned char* dg = (unsigned char*)d.dgrad;
-  {
-    const int64_t plane = tile_plane_bytes(bn_f);
-    const int64_t blob = ((int64_t)(k * (Cin / 32) + ci / 32) * (Cout / bn_f) + co / bn_f) * 2 * plane;
-    const int nn = co % bn_f, c = ci % 32;
-    const int64_t off = blob + (c / 8) * (plane / 4) + (nn / 8) * 128 + (nn % 8) * 16 + (c % 8) * 2;
-    if (d.flags & PCB_PLANES_B_FP16) {
-      const float ws = fminf(fmaxf(w * 1024.0f, -65000.f), 65000.f);
-      const __half fh = __float2half_rn(ws);
-      const __half fl = __float2half_rn(ws - __half2float(fh));
-      *reinterpret_cast<__half*>(fwd + off) = fh;
-      *reinterpret_cast<__half*>(fwd + off + plane) = fl;
-    } else {
-      *reinterpret_cast<__nv_bfloat16*>(fwd + off) = h;
-      *reinterpret_cast<__nv_bfloat16*>(fwd + off + plane) = l;
-    }
+  const int64_t t8 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;      // chunk index; every start is a multiple of 8 (channels % 32 == 0)
+  if (t8 * 8 >= total) return;
+  int lo_ = 0, hi_ = n - 1;
+  while (lo_ < hi_) { const int mid = (lo_ + hi_ + 1) >> 1; if (s_start[mid] <= t8 * 8) lo_ = mid; else hi_ = mid - 1; }
+  const pcb_tile_desc d = descs[lo_];
+  const int64_t t = t8 - d.start / 8;
+  const int Cin = d.Cin, Cout = d.Cout;
+  const float* __restrict__ W = d.W;
+  {   // forward roles: N = Cout, contraction = Cin; chunk = input channels ci0 .. ci0 + 7 of output channel co
+    const int co = (int)(t % Cout);
+    const int64_t g = t / Cout;
+    const int cig = (int)(g % (Cin / 8)), k = (int)(g / (Cin / 8));
+    const int ci0 = cig * 8;
+    float w[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) w[j] = __ldg(W + ((int64_t)k * Cin + ci0 + j) * Cout + co);
+    const int bn = d.bn_f;
+    const int64_t plane = tile_plane_bytes(bn);
+    const int64_t blob = ((int64_t)(k * (Cin / 32) + ci0 / 32) * (Cout / bn) + co / bn) * 2 * plane;
+    const int nn = co % bn, c = ci0 % 32;
+    unsigned char* dst = (unsigned char*)d.fwd + blob + (c / 8) * (plane / 4) + (nn / 8) * 128 + (nn % 8) * 16;
+    uint4 h, l;
+    if (d.flags & PCB_PLANES_B_FP16) split8<true>(w, h, l); else split8<false>(w, h, l);
+    *reinterpret_cast<uint4*>(dst) = h;
+    *reinterpret_cast<uint4*>(dst + plane) = l;
   }
-  {
-    const int64_t plane = tile_plane_bytes(bn_d);
-    const int64_t blob = ((int64_t)(k * (Cout / 32) + co / 32) * (Cin / bn_d) + ci / bn_d) * 2 * plane;
-    const int nn = ci % bn_d, c = co % 32;
-    const int64_t off = blob + (c / 8) * (plane / 4) + (nn / 8) * 128 + (nn % 8) * 16 + (c % 8) * 2;
-    *reinterpret_cast<__nv_bfloat16*>(dg + off) = h;
-    *reinterpret_cast<__nv_bfloat16*>(dg + off + plane) = l;
+  {   // data-gradient roles: N = Cin, contraction = Cout; chunk = output channels co0 .. co0 + 7 of input channel ci
+    const int ci = (int)(t % Cin);
+    const int64_t g = t / Cin;
+    const int cog = (int)(g % (Cout / 8)), k = (int)(g / (Cout / 8));
+    const int co0 = cog * 8;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(W + ((int64_t)k * Cin + ci) * Cout + co0));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(W + ((int64_t)k * Cin + ci) * Cout + co0) + 1);
+    const float w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    const int bn = d.bn_d;
+    const int64_t plane = tile_plane_bytes(bn);
+    const int64_t blob = ((int64_t)(k * (Cout / 32) + co0 / 32) * (Cin / bn) + ci / bn) * 2 * plane;
+    const int nn = ci % bn, c = co0 % 32;
+    unsigned char* dst = (unsigned char*)d.dgrad + blob + (c / 8) * (plane / 4) + (nn / 8) * 128 + (nn % 8) * 16;
+    uint4 h, l;
+    split8<false>(w, h, l);
+    *reinterpret_cast<uint4*>(dst) = h;
+    *reinterpret_cast<uint4*>(dst + plane) = l;
   }
 }
 }  // namespace
@@ -507,7 +539,8 @@ extern "C" int pcb_tile_desc_fill(pcb_tile_desc* d, const float* W, int K, int C
 extern "C" int pcb_weight_tile_batch(const pcb_tile_desc* descs_dev, int n, int64_t total, void* stream) {
   PCB_ARG(descs_dev && n >= 1 && n <= 256 && total >= 1);
   ProfScope prof((cudaStream_t)stream, 6);
-  launch_kernel(weight_tile_batch_kernel, (unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream, descs_dev, n, total);
+  PCB_ARG(total % 8 == 0);
+  launch_kernel(weight_tile_batch_kernel, (unsigned)((total / 8 + 255) / 256), 256, 0, (cudaStream_t)stream, descs_dev, n, total);
   return check_launch("weight_tile_batch_kernel");
 }
 

@@ -471,3 +471,34 @@ def test_global_pooling_broadcast_and_instance_norm():
         xi = x[b == i]
         refn[b == i] = (xi - xi.mean(0)) / torch.sqrt(xi.var(0, unbiased=False) + 1e-6)
     assert max_rel_err(y, refn) < 1e-4
+
+
+@pytest.mark.parametrize("fp16", [False, True])
+def test_batched_weight_tiling_equals_per_convolution_tiling(fp16):
+    """`pcb_weight_tile_batch` (all convolutions of a network in one launch, 16-byte chunk per thread) writes bit for bit the tile images
+    of `pcb_weight_tile` (one convolution, element per thread): forward roles (fp16 of W * 2^10 or bf16) and data-gradient roles (bf16)."""
+    import ctypes
+    from pointcontrast_b200._lib import PcbTileDesc
+    g = torch.Generator().manual_seed(3)
+    shapes = [(27, 96, 96), (8, 32, 64), (1, 128, 256), (27, 384, 256), (27, 32, 32)]
+    Ws = [(torch.randn(K, ci, co, generator=g) * (0.3 if i else 1e-3)).cuda() for i, (K, ci, co) in enumerate(shapes)]
+    flag = 16 if fp16 else 0
+    ref = []
+    for W, (K, ci, co) in zip(Ws, shapes):
+        f = torch.zeros(lib.pcb_weight_tile_bytes(K, ci, co, 0), dtype=torch.uint8, device="cuda")
+        d = torch.zeros(lib.pcb_weight_tile_bytes(K, ci, co, 1), dtype=torch.uint8, device="cuda")
+        check(lib.pcb_weight_tile(ptr(W), K, ci, co, ptr(f), ptr(d), flag, stream()))
+        ref.append((f, d))
+    descs = (PcbTileDesc * len(shapes))()
+    outs, start = [], 0
+    for i, (W, (K, ci, co)) in enumerate(zip(Ws, shapes)):
+        f = torch.zeros_like(ref[i][0]); d = torch.zeros_like(ref[i][1])
+        check(lib.pcb_tile_desc_fill(ctypes.byref(descs[i]), W.data_ptr(), K, ci, co, f.data_ptr(), d.data_ptr(), flag, start))
+        start += K * ci * co
+        outs.append((f, d))
+    dev = torch.frombuffer(bytearray(bytes(descs)), dtype=torch.uint8).cuda()
+    check(lib.pcb_weight_tile_batch(dev.data_ptr(), len(shapes), start, stream()))
+    torch.cuda.synchronize()
+    for (f, d), (rf, rd), sh in zip(outs, ref, shapes):
+        assert torch.equal(f, rf), sh
+        assert torch.equal(d, rd), sh
