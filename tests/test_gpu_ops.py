@@ -478,7 +478,7 @@ def test_batched_weight_tiling_equals_per_convolution_tiling(fp16):
     """`pcb_weight_tile_batch` (all convolutions of a network in one launch, 16-byte chunk per thread) writes bit for bit the tile images
     of `pcb_weight_tile` (one convolution, element per thread): forward roles (fp16 of W * 2^10 or bf16) and data-gradient roles (bf16)."""
     import ctypes
-    from pointcontrast_b200._lib import PcbTileDesc
+    from pointcontrast_b200._lib import PcbTileDesc, check, lib, ptr, stream
     g = torch.Generator().manual_seed(3)
     shapes = [(27, 96, 96), (8, 32, 64), (1, 128, 256), (27, 384, 256), (27, 32, 32)]
     Ws = [(torch.randn(K, ci, co, generator=g) * (0.3 if i else 1e-3)).cuda() for i, (K, ci, co) in enumerate(shapes)]
@@ -500,5 +500,5 @@ def test_batched_weight_tiling_equals_per_convolution_tiling(fp16):
     check(lib.pcb_weight_tile_batch(dev.data_ptr(), len(shapes), start, stream()))
     torch.cuda.synchronize()
     for (f, d), (rf, rd), sh in zip(outs, ref, shapes):
-        assert torch.equal(f, rf), sh
-        assert torch.equal(d, rd), sh
+        assert torch.equal(f, rf), (sh, "forward tiles", int((f != rf).sum()), f.numel(), (f != rf).nonzero()[:8].flatten().tolist())
+        assert torch.equal(d, rd), (sh, "data-gradient tiles", int((d != rd).sum()), d.numel(), (d != rd).nonzero()[:8].flatten().tolist())
