@@ -34,7 +34,9 @@ PAIR = os.environ.get("PCB_PAIR", "1") == "1"
 VIEW1_BATCH_OFFSET = 1 << 14      # batch indices of view 1 in a stacked tensor (packed keys hold batch < 65535)
 # Coordinate-manager build on a side stream (0: on the current stream, as the modular `SparseTensor(...)` path always does).
 SIDE_STREAM = os.environ.get("PCB_COORDS_STREAM", "1") == "1"
-SIDE_PRIORITY = int(os.environ.get("PCB_COORDS_PRIORITY", "-1"))      # CUDA stream priority of that stream (-1 = high, 0 = default)
+# CUDA stream priority of that stream (0 = default, -1 = high).  Same-box A/B (profiles/r2_results.md): 158.9 vs 159.8 pairs/s end to end,
+# 165.7 vs 166.0 device-resident: no effect, default kept.
+SIDE_PRIORITY = int(os.environ.get("PCB_COORDS_PRIORITY", "0"))
 # Cross-check switch: BatchNorm statistics by a separate pass over z instead of the convolution epilogue.
 SEPARATE_STATS = os.environ.get("PCB_SEPARATE_STATS", "0") == "1"
 # Test hook: a list to which every ReLU unit of a training forward pass appends (rows of view 0, bool [n, C] = the ReLU decision
@@ -50,8 +52,6 @@ _READY = {}       # (data_ptr, version, numel) of a device-resident input -> eve
 
 
 def _side_stream(device):
-    """High priority: the coordinate kernels are tiny (a few CTAs, microseconds each) and queue behind convolution grids that fill every
-    SM; with equal priority they can sit until the compute stream drains, and the next step -- which waits for them -- starts late."""
     s = _SIDE.get(device.index)
     if s is None:
         s = _SIDE[device.index] = torch.cuda.Stream(device=device, priority=SIDE_PRIORITY)
