@@ -9,7 +9,7 @@ both views (stacked in one pass by default; PCB_PAIR=0: two forward calls), loss
 overlapped with the backward pass), fused SGD step.  Prints ONE JSON line (rank 0).
 
   value    : pairs/s with the batch already resident in HBM, CUDA-event timed, max over ranks.
-  e2e      : pairs/s through the public trainer call (`Trainer._train_iter`) with the batch in pinned HOST memory,
+  e2e      : pairs/s through the public trainer call (`Trainer.iter_losses`, the loop of `Trainer.train()`) with the batch in pinned HOST memory,
              host->device copies and the loss read-back inside the timed region.
   roofline : the dominant kernel (conv_tcgen05_split_kernel: sparse-conv forward / data-gradient) -- algorithmic bytes
               of all its launches in one step / their CUDA-event time (events recorded by the library
@@ -319,15 +319,15 @@ def run_ours(args):
 
     # ---- end-to-end through the public trainer call, host (pinned) batches
     it = iter(loader)
-    for _ in range(2):
-        trainer._train_iter(it, None)
+    for _ in trainer.iter_losses(it, 2):
+        pass
     sync_all()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
-        trainer._train_iter(it, None)
+    e2e_losses = list(trainer.iter_losses(it, args.steps))       # what Trainer.train() runs between two LR / checkpoint boundaries
     e1.record()
     sync_all()
+    assert len(e2e_losses) == args.steps and all(np.isfinite(np.asarray(e2e_losses, dtype=np.float64).ravel()))
     e2e_value = pairs_per_step * args.steps / (gather_max(e0.elapsed_time(e1)) / 1e3)
     h2d = int(np.mean([sum(b[k].numel() * b[k].element_size() for k in keys) for b in host_batches]))
 

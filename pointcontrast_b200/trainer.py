@@ -218,24 +218,77 @@ class ContrastiveLossTrainer:
             if "tail" in self.timing:
                 self.timing["tail"][1] = e
 
+    # -- iterations.  `ddp_trainer.py:278-326,380-440`: fetch batch -> forward both views -> loss -> backward -> step -> loss.item()
+    LOSS_NAMES = ("loss",)
+
+    def _enqueue_iter(self, data_loader_iter):
+        """Everything of one iteration that the GPU has to do, enqueued; the losses (averaged over ranks, `lib/distributed.py:260-270`)
+        travel to a pinned host slot by an asynchronous copy that is stream-ordered after THIS iteration only, with an event behind it."""
+        input_dict = self._next_batch(data_loader_iter)
+        out = self.train_step(input_dict)
+        vals = out if isinstance(out, tuple) else (out,)
+        res = scaled_all_reduce_dict(dict(zip(self.LOSS_NAMES, vals)), self.world)
+        slots = self.__dict__.setdefault("_loss_slots", [])
+        if not slots:
+            slots.extend((torch.empty(4, dtype=torch.float32).pin_memory(), torch.cuda.Event()) for _ in range(2))
+        n_done = self.__dict__.get("_loss_slot_i", 0)
+        self._loss_slot_i = n_done + 1
+        buf, ev = slots[n_done % 2]
+        dev = res[self.LOSS_NAMES[0]].float().reshape(1) if len(vals) == 1 else torch.stack([res[k].float() for k in self.LOSS_NAMES])
+        buf[:len(vals)].copy_(dev, non_blocking=True)
+        ev.record()
+        self._stage_next(data_loader_iter)
+        return buf, ev, len(vals)
+
+    @staticmethod
+    def _finish_iter(pending):
+        buf, ev, n = pending
+        ev.synchronize()
+        vals = buf[:n].tolist()
+        return vals[0] if n == 1 else tuple(vals)
+
+    def _train_iter(self, data_loader_iter, timers):
+        """One iteration; returns its loss(es) as Python floats (the reference's `_train_iter`)."""
+        return self._finish_iter(self._enqueue_iter(data_loader_iter))
+
+    def iter_losses(self, data_loader_iter, n):
+        """`n` consecutive iterations with nothing between them that needs the host (no LR change, checkpoint or validation), yielding each
+        iteration's loss(es).  Iteration i+1 is enqueued BEFORE the loss of iteration i is waited for, so the GPU never idles while the
+        host restarts the pipeline after a read-back (`_train_iter` in a loop: 5-15 % of a step, depending on the host).  When the generator
+        is exhausted exactly `n` iterations have been enqueued and read; nothing runs ahead of the last one."""
+        pending = None
+        for i in range(n):
+            cur = pending if pending is not None else self._enqueue_iter(data_loader_iter)
+            pending = self._enqueue_iter(data_loader_iter) if i + 1 < n else None
+            yield self._finish_iter(cur)
+
     def train(self):
+        """`ddp_trainer.py:240-266`.  The host acts after iteration 1 and after every `lr_update_freq`-th (LR step + checkpoint); the
+        iterations in between run through `iter_losses`."""
         curr_iter = self.curr_iter
         it = iter(self.data_loader)
-        first = curr_iter + 1
-        while curr_iter < self.config.opt.max_iter:
-            curr_iter += 1
-            out = self._train_iter(it, None)
-            if curr_iter == first:
+        max_iter, f = self.config.opt.max_iter, self.lr_update_freq
+        boundary = lambda i: i % f == 0 or i == 1
+        first = True
+        while curr_iter < max_iter:
+            n = 1
+            if not first:
+                while curr_iter + n < max_iter and not boundary(curr_iter + n):
+                    n += 1
+            for out in self.iter_losses(it, n):
+                curr_iter += 1
+                batch_loss = out[0] if isinstance(out, tuple) else out
+                if boundary(curr_iter):                      # only the last iteration of a chunk can be one
+                    lr = self.scheduler.get_last_lr()
+                    self.scheduler.step()
+                    if self.is_master:
+                        logging.info(" Iter: %d, LR: %s", curr_iter, lr)
+                        self._save_checkpoint(curr_iter, "checkpoint_" + str(curr_iter))
+                if curr_iter % self.stat_freq == 0 and self.is_master:
+                    logging.info("Train iter %d, Current Loss: %.3e, LR: %s", curr_iter, batch_loss, self.scheduler.get_last_lr())
+            if first:
                 quiesce_gc()
-            batch_loss = out[0] if isinstance(out, tuple) else out
-            if curr_iter % self.lr_update_freq == 0 or curr_iter == 1:
-                lr = self.scheduler.get_last_lr()
-                self.scheduler.step()
-                if self.is_master:
-                    logging.info(" Iter: %d, LR: %s", curr_iter, lr)
-                    self._save_checkpoint(curr_iter, "checkpoint_" + str(curr_iter))
-            if curr_iter % self.stat_freq == 0 and self.is_master:
-                logging.info("Train iter %d, Current Loss: %.3e, LR: %s", curr_iter, batch_loss, self.scheduler.get_last_lr())
+                first = False
         self.curr_iter = curr_iter
 
 
@@ -250,6 +303,7 @@ def quiesce_gc():
 
 class HardestContrastiveLossTrainer(ContrastiveLossTrainer):
     """`ddp_trainer.py:171-326`."""
+    LOSS_NAMES = ("loss", "pos_loss", "neg_loss")
 
     def contrastive_hardest_negative_loss(self, F0, F1, positive_pairs, num_pos=5192, num_hn_samples=2048, thresh=None):
         N0, N1 = F0.shape[0], F1.shape[0]
@@ -277,13 +331,6 @@ class HardestContrastiveLossTrainer(ContrastiveLossTrainer):
         self._step_timing(False)
         return loss.detach(), pos_loss.detach(), neg_loss.detach()
 
-    def _train_iter(self, data_loader_iter, timers):
-        input_dict = self._next_batch(data_loader_iter)
-        loss, pos_loss, neg_loss = self.train_step(input_dict)
-        self._stage_next(data_loader_iter)
-        result = scaled_all_reduce_dict({"loss": loss, "pos_loss": pos_loss, "neg_loss": neg_loss}, self.world)
-        return result["loss"].item(), result["pos_loss"].item(), result["neg_loss"].item()
-
 
 class PointNCELossTrainer(ContrastiveLossTrainer):
     """`ddp_trainer.py:328-440`."""
@@ -306,13 +353,6 @@ class PointNCELossTrainer(ContrastiveLossTrainer):
         self.optimizer.step()
         self._step_timing(False)
         return loss.detach()
-
-    def _train_iter(self, data_loader_iter, timers):
-        input_dict = self._next_batch(data_loader_iter)
-        loss = self.train_step(input_dict)
-        self._stage_next(data_loader_iter)
-        result = scaled_all_reduce_dict({"loss": loss}, self.world)
-        return result["loss"].item()
 
 
 def get_trainer(trainer):

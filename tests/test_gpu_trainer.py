@@ -129,3 +129,26 @@ def test_trainers_step_and_checkpoint_roundtrip(tmp_path, monkeypatch):
     th = get_trainer("HardestContrastiveLossTrainer")(default_config(["trainer.batch_size=1"]), loader)
     out = th._train_iter(iter(loader), None)
     assert len(out) == 3 and all(np.isfinite(v) for v in out) and abs(out[0] - (out[1] + out[2])) < 1e-4
+
+
+def test_pipelined_iterations_equal_one_at_a_time(tmp_path, monkeypatch):
+    """`Trainer.iter_losses(it, n)` (iteration i+1 enqueued before the loss of iteration i is read back; what `train()` runs between two
+    LR / checkpoint boundaries) returns the losses of n `_train_iter` calls on a twin trainer, and leaves the same parameters."""
+    from pointcontrast_b200.config import default_config
+    from pointcontrast_b200.data import SyntheticPairLoader
+    from pointcontrast_b200.trainer import get_trainer
+    monkeypatch.chdir(tmp_path)
+    cfg = default_config(["trainer.batch_size=1", "misc.nceT=0.4"])
+    loader = SyntheticPairLoader(1, scale=0.12, num_batches=2, pin=True)
+    outs = []
+    for mode in ("single", "pipelined"):
+        torch.manual_seed(0)
+        tr = get_trainer("PointNCELossTrainer")(cfg, loader)
+        it = iter(loader)
+        ls = [tr._train_iter(it, None) for _ in range(4)] if mode == "single" else list(tr.iter_losses(it, 4))
+        torch.cuda.synchronize()
+        outs.append((ls, tr.optimizer.flat_param.clone()))
+    (l_a, p_a), (l_b, p_b) = outs
+    assert len(l_a) == len(l_b) == 4 and all(isinstance(v, float) for v in l_b)
+    assert max(abs(a - b) / abs(a) for a, b in zip(l_a, l_b)) < 1e-5, (l_a, l_b)      # the loss's gather backward uses atomics: not bit for bit
+    assert float((p_a - p_b).norm() / p_a.norm()) < 1e-5
