@@ -6,7 +6,7 @@ This module runs the SAME graph (`pretrain/pointcontrast/model/res16unet.py:206-
 
   * unit = conv -> BatchNorm statistics -> one elementwise pass doing normalise + residual add + ReLU
     (`model/modules/resnet_block.py:44-60` collapses to two units per BasicBlock), issued by ONE C call
-    (`pcb_unit_forward`, include/pcb200.h): the BatchNorm column sums come out of the convolution's TMEM epilogue;
+    (`pcb_unit_forward`, include/pcb200.h); on the offset-split levels the convolution's reduction pass also produces the BatchNorm column sums;
   * `me.cat` is free: the two producers write straight into the column halves of one wider buffer (row strides);
   * backward is a hand-written reverse sweep, one C call per unit (`pcb_unit_backward`): ReLU mask + BatchNorm backward +
     residual-gradient fan-out in one pass, the weight gradient accumulated straight into the (flat) parameter gradient
