@@ -206,7 +206,23 @@ class ContrastiveLossTrainer:
             if self._comm is not None:
                 torch.cuda.current_stream().wait_stream(self._comm)
 
+    MAX_STEPS_IN_FLIGHT = 2
+
     def _step_timing(self, begin):
+        """Called at the start and at the end of every `train_step`.  Bounds how far the host may run ahead of the GPU: a step starts
+        being enqueued only when all but the latest MAX_STEPS_IN_FLIGHT - 1 earlier ones have finished.  A caller that never reads a
+        loss back (`bench.py`'s device-resident loop) otherwise queues several steps' worth of launches and side-stream allocations,
+        and a rank's occasional host hiccup then shows up as a 45-70 ms step on all ranks through the all-reduce (8 GPUs, run 17)."""
+        q = self.__dict__.setdefault("_steps_in_flight", [])
+        if begin:
+            while len(q) >= self.MAX_STEPS_IN_FLIGHT:
+                q.pop(0).synchronize()
+        else:
+            pool = self.__dict__.setdefault("_step_events", [torch.cuda.Event() for _ in range(self.MAX_STEPS_IN_FLIGHT + 1)])
+            e = pool[self.__dict__.get("_step_event_i", 0) % len(pool)]
+            self._step_event_i = self.__dict__.get("_step_event_i", 0) + 1
+            e.record()
+            q.append(e)
         if self.timing is None:
             return
         e = torch.cuda.Event(enable_timing=True)
