@@ -8,9 +8,10 @@ One "step" = one full training iteration on one batch of synthetic scene pairs p
 both views (stacked in one pass by default; PCB_PAIR=0: two forward calls), loss, backward, gradient all-reduce (N > 1,
 overlapped with the backward pass), fused SGD step.  Prints ONE JSON line (rank 0).
 
-  value    : pairs/s with the batch already resident in HBM, CUDA-event timed, max over ranks.
-  e2e      : pairs/s through the public trainer call (`Trainer.iter_losses`, the loop of `Trainer.train()`) with the batch in pinned HOST memory,
-             host->device copies and the loss read-back inside the timed region.
+  value    : pairs/s with the batches already resident in HBM, through the trainer's own loop (`Trainer.iter_losses`, what
+             `Trainer.train()` runs: the next batch staged and enqueued while the current one runs, every loss read back), CUDA-event
+             timed over all K steps, max over ranks.
+  e2e      : the same loop with the batches in pinned HOST memory: host->device copies and the loss read-back inside the timed region.
   roofline : the dominant kernel (conv_tcgen05_split_kernel: sparse-conv forward / data-gradient) -- algorithmic bytes
               of all its launches in one step / their CUDA-event time (events recorded by the library
              around every launch, `pcb_profile_enable`), vs the measured HBM peak.
@@ -292,26 +293,30 @@ def run_ours(args):
     # (the nvidia-smi sampler is started BEFORE the warm-up: its start-up -- process spawn, NVML / driver initialisation -- otherwise opens
     #  an idle gap right before the timed region, the SM clocks drop, and the first timed steps take 60-90 ms while they ramp up again)
     clocks = Clocks(local) if rank == 0 else None
-    for i in range(args.warmup):
-        trainer.train_step(dev_batches[i % len(dev_batches)])
+    # The timed loop is the trainer's own loop (`Trainer.iter_losses`: batch i+1 staged and enqueued while batch i runs, every loss read
+    # back) over DEVICE-resident batches.  Calling `train_step(batch)` back to back instead builds each batch's coordinate manager inline
+    # and never reads a loss: at 8 ranks that loop showed 3-4 steps of 45-80 ms among the first ten (all ranks wait in the all-reduce
+    # for one late rank), the trainer's loop none in 60 (profiles/r2_results.md, runs 17 / 23).
+    import itertools
+    it_dev = itertools.cycle(dev_batches)
+    for _ in trainer.iter_losses(it_dev, args.warmup):
+        pass
     sync_all()
     from pointcontrast_b200.trainer import quiesce_gc
     quiesce_gc()                       # what Trainer.train() does after its first iteration
     l0 = _lib.launch_count()
-    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.time()
-    evs[0].record()
-    host_enq = []
-    for i in range(args.steps):
-        t_h = time.perf_counter()
-        loss = trainer.train_step(dev_batches[i % len(dev_batches)])
-        evs[i + 1].record()
-        host_enq.append((time.perf_counter() - t_h) * 1e3)
+    ev0.record()
+    arrivals = [time.perf_counter()]
+    for loss in trainer.iter_losses(it_dev, args.steps):
+        arrivals.append(time.perf_counter())         # the loss of a step arrives when the step has finished on the GPU
+    ev1.record()
     sync_all()
     t_wall1 = time.time()
     launches = _lib.launch_count() - l0
-    ms_total = gather_max(evs[0].elapsed_time(evs[-1]))
-    per_step = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
+    ms_total = gather_max(ev0.elapsed_time(ev1))
+    per_step = [(b - a) * 1e3 for a, b in zip(arrivals[:-1], arrivals[1:])]
     host_ms_per_step = (t_wall1 - t_wall0) * 1e3 / args.steps
     clk = clocks.stop(t_wall0, t_wall1) if clocks else None
     pairs_per_step = wl["batch"] * world
@@ -334,8 +339,10 @@ def run_ours(args):
     # ---- per-rank breakdown of one step (N > 1): own compute vs waiting in / for the gradient all-reduce
     ranks = None
     if world > 1:
+        staged = trainer.prepare(dev_batches[0])
+        torch.cuda.synchronize()
         trainer.timing = {}
-        trainer.train_step(dev_batches[0])
+        trainer.train_step(staged)
         torch.cuda.synchronize()
         tm = trainer.timing
         mine = torch.tensor([tm["total"][0].elapsed_time(tm["total"][1]),
@@ -410,7 +417,7 @@ def run_ours(args):
                             "per_step_ms": {"median": float(np.median(per_step)), "min": float(np.min(per_step)), "max": float(np.max(per_step)),
                                             "p90": float(np.percentile(per_step, 90))},
                             "per_step_ms_list": [round(t, 2) for t in per_step],
-                            "host_enqueue_ms_per_step": {"median": float(np.median(host_enq)), "max": float(np.max(host_enq))},
+                            "per_step_note": "host arrival times of the per-step loss read-backs; ms_per_step / value from CUDA events around all steps",
                             "host_ms_per_step": host_ms_per_step, "launches_per_step": launches / args.steps, "ranks": ranks},
                 "clocks": clk, "gpu_launches": int(launches),
                 "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
