@@ -519,7 +519,8 @@ class Runner:
             out = Buf(out_t, out_t.data_ptr(), n[0], fin.out_channels, fin.out_channels, dev)
             self._conv(x, p1[0].fwd_tbl, None, fin, False, n[0], out, False,
                        bias=fin.bias.detach().reshape(-1) if fin.bias is not None else None, plan=p1[0])
-            torch._foreach_add_([bn.num_batches_tracked for bn in self.bns], g.calls)       # one multi-tensor launch, not 62
+            if self.bns:
+                torch._foreach_add_([bn.num_batches_tracked for bn in self.bns], g.calls)       # one multi-tensor launch, not 62
         self._fwd_hint = _grow_hint(self._fwd_hint, arena.total)
         if eval_mode:
             self.units = self.arena = self.stats = None

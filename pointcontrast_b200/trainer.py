@@ -253,6 +253,10 @@ class ContrastiveLossTrainer:
         dev = res[self.LOSS_NAMES[0]].float().reshape(1) if len(vals) == 1 else torch.stack([res[k].float() for k in self.LOSS_NAMES])
         buf[:len(vals)].copy_(dev, non_blocking=True)
         ev.record()
+        log = self.__dict__.get("step_end_events")          # bench.py: a list -> one timing event per iteration boundary
+        if log is not None:
+            log.append(torch.cuda.Event(enable_timing=True))
+            log[-1].record()
         self._stage_next(data_loader_iter)
         return buf, ev, len(vals)
 
