@@ -163,3 +163,44 @@ def test_scannet_pair_formats_and_samplers(tmp_path):
     # two ranks partition each permutation pass
     a, c = SP.DistributedInfSampler(10, 2, 0, shuffle=False), SP.DistributedInfSampler(10, 2, 1, shuffle=False)
     assert [next(a) for _ in range(5)] == [0, 2, 4, 6, 8] and [next(c) for _ in range(5)] == [1, 3, 5, 7, 9]
+
+
+def test_train_loop_chunks_and_pipelining_host_logic(monkeypatch):
+    """`Trainer.train()` host logic without a GPU: the iterations between two LR / checkpoint boundaries (iteration 1 and every
+    `lr_update_freq`-th, `ddp_trainer.py:258-263`) run through `iter_losses`, which enqueues iteration i+1 before it waits for the loss
+    of iteration i and never runs ahead of the last iteration of a chunk."""
+    import types
+    from pointcontrast_b200 import trainer as T
+    monkeypatch.setattr(T, "quiesce_gc", lambda: None)
+    log = []
+
+    class Sched:
+        def get_last_lr(self):
+            return [0.1]
+
+        def step(self):
+            log.append("lr")
+
+    tr = object.__new__(T.PointNCELossTrainer)
+    tr.curr_iter, tr.data_loader, tr.lr_update_freq, tr.stat_freq, tr.is_master = 0, [None], 3, 1000, True
+    tr.config = types.SimpleNamespace(opt=types.SimpleNamespace(max_iter=7))
+    tr.scheduler = Sched()
+    count = [0]
+
+    def enqueue(it):
+        count[0] += 1
+        log.append(f"e{count[0]}")
+        return count[0]
+
+    tr._enqueue_iter = enqueue
+    tr._finish_iter = lambda pending: log.append(f"f{pending}") or float(pending)
+    tr._save_checkpoint = lambda i, name: log.append(f"ckpt{i}")
+    tr.train()
+    assert tr.curr_iter == 7 and count[0] == 7
+    assert log == ["e1", "f1", "lr", "ckpt1",                                 # first iteration alone (boundary: iteration 1)
+                   "e2", "e3", "f2", "f3", "lr", "ckpt3",                     # 2..3: iteration 3 enqueued before loss 2 is read
+                   "e4", "e5", "f4", "e6", "f5", "f6", "lr", "ckpt6",        # 4..6
+                   "e7", "f7"], log                                           # 7 = max_iter, not a boundary
+    # the single-iteration entry point of the reference
+    log.clear()
+    assert tr._train_iter(iter([None]), None) == 8.0 and log == ["e8", "f8"]
