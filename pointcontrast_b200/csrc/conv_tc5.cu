@@ -9,8 +9,9 @@
 //       M = 128, N = BN, fp32 accumulate in TMEM; tcgen05.commit -> mbarrier releases the smem stage (3-stage ring);
 //   epilogue: tcgen05.ld 32x32b -> registers -> 64-byte contiguous stores per thread.
 //
-// Same arguments, kernel-offset skipping and split-reduce mode as conv_mma_kernel; results agree with it to fp32
-// rounding (same 3-term bf16 split, fp32 accumulation).
+// This first kernel (conv_tcgen05_kernel) takes fp32 rows and serves the modular per-operator surface; the training / inference
+// executor runs conv_tcgen05_split_kernel below on operands that already are 16-bit hi/lo planes.  Both skip kernel offsets without a
+// neighbour in the tile and have an offset-split mode (partial planes + fixed-order reduce) for levels with few rows.
 #include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
@@ -279,13 +280,14 @@ __global__ void __launch_bounds__(NTHR, 2) conv_tcgen05_kernel(const Args p) {
 }
 
 
-// ------------------------------------------------------------------------------------------------ split-operand forward, deep pipeline
-// Warp-specialised: warps 0-7 are copy producers (cp.async of the gathered hi/lo rows + the weight tile, DEPTH stages in
-// flight, never blocked by MMA issue), warp 8 issues the tcgen05.mma's.  Hand-off through mbarriers only:
-//   full[s]  : 256 producer arrivals (each after its own copies of stage s have landed + fence.proxy.async)
+// ------------------------------------------------------------------------------------------------ split-operand forward / data gradient
+// Warp-specialised: warps 0-7 are producers (the gathered hi/lo row segments: 128-bit loads three stages ahead in registers -> 128-bit
+// st.shared; thread 0 also launches the stage's weight tile as one TMA bulk copy), warp 8 issues the tcgen05.mma's.  Hand-off through
+// mbarriers only:
+//   full[s]  : one arrival per producer warp (release, after its stores of stage s) + the weight tile's transaction bytes
 //   empty[s] : tcgen05.commit of the MMAs that read stage s
-// One CTA per SM (the 6-stage ring fills the shared memory), accumulators in TMEM, same epilogue as above.
-constexpr int DEPTH = 4;
+// The generic -> async proxy fence of a stage is issued by the MMA thread after its acquire (consumer_fence() below).  Two CTAs per SM
+// with a 3-slot ring each, accumulators in TMEM, same epilogue as above.
 
 template <int BN, int DNS>
 struct DSmem {
