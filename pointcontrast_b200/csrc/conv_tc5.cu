@@ -609,12 +609,13 @@ int wgrad_group() {
 // ------------------------------------------------------------------------------------------------ weight gradient
 // dW[k] (Ca x Cb) = sum_j A[tbl[k][j], :]^T . B[j, :] on split (bf16 hi/lo) operands.
 // UMMA view: D_k[M = Ca-block (padded to 128)][N = Cb-block] += A_k[M x 16 rows] . B[16 rows x N]; both operands MN-major
-// (a matrix row is contiguous along channels): core matrix = 8 rows (K) x 16 B (8 channels), channel-chunk stride 128 B,
+// (a matrix row is contiguous along channels): core matrix = 8 rows (K) x 16 B (8 channels), channel-chunk stride SBO = 144 B,
 // 8-row-group stride LBO.
-// A CTA owns a GROUP of up to 4 kernel offsets and a range of table rows: the row-aligned operand B is staged ONCE per
-// 16-row step and shared by the 4 gathered operands A_k, each accumulating into its own TMEM accumulator (4 x TN columns).
-// 16 producer warps (thread = one row, one 16-byte channel chunk, two of the four offsets, both planes; table entries prefetched one step ahead of
-// the 128-bit data loads, which are two steps ahead of the 128-bit shared stores) + 1 MMA-issuer warp, one CTA per SM.
+// A CTA owns a GROUP of GK kernel offsets (2 by default, 4 optional) and a range of table rows: the row-aligned operand B is staged ONCE
+// per 16-row step and shared by the GK gathered operands A_k, each accumulating into its own TMEM accumulator (GK x TN columns).
+// Producer warps (thread = one row, one 16-byte channel chunk, two offsets, both planes; table entries prefetched three steps ahead of
+// the 128-bit data loads, which are two steps ahead of the 128-bit shared stores) + 1 MMA-issuer warp; GK = 2: 8 producer warps, two
+// CTAs per SM; GK = 4: 16 producer warps, one CTA per SM.
 // grid: x = groups * mblocks * nblocks, y = row splits; partial tiles are reduced by wgrad_reduce_kernel (conv.cu).
 namespace wg {
 
