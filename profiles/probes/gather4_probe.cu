@@ -55,14 +55,21 @@ __global__ void layout_kernel(const __grid_constant__ CUtensorMap tm, __half* ou
 
 // Every CTA: `stages` stages of `rps` rows (rps / 4 gather4's of 64 bytes per row) into a 3-slot ring; one thread issues, waits for the
 // slot's barrier before reusing it (the consumer is absent: this is the producer-side ceiling).
-__global__ void rate_kernel(const __grid_constant__ CUtensorMap tm, const int* __restrict__ rows, int n_rows_list, int rps, int stages, int* sink) {
+// NOTE on the round-2 run (profiles/reports/r2c27_gather4_probe.txt, 0.54-0.62 TB/s): that version read the four row indices of every
+// gather4 from GLOBAL memory inside the issue loop, so the figure is bounded by that load's latency, not by the TMA unit.  The indices
+// are now staged in shared memory first (as a convolution kernel would have them); re-run before drawing a conclusion on the rate.
+constexpr int IDX_SMEM = 4096;
+__global__ void rate_kernel(const __grid_constant__ CUtensorMap tm, const int* __restrict__ rows_g, int n_rows_list, int rps, int stages, int* sink) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ __align__(8) uint64_t bar[3];
+  __shared__ int rows[IDX_SMEM];
   const int slot_bytes = rps * BOXC * 2;
+  for (int i = threadIdx.x; i < IDX_SMEM; i += blockDim.x) rows[i] = rows_g[((blockIdx.x * 977) % (n_rows_list - IDX_SMEM)) + i];
+  n_rows_list = IDX_SMEM;
   if (threadIdx.x == 0) { for (int i = 0; i < 3; ++i) mbar_init(smem_u32(&bar[i]), 1); asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
   __syncthreads();
   if (threadIdx.x == 0) {
-    int base = (blockIdx.x * 977) % (n_rows_list - rps);
+    int base = 0;
     for (int s = 0; s < stages; ++s) {
       const int slot = s % 3;
       if (s >= 3) mbar_wait(smem_u32(&bar[slot]), ((s / 3) - 1) & 1);
