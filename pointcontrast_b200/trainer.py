@@ -218,7 +218,9 @@ class ContrastiveLossTrainer:
             while len(q) >= self.MAX_STEPS_IN_FLIGHT:
                 q.pop(0).synchronize()
         else:
-            pool = self.__dict__.setdefault("_step_events", [torch.cuda.Event() for _ in range(self.MAX_STEPS_IN_FLIGHT + 1)])
+            pool = self.__dict__.get("_step_events")
+            if pool is None:
+                pool = self._step_events = [torch.cuda.Event() for _ in range(self.MAX_STEPS_IN_FLIGHT + 1)]
             e = pool[self.__dict__.get("_step_event_i", 0) % len(pool)]
             self._step_event_i = self.__dict__.get("_step_event_i", 0) + 1
             e.record()

@@ -204,3 +204,44 @@ def test_train_loop_chunks_and_pipelining_host_logic(monkeypatch):
     # the single-iteration entry point of the reference
     log.clear()
     assert tr._train_iter(iter([None]), None) == 8.0 and log == ["e8", "f8"]
+
+
+def test_arena_hint_and_step_throttle_host_logic():
+    """Two small pieces of host logic behind the timed step: the arena size hint only grows, in 64 MiB steps (so the caching allocator sees
+    one block size per pass); at most `MAX_STEPS_IN_FLIGHT` training steps are enqueued and unfinished."""
+    import types
+    import torch
+    from pointcontrast_b200 import fused, trainer as T
+    step = 64 << 20
+    h = 0
+    for used in (10 << 20, 100 << 20, 90 << 20, 129 << 20, 1 << 20):
+        nh = fused._grow_hint(h, used)
+        assert nh >= h and nh % step == 0 and nh >= used
+        h = nh
+    assert h == 3 * step
+
+    synced, made = [], []
+
+    class Ev:
+        def __init__(self):
+            made.append(self)
+
+        def record(self):
+            self.rec = getattr(self, "rec", 0) + 1
+
+        def synchronize(self):
+            synced.append(self)
+
+    tr = object.__new__(T.PointNCELossTrainer)
+    tr.timing = None
+    orig = torch.cuda.Event
+    torch.cuda.Event = Ev
+    try:
+        for _ in range(5):
+            tr._step_timing(True)
+            tr._step_timing(False)
+    finally:
+        torch.cuda.Event = orig
+    assert len(made) == T.ContrastiveLossTrainer.MAX_STEPS_IN_FLIGHT + 1          # a fixed pool, reused
+    assert len(tr._steps_in_flight) == T.ContrastiveLossTrainer.MAX_STEPS_IN_FLIGHT
+    assert len(synced) == 3                                                        # steps 3, 4, 5 each waited for the step two before
